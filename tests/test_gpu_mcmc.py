@@ -1,0 +1,135 @@
+"""GPU parity of the device-resident DRAM sampler, through the C ABI, against the CPU oracle.
+
+mcmcstat records no proposals and the reference sets no RNG seed, so
+"replaying the reference's recorded proposals" is realised as: the SAME randomness (z1,u1,z2,u2,
+chi2 per step) is fed to the oracle's DRAM restatement and to the GPU kernel; accept/reject flags
+must be identical and the chains equal to rounding."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(gpu_cells, chain_cell, seed):
+    from transcriptioncycleinference_b200 import setup_cell
+    rng = np.random.default_rng(seed)
+    return setup_cell.chain_inputs(gpu_cells, chain_cell, rng)
+
+
+def _streams(nch, nsimu, ld, N_of_chain, seed):
+    g = np.random.default_rng(seed)
+    st = dict(z1=g.standard_normal((nch, nsimu, ld)), u1=g.random((nch, nsimu)),
+              z2=g.standard_normal((nch, nsimu, ld)), u2=g.random((nch, nsimu)),
+              chi2=np.zeros((nch, nsimu)))
+    for i, N in enumerate(N_of_chain):
+        st["chi2"][i] = g.chisquare(1 + 2 * N, nsimu)
+    return st
+
+
+def _oracle_chain(orc, cells_npz, c, opts_kw, inputs, i, streams=None):
+    co, cons = orc
+    N = int(cells_npz["N"][c]); o = int(cells_npz["off"][c]); npar = 7 + N
+    t, ms2, pp7 = (cells_npz[k][o:o + N] for k in ("t", "ms2", "pp7"))
+    th0, q, lo, hi, mu, sg = (x[i, :npar] for x in inputs)
+    st = None
+    if streams is not None:
+        st = dict(z1=streams["z1"][i][:, :npar], u1=streams["u1"][i], z2=streams["z2"][i][:, :npar],
+                  u2=streams["u2"][i], chi2=streams["chi2"][i])
+    opts = co.default_opts(opts_kw["nsimu"], opts_kw["burnintime"])
+    return co.dram(cons, t, ms2, pp7, opts, th0, q, lo, hi, mu, sg, streams=st)
+
+
+@pytest.mark.parametrize("algo", [1, 0])
+def test_replay_accept_reject_identical(gpu_cells, cells_npz, orc, algo):
+    """600 steps with burn-in 300: covers burn-in, the first covariance adaptation (Cholesky of
+    the 300-row covariance) and three later ones."""
+    from transcriptioncycleinference_b200 import _lib
+    chain_cell = np.array([0, 5, 77, 150, 298, 42], dtype=np.int32)
+    nsimu, burn = 600, 300
+    inputs = _setup(gpu_cells, chain_cell, 11)
+    st = _streams(len(chain_cell), nsimu, gpu_cells.ld, cells_npz["N"][chain_cell], 12)
+    opts = _lib.default_opts(nsimu=nsimu, burnintime=burn, n_burn=1, store_chain=1, replay=1, algo=algo)
+    out = gpu_cells.mcmc_run(opts, chain_cell, *inputs, replay=st, want_flags=True)
+    for i, c in enumerate(chain_cell):
+        ref = _oracle_chain(orc, cells_npz, int(c), dict(nsimu=nsimu, burnintime=burn), inputs, i, st)
+        npar = 7 + int(cells_npz["N"][c])
+        assert np.array_equal(out["flags"][i], ref["flags"]), "accept/reject sequence differs (chain %d)" % i
+        np.testing.assert_allclose(out["sschain"][i], ref["sschain"], rtol=1e-9)
+        np.testing.assert_allclose(out["chain"][i][:, :npar], ref["chain"], rtol=0, atol=1e-7)
+        np.testing.assert_allclose(out["s2chain"][i], ref["s2chain"], rtol=1e-9)
+        cnt = out["counters"][i]
+        assert cnt[_lib.CNT_SS_EVALS] == ref["counters"][0]
+        assert cnt[_lib.CNT_ACC_STAGE1] == ref["counters"][1]
+        assert cnt[_lib.CNT_ACC_STAGE2] == ref["counters"][2]
+        assert cnt[_lib.CNT_ADAPTATIONS] == ref["counters"][4] == 4
+        # summaries = mean / population std of the stored rows (TranscriptionCycleMCMC.m:286-303)
+        np.testing.assert_allclose(out["mean"][i][:npar], ref["chain"].mean(axis=0), rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(out["std"][i][:npar], ref["chain"].std(axis=0), rtol=1e-6, atol=1e-9)
+        np.testing.assert_allclose(out["sig"][i][0], np.sqrt(ref["s2chain"].mean()), rtol=1e-9)
+        np.testing.assert_allclose(out["sig"][i][1], np.sqrt(ref["s2chain"]).std(), rtol=1e-8)
+
+
+def test_production_rng_equals_replay_of_its_own_dump(gpu_cells, cells_npz, orc):
+    """Philox path: dump the device's streams for (seed, uid), feed them to the ORACLE, compare with
+    the production (non-replay) run."""
+    from transcriptioncycleinference_b200 import _lib
+    chain_cell = np.array([3, 200], dtype=np.int32)
+    uid = np.array([1000003, 77], dtype=np.uint64)
+    nsimu, burn, seed = 400, 200, 987654321
+    inputs = _setup(gpu_cells, chain_cell, 21)
+    opts = _lib.default_opts(nsimu=nsimu, burnintime=burn, n_burn=1, store_chain=1, seed=seed)
+    out = gpu_cells.mcmc_run(opts, chain_cell, *inputs, chain_uid=uid, want_flags=True)
+    for i, c in enumerate(chain_cell):
+        N = int(cells_npz["N"][c]); npar = 7 + N
+        d = _lib.rng_dump(seed, int(uid[i]), npar, 1 + 2 * N, nsimu)
+        # sanity of the streams themselves
+        assert abs(d["z1"][1:].mean()) < 0.02 and abs(d["z1"][1:].std() - 1) < 0.02
+        assert 0 < d["u1"].min() and d["u1"].max() < 1
+        assert abs(d["chi2"][1:].mean() / (1 + 2 * N) - 1) < 0.02
+        st = {k: v[None] for k, v in d.items()}
+        pad = np.zeros((1, nsimu, gpu_cells.ld)); pad[0, :, :npar] = d["z1"]; st["z1"] = pad
+        pad = np.zeros((1, nsimu, gpu_cells.ld)); pad[0, :, :npar] = d["z2"]; st["z2"] = pad
+        ref = _oracle_chain(orc, cells_npz, int(c), dict(nsimu=nsimu, burnintime=burn),
+                            [x[i:i + 1] for x in inputs], 0, st)
+        assert np.array_equal(out["flags"][i], ref["flags"])
+        np.testing.assert_allclose(out["chain"][i][:, :npar], ref["chain"], rtol=0, atol=1e-7)
+
+
+def test_results_independent_of_partition(gpu_cells):
+    """Philox draws are keyed by (seed, chain_uid): running a chain alone or inside a larger batch
+    gives bit-identical output (this is what makes the output independent of the GPU count)."""
+    from transcriptioncycleinference_b200 import _lib
+    cc = np.array([10, 20, 30, 40], dtype=np.int32)
+    uid = np.array([10, 20, 30, 40], dtype=np.uint64)
+    inputs = _setup(gpu_cells, cc, 31)
+    opts = _lib.default_opts(nsimu=300, burnintime=100, n_burn=50)
+    full = gpu_cells.mcmc_run(opts, cc, *inputs, chain_uid=uid)
+    sub = gpu_cells.mcmc_run(opts, cc[2:3], *[x[2:3] for x in inputs], chain_uid=uid[2:3])
+    assert np.array_equal(full["mean"][2], sub["mean"][0])
+    assert np.array_equal(full["sig"][2], sub["sig"][0])
+
+
+def test_chain_layout_and_bounds(gpu_cells, cells_npz):
+    """Row 1 = x0, s2chain(1) = sigma2_0 = 1, n_steps - n_burn + 1 stored rows, samples inside the
+    bounds."""
+    from transcriptioncycleinference_b200 import _lib
+    cc = np.arange(0, 299, 23, dtype=np.int32)
+    inputs = _setup(gpu_cells, cc, 41)
+    th0, q, lo, hi, mu, sg = inputs
+    opts = _lib.default_opts(nsimu=500, burnintime=200, n_burn=200, store_chain=1)
+    out = gpu_cells.mcmc_run(opts, cc, *inputs)
+    assert out["chain"].shape == (len(cc), 301, gpu_cells.ld)
+    assert np.all(out["s2chain"][:, 0] == 1.0)
+    for i, c in enumerate(cc):
+        npar = 7 + int(cells_npz["N"][c])
+        ch = out["chain"][i][:, :npar]
+        assert np.all(ch >= lo[i, :npar]) and np.all(ch <= hi[i, :npar])
+        np.testing.assert_allclose(out["mean"][i][:npar], ch.mean(axis=0), rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(out["std"][i][:npar], ch.std(axis=0), rtol=1e-8, atol=1e-10)
+    opts1 = _lib.default_opts(nsimu=50, burnintime=10, n_burn=1, store_chain=1)
+    out1 = gpu_cells.mcmc_run(opts1, cc, *inputs)
+    for i, c in enumerate(cc):
+        npar = 7 + int(cells_npz["N"][c])
+        assert np.array_equal(out1["chain"][i][0, :npar], th0[i, :npar])
+    acc = out["counters"][:, _lib.CNT_ACC_STAGE1] + out["counters"][:, _lib.CNT_ACC_STAGE2]
+    assert np.all(acc > 0)

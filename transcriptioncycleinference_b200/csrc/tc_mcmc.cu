@@ -1,0 +1,1068 @@
+// tc_mcmc.cu — kernels and C ABI of libtcmcmc.so (sm_100a).  See include/tcmcmc.h for the boundary
+// and DESIGN.md for the data layout and roofline of each kernel.
+//
+//   ss_batch_kernel   one CTA per (cell, theta): the batched ssfun
+//                     (replaces src/SumofSquaresFunction_TranscriptionCycleMCMC.m:1-65)
+//   forward_kernel    model curves for the best-fit plots (src/TranscriptionCycleMCMC.m:307-309)
+//   dram_kernel       one CTA per chain, the whole mcmcrun DRAM loop device-resident
+//                     (replaces the call at src/TranscriptionCycleMCMC.m:273 + summaries :276-303)
+//   rng_dump_kernel   the Philox streams of a chain, for the parity harness
+//   dfma_peak_kernel  FP64 pipe micro-benchmark (roofline denominator)
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "tc_device.cuh"
+
+using namespace tc;
+
+// ------------------------------------------------------------------------------------ utilities
+static thread_local std::string g_err;
+static thread_local double g_last_kernel_s = 0.0;
+
+static int fail(int code, const std::string &msg)
+{
+    g_err = msg;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                        \
+    do {                                                                                      \
+        cudaError_t e__ = (expr);                                                             \
+        if (e__ != cudaSuccess)                                                               \
+            return fail(TC_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));       \
+    } while (0)
+
+#define DRAM_THREADS 128
+#define SS_THREADS 128
+#define COV_RC 8          // rows of the chain block staged per pass of the scatter update
+
+// packed upper-triangular row-major index of (i, j), j >= i
+__host__ __device__ __forceinline__ int pidx(int n, int i, int j) { return i * n - (i * (i - 1)) / 2 + (j - i); }
+
+// --------------------------------------------------------------------------------- SS / forward
+struct SsArgs {
+    CellsDev cells;
+    tc_construct cons;
+    long long nbatch;
+    const int *cell_id;
+    const double *theta;
+    int ld, algo, raw_grid, ldo;
+    double *ss_out, *out1, *out2;
+};
+
+__global__ void __launch_bounds__(SS_THREADS) ss_batch_kernel(const __grid_constant__ SsArgs a)
+{
+    extern __shared__ __align__(16) double smem[];
+    for (long long b = blockIdx.x; b < a.nbatch; b += gridDim.x) {
+        const int cid = a.cell_id[b];
+        const int N = a.cells.N[cid];
+        double *p = smem;
+        CellView cv;
+        Work w;
+        carve_cell(p, N, cv);
+        carve_work(p, N, w);
+        double *th = p;                                   // [7+N]
+        __syncthreads();                                  // previous iteration done with smem
+        load_cell(a.cells, cid, a.raw_grid != 0, cv);
+        for (int i = threadIdx.x; i < 7 + N; i += blockDim.x) th[i] = a.theta[b * a.ld + i];
+        __syncthreads();
+        double *o1 = a.out1 ? a.out1 + b * a.ldo : nullptr;
+        double *o2 = a.out2 ? a.out2 + b * a.ldo : nullptr;
+        const double ss = ss_eval(a.cons, cv, th, w, a.algo, false, o1, o2);
+        if (threadIdx.x == 0 && a.ss_out) a.ss_out[b] = ss;
+    }
+}
+
+// ------------------------------------------------------------------------------------- sampler
+struct RunArgs {
+    CellsDev cells;
+    tc_construct cons;
+    // options
+    int nsimu, burnintime, adaptint, ntry, updatesigma, burnin_cumulative, n_burn, store_chain, replay,
+        algo;
+    double drscale, adascale, qcovadj, burnin_scale, N0, S20, sigma2_0;
+    unsigned long long seed;
+    // chains
+    int nchains, ld, r_in_smem, ldR, do_cov;
+    const int *chain_cell;
+    const unsigned long long *chain_uid;
+    const double *theta0, *qcov_diag, *low, *upp, *pmu, *psig;
+    double *mean, *std, *sig;
+    long long *counters;
+    double *chain, *s2chain;
+    const double *z1, *u1, *z2, *u2, *chi2;
+    int *flags;
+    double *sschain;
+    // scratch (global)
+    double *gR, *gRw, *gM2, *gRows, *gCmean;
+};
+
+struct ChainSmem {
+    double *x, *y1, *y2, *zz, *lo, *hi, *pmu, *pinv, *wmean, *wM2, *rdiag, *mb, *dm, *chunk, *R;
+};
+
+__host__ __device__ inline int chain_doubles(int npar, int npad) { return 13 * npar + npar + COV_RC * npad + 8; }
+
+// in-place upper Cholesky of the packed matrix in Rw (R'R = A); returns false when not PD.
+__device__ bool chol_packed(int n, double *Rw, double *s_piv)
+{
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int j = 0; j < n; ++j) {
+        const int rj = pidx(n, j, j);
+        // left-looking: s(j,i) = A(j,i) - sum_{k<j} R(k,j) R(k,i), i >= j
+        for (int i = j + tid; i < n; i += nt) {
+            double s = Rw[rj + (i - j)];
+            int rk = 0;                                   // start of packed row k
+            for (int k = 0; k < j; ++k) {
+                s = fma(-Rw[rk + (j - k)], Rw[rk + (i - k)], s);
+                rk += n - k;
+            }
+            Rw[rj + (i - j)] = s;
+            if (i == j) *s_piv = s;
+        }
+        __syncthreads();
+        const double piv = *s_piv;
+        if (!(piv > 0.0)) return false;                   // uniform: every thread reads the same value
+        const double rjj = sqrt(piv);
+        for (int i = j + tid; i < n; i += nt) {
+            const double s = Rw[rj + (i - j)];
+            Rw[rj + (i - j)] = (i == j) ? rjj : s / rjj;
+        }
+        __syncthreads();
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(DRAM_THREADS) dram_kernel(const __grid_constant__ RunArgs a)
+{
+    extern __shared__ __align__(16) double smem[];
+    __shared__ double s_sc[8];
+    __shared__ int s_dec[2];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int ch = blockIdx.x;
+    if (ch >= a.nchains) return;
+    const int cid = a.chain_cell[ch];
+    const int N = a.cells.N[cid];
+    const int npar = 7 + N, npad = (npar + 3) & ~3, ld = a.ld;
+    const unsigned long long uid = a.chain_uid ? a.chain_uid[ch] : (unsigned long long)ch;
+    const int npk = npar * (npar + 1) / 2;
+
+    double *p = smem;
+    CellView cv;
+    Work w;
+    ChainSmem cs;
+    carve_cell(p, N, cv);
+    carve_work(p, N, w);
+    cs.x = p; p += npar;   cs.y1 = p; p += npar;   cs.y2 = p; p += npar;
+    cs.zz = p; p += 2 * npar;
+    cs.lo = p; p += npar;  cs.hi = p; p += npar;   cs.pmu = p; p += npar;  cs.pinv = p; p += npar;
+    cs.wmean = p; p += npar; cs.wM2 = p; p += npar; cs.rdiag = p; p += npar;
+    cs.mb = p; p += npar;  cs.dm = p; p += npar;
+    p += ((p - smem) & 1);                                 // 16-byte align the chunk
+    cs.chunk = p; p += COV_RC * npad;
+    cs.R = a.r_in_smem ? p : a.gRw + (size_t)ch * a.ldR;
+    double *gRb = a.gR + (size_t)ch * a.ldR;               // R backup (restored on a failed Cholesky)
+    double *gM2 = a.gM2 ? a.gM2 + (size_t)ch * a.ldR : nullptr;
+    double *gRows = a.gRows ? a.gRows + (size_t)ch * (size_t)a.adaptint * ld : nullptr;
+
+    load_cell(a.cells, cid, false, cv);
+    const double adascale = a.adascale > 0.0 ? a.adascale : 2.4 / sqrt((double)npar);
+    for (int i = tid; i < npar; i += nt) {
+        const size_t g = (size_t)ch * ld + i;
+        cs.x[i] = a.theta0[g];
+        cs.lo[i] = a.low[g];
+        cs.hi[i] = a.upp[g];
+        cs.pmu[i] = a.pmu[g];
+        const double sg = a.psig[g];
+        cs.pinv[i] = isinf(sg) ? 0.0 : 1.0 / sg;
+        cs.rdiag[i] = sqrt(a.qcov_diag[g]);                // chol(diag(J0))
+        cs.wmean[i] = 0.0;
+        cs.wM2[i] = 0.0;
+    }
+    __syncthreads();
+
+    // ---- state
+    bool r_diag = true;
+    double cov_n = 0.0;                                    // rows folded into (cmean, M2) so far
+    double *cmean = a.gCmean ? a.gCmean + (size_t)ch * ld : nullptr;
+    if (a.do_cov) {
+        for (int i = tid; i < npk; i += nt) gM2[i] = 0.0;
+        for (int i = tid; i < npar; i += nt) cmean[i] = 0.0;
+    }
+    double ss = ss_eval(a.cons, cv, cs.x, w, a.algo, false, nullptr, nullptr);
+    double pri;
+    {
+        double s = 0.0, d0 = 0.0;
+        for (int i = tid; i < npar; i += nt) { const double e = (cs.x[i] - cs.pmu[i]) * cs.pinv[i]; s += e * e; }
+        block_sum2(s, d0, w.red);
+        pri = s;
+    }
+    double sigma2 = a.sigma2_0;
+    long long n_ss = 1, n_acc1 = 0, n_acc2 = 0, n_oob = 0, n_adapt = 0, n_cholfail = 0, n_dr = 0;
+    long long rej = 0, reju = 0;
+    // s2chain statistics over ALL rows (TranscriptionCycleMCMC.m:302-303), thread 0
+    double s2_sum = sigma2, sq_mean = sqrt(sigma2), sq_M2 = 0.0, s2_cnt = 1.0;
+    double wcnt = 0.0;                                     // rows folded into the summaries
+    const int first_row = a.n_burn - 1;                    // chain(n_burn:end,:) in 0-based rows
+    const int nstore = a.nsimu - first_row;
+    const bool bad0 = !isfinite(ss);
+
+    auto emit_row = [&](int k) {
+        // row k of the chain = current state: summaries, optional storage, covariance block buffer
+        if (k >= first_row) {
+            wcnt += 1.0;
+            for (int i = tid; i < npar; i += nt) {
+                const double xi = cs.x[i], d1 = xi - cs.wmean[i];
+                const double m = cs.wmean[i] + d1 / wcnt;
+                cs.wmean[i] = m;
+                cs.wM2[i] = fma(d1, xi - m, cs.wM2[i]);
+            }
+            if (a.store_chain && a.chain) {
+                double *dst = a.chain + ((size_t)ch * nstore + (k - first_row)) * ld;
+                for (int i = tid; i < npar; i += nt) dst[i] = cs.x[i];
+            }
+        }
+        if (a.do_cov) {
+            double *dst = gRows + (size_t)(k % a.adaptint) * ld;
+            for (int i = tid; i < npar; i += nt) dst[i] = cs.x[i];
+        }
+        if (tid == 0) {
+            if (a.store_chain && a.s2chain) a.s2chain[(size_t)ch * a.nsimu + k] = sigma2;
+            if (a.sschain) a.sschain[(size_t)ch * a.nsimu + k] = ss;
+        }
+    };
+    emit_row(0);
+    if (tid == 0 && a.flags) a.flags[(size_t)ch * a.nsimu] = 0;
+
+    for (int k = 1; k < a.nsimu && !bad0; ++k) {
+        const int isimu = k + 1;
+        // ---- 1. randomness of this step: z1, z2 (interleaved), u1, u2, chi2
+        double u1, u2, chi2v = 0.0;
+        if (a.replay) {
+            const size_t g = ((size_t)ch * a.nsimu + k) * ld;
+            for (int i = tid; i < npar; i += nt) { cs.zz[2 * i] = a.z1[g + i]; cs.zz[2 * i + 1] = a.z2[g + i]; }
+            u1 = a.u1[(size_t)ch * a.nsimu + k];
+            u2 = a.u2[(size_t)ch * a.nsimu + k];
+            if (tid == 0) chi2v = a.chi2[(size_t)ch * a.nsimu + k];
+        } else {
+            for (int q = tid; 2 * q < npar; q += nt) {
+                double za, zb;
+                normal_pair(draw(a.seed, uid, k, RK_Z1, q), za, zb);
+                cs.zz[4 * q] = za;
+                if (2 * q + 1 < npar) cs.zz[4 * q + 2] = zb;
+                normal_pair(draw(a.seed, uid, k, RK_Z2, q), za, zb);
+                cs.zz[4 * q + 1] = za;
+                if (2 * q + 1 < npar) cs.zz[4 * q + 3] = zb;
+            }
+            const u32x4 ru = draw(a.seed, uid, k, RK_U, 0);
+            u1 = u01(ru.x, ru.y);
+            u2 = u01(ru.z, ru.w);
+            if (tid == 0 && a.updatesigma) chi2v = chi2_draw(a.seed, uid, k, a.N0 + 2.0 * N);
+        }
+        __syncthreads();
+        // ---- 2. both proposals in one pass over R:  y1 = x + z1 R,  y2 = x + z2 R / drscale
+        double pr1 = 0.0, pr2 = 0.0;
+        int oob = 0;
+        const double inv_dr = 1.0 / a.drscale;
+        for (int j = tid; j < npar; j += nt) {
+            double s1 = 0.0, s2 = 0.0;
+            if (r_diag) {
+                s1 = cs.zz[2 * j] * cs.rdiag[j];
+                s2 = cs.zz[2 * j + 1] * cs.rdiag[j];
+            } else {
+                int rk = 0;
+                for (int i = 0; i <= j; ++i) {
+                    const double r = cs.R[rk + (j - i)];
+                    s1 = fma(cs.zz[2 * i], r, s1);
+                    s2 = fma(cs.zz[2 * i + 1], r, s2);
+                    rk += npar - i;
+                }
+            }
+            const double xj = cs.x[j], a1 = xj + s1, a2 = xj + s2 * inv_dr;
+            cs.y1[j] = a1;
+            cs.y2[j] = a2;
+            const double lo = cs.lo[j], hi = cs.hi[j];
+            if (a1 < lo || a1 > hi) oob |= 1;
+            if (a2 < lo || a2 > hi) oob |= 2;
+            const double e1 = (a1 - cs.pmu[j]) * cs.pinv[j], e2 = (a2 - cs.pmu[j]) * cs.pinv[j];
+            pr1 = fma(e1, e1, pr1);
+            pr2 = fma(e2, e2, pr2);
+        }
+        block_sum2(pr1, pr2, w.red);
+        const int oob1 = __syncthreads_or(oob & 1), oob2 = __syncthreads_or(oob & 2);
+
+        // ---- 3. stage 1
+        int fl = 0, accept = 0;
+        double ss1, a12;
+        if (oob1) {
+            ss1 = INFINITY; pr1 = 0.0; a12 = 0.0; fl |= TC_FL_OOB1; ++n_oob;
+        } else {
+            ss1 = ss_eval(a.cons, cv, cs.y1, w, a.algo, false, nullptr, nullptr);
+            ++n_ss;
+            a12 = exp(-0.5 * ((ss1 - ss) / sigma2 + pr1 - pri));
+            if (a12 <= 0.0) accept = 0;
+            else if (a12 >= 1.0) accept = 1;
+            else accept = a12 > u1;
+            if (accept) ++n_acc1;
+        }
+        const double *newp = cs.y1;
+        double ssn = ss1, prin = pr1;
+        // ---- 4. delayed rejection with R/drscale
+        if (!accept && a.ntry >= 2) {
+            fl |= TC_FL_DR; ++n_dr;
+            if (oob2) {
+                fl |= TC_FL_OOB2; ++n_oob;
+            } else {
+                const double ss2 = ss_eval(a.cons, cv, cs.y2, w, a.algo, false, nullptr, nullptr);
+                ++n_ss;
+                double a32 = exp(-0.5 * ((ss1 - ss2) / sigma2 + pr1 - pr2));
+                a32 = a32 > 1.0 ? 1.0 : a32;
+                if (!(a32 >= 0.0)) a32 = 0.0;
+                const double l2 = -0.5 * ((ss2 - ss) / sigma2 + pr2 - pri);
+                // q1 = -1/2 (|(y1-y2) R^-1|^2 - |(y1-x) R^-1|^2) = -1/2 (|z1 - z2/drscale|^2 - |z1|^2)
+                double n1 = 0.0, n0 = 0.0;
+                for (int i = tid; i < npar; i += nt) {
+                    const double za = cs.zz[2 * i], d = za - cs.zz[2 * i + 1] * inv_dr;
+                    n1 = fma(d, d, n1);
+                    n0 = fma(za, za, n0);
+                }
+                block_sum2(n1, n0, w.red);
+                const double q1 = -0.5 * (n1 - n0);
+                double a13 = exp(l2 + q1) * (1.0 - a32) / (1.0 - a12);
+                a13 = a13 > 1.0 ? 1.0 : a13;
+                const int acc2 = (a13 >= 1.0) || (a13 > u2);
+                if (acc2) { accept = 1; fl |= TC_FL_STAGE2; newp = cs.y2; ssn = ss2; prin = pr2; ++n_acc2; }
+            }
+        }
+        __syncthreads();
+        if (accept) {
+            fl |= TC_FL_ACCEPT;
+            for (int i = tid; i < npar; i += nt) cs.x[i] = newp[i];
+            ss = ssn; pri = prin;
+        } else { ++rej; ++reju; }
+        // ---- 5. sigma2 | ss ~ inv-chi2 (thread 0 draws, broadcast)
+        if (a.updatesigma) {
+            if (tid == 0) s_sc[0] = (a.N0 * a.S20 + ss) / chi2v;
+            __syncthreads();
+            sigma2 = s_sc[0];
+        } else __syncthreads();
+        if (tid == 0) {
+            s2_cnt += 1.0;
+            s2_sum += sigma2;
+            const double sq = sqrt(sigma2), d1 = sq - sq_mean;
+            sq_mean += d1 / s2_cnt;
+            sq_M2 = fma(d1, sq - sq_mean, sq_M2);
+            if (a.flags) a.flags[(size_t)ch * a.nsimu + k] = fl;
+        }
+        emit_row(k);
+
+        // ---- 6. adaptation
+        if (a.adaptint > 0 && isimu % a.adaptint == 0) {
+            __syncthreads();
+            if (a.do_cov) {
+                // fold rows [isimu-adaptint, isimu) into the running (cmean, M2): Chan's block update
+                const int m = a.adaptint;
+                for (int i = tid; i < npar; i += nt) {
+                    double s = 0.0;
+                    for (int r = 0; r < m; ++r) s += gRows[(size_t)r * ld + i];
+                    const double mb = s / m;
+                    cs.mb[i] = mb;
+                    cs.dm[i] = mb - cmean[i];
+                }
+                const double fcorr = cov_n * m / (cov_n + m);
+                const int ntile = (npar + 3) >> 2, T = ntile * (ntile + 1) / 2;
+                for (int base = 0; base < T; base += 2 * nt) {
+                    int tix[2] = {base + tid, base + nt + tid}, bi[2], bj[2];
+                    double acc[2][16];
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        int rem = tix[u] < T ? tix[u] : 0, b = 0;
+                        while (rem >= ntile - b) { rem -= ntile - b; ++b; }
+                        bi[u] = b; bj[u] = b + rem;
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) acc[u][e] = 0.0;
+                    }
+                    for (int r0 = 0; r0 < m; r0 += COV_RC) {
+                        const int rc = min(COV_RC, m - r0);
+                        __syncthreads();
+                        for (int e = tid; e < rc * npad; e += nt) {
+                            const int r = e / npad, c = e - r * npad;
+                            cs.chunk[e] = c < npar ? gRows[(size_t)(r0 + r) * ld + c] - cs.mb[c] : 0.0;
+                        }
+                        __syncthreads();
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            if (tix[u] >= T) continue;
+                            for (int r = 0; r < rc; ++r) {
+                                const double2 *ra = reinterpret_cast<const double2 *>(cs.chunk + r * npad + 4 * bi[u]);
+                                const double2 *rb = reinterpret_cast<const double2 *>(cs.chunk + r * npad + 4 * bj[u]);
+                                const double2 a0 = ra[0], a1 = ra[1], b0 = rb[0], b1 = rb[1];
+                                const double av[4] = {a0.x, a0.y, a1.x, a1.y}, bv[4] = {b0.x, b0.y, b1.x, b1.y};
+#pragma unroll
+                                for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+                                    for (int jj = 0; jj < 4; ++jj) acc[u][4 * ii + jj] = fma(av[ii], bv[jj], acc[u][4 * ii + jj]);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        if (tix[u] >= T) continue;
+#pragma unroll
+                        for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+                            for (int jj = 0; jj < 4; ++jj) {
+                                const int pp = 4 * bi[u] + ii, qq = 4 * bj[u] + jj;
+                                if (pp <= qq && qq < npar)
+                                    gM2[pidx(npar, pp, qq)] += acc[u][4 * ii + jj] + fcorr * cs.dm[pp] * cs.dm[qq];
+                            }
+                    }
+                }
+                __syncthreads();
+                for (int i = tid; i < npar; i += nt) cmean[i] += cs.dm[i] * (m / (cov_n + m));
+                cov_n += m;
+                __syncthreads();
+            }
+            if (isimu < a.burnintime) {
+                const double rate = a.burnin_cumulative ? (double)rej / isimu : (double)reju / a.adaptint;
+                double f = 1.0;
+                if (rate > 0.95) f = 1.0 / a.burnin_scale;
+                else if (rate < 0.05) f = a.burnin_scale;
+                if (f != 1.0) {
+                    if (r_diag) for (int i = tid; i < npar; i += nt) cs.rdiag[i] *= f;
+                    else for (int i = tid; i < npk; i += nt) { cs.R[i] *= f; gRb[i] = cs.R[i]; }
+                    __syncthreads();
+                }
+                reju = 0;
+            } else {
+                // R = chol(cov + qcovadj I) * adascale
+                for (int i = tid; i < npk; i += nt) cs.R[i] = gM2[i] / (cov_n - 1.0);
+                __syncthreads();
+                for (int i = tid; i < npar; i += nt) cs.R[pidx(npar, i, i)] += a.qcovadj;
+                __syncthreads();
+                const bool ok = chol_packed(npar, cs.R, &s_sc[1]);
+                __syncthreads();
+                if (ok) {
+                    for (int i = tid; i < npk; i += nt) { const double r = cs.R[i] * adascale; cs.R[i] = r; gRb[i] = r; }
+                    r_diag = false;
+                    ++n_adapt;
+                } else {
+                    ++n_cholfail;
+                    if (!r_diag) for (int i = tid; i < npk; i += nt) cs.R[i] = gRb[i];
+                }
+                __syncthreads();
+                reju = 0;
+            }
+        }
+    }
+
+    // ---- summaries (TranscriptionCycleMCMC.m:286-303)
+    __syncthreads();
+    for (int i = tid; i < npar; i += nt) {
+        if (a.mean) a.mean[(size_t)ch * ld + i] = cs.wmean[i];
+        if (a.std) a.std[(size_t)ch * ld + i] = wcnt > 0 ? sqrt(cs.wM2[i] / wcnt) : 0.0;
+    }
+    if (tid == 0) {
+        if (a.sig) {
+            a.sig[2 * (size_t)ch] = sqrt(s2_sum / s2_cnt);
+            a.sig[2 * (size_t)ch + 1] = sqrt(sq_M2 / s2_cnt);
+        }
+        if (a.counters) {
+            long long *c = a.counters + (size_t)ch * TC_NCOUNTERS;
+            c[TC_CNT_SS_EVALS] = n_ss; c[TC_CNT_ACC_STAGE1] = n_acc1; c[TC_CNT_ACC_STAGE2] = n_acc2;
+            c[TC_CNT_OUT_OF_BOUNDS] = n_oob; c[TC_CNT_ADAPTATIONS] = n_adapt;
+            c[TC_CNT_CHOL_FAIL] = n_cholfail; c[TC_CNT_DR_TRIES] = n_dr; c[TC_CNT_STATUS] = bad0 ? 1 : 0;
+        }
+    }
+}
+
+// -------------------------------------------------------------------------- RNG dump / FP64 peak
+__global__ void rng_dump_kernel(unsigned long long seed, unsigned long long uid, int npar, double dof,
+                                int nsimu, double *z1, double *u1, double *z2, double *u2, double *chi2)
+{
+    for (int k = blockIdx.x; k < nsimu; k += gridDim.x) {
+        for (int q = threadIdx.x; 2 * q < npar; q += blockDim.x) {
+            double za, zb;
+            normal_pair(draw(seed, uid, k, RK_Z1, q), za, zb);
+            z1[(size_t)k * npar + 2 * q] = za;
+            if (2 * q + 1 < npar) z1[(size_t)k * npar + 2 * q + 1] = zb;
+            normal_pair(draw(seed, uid, k, RK_Z2, q), za, zb);
+            z2[(size_t)k * npar + 2 * q] = za;
+            if (2 * q + 1 < npar) z2[(size_t)k * npar + 2 * q + 1] = zb;
+        }
+        if (threadIdx.x == 0) {
+            const u32x4 ru = draw(seed, uid, k, RK_U, 0);
+            u1[k] = u01(ru.x, ru.y);
+            u2[k] = u01(ru.z, ru.w);
+            chi2[k] = chi2_draw(seed, uid, k, dof);
+        }
+    }
+}
+
+__global__ void dfma_peak_kernel(double *out, long long *clk, int iters)
+{
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
+           a7 = a0 + 7;
+    const double m = 1.0000001, c = 1e-7;
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    const long long t1 = clock64();
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (threadIdx.x == 0) clk[blockIdx.x] = t1 - t0;
+}
+
+// ===================================================================================== host side
+struct DevCells {
+    int device = -1;
+    CellsDev d{};
+    std::vector<void *> allocs;
+};
+
+struct tc_cells {
+    tc_construct cons;
+    int ncells = 0, Nmax = 0;
+    std::vector<int> N;
+    std::vector<long long> off;
+    std::vector<double> t, tg, dtraw, dtg, ms2, pp7, iw, dmean;
+    std::vector<int> ik;
+    std::vector<DevCells> dev;
+};
+
+static double ml_round(double x) { return x >= 0 ? std::floor(x + 0.5) : -std::floor(-x + 0.5); }
+
+// MATLAB a:d:b (Moler's colon algorithm) — t_interp = t(1):dt:t(end), SumofSquares...m:30
+static std::vector<double> matlab_colon(double a, double d, double b)
+{
+    std::vector<double> out;
+    if (d == 0 || (d > 0 && a > b) || (d < 0 && a < b) || std::isnan(a) || std::isnan(b) || std::isnan(d)) return out;
+    const double tol = 2.0 * std::numeric_limits<double>::epsilon() * std::max(std::fabs(a), std::fabs(b));
+    const double sig = d > 0 ? 1.0 : -1.0;
+    long long n;
+    if (a == std::floor(a) && d == 1) n = (long long)(std::floor(b) - a);
+    else if (a == std::floor(a) && d == std::floor(d)) {
+        const double q = std::floor(a / d), r = a - q * d;
+        n = (long long)(std::floor((b - r) / d) - q);
+    } else {
+        n = (long long)ml_round((b - a) / d);
+        if (sig * (a + n * d - b) > tol) n -= 1;
+    }
+    double c = a + n * d;
+    if (sig * (c - b) > -tol) c = b;
+    out.assign((size_t)n + 1, 0.0);
+    for (long long k = 0; k <= n / 2; ++k) {
+        out[(size_t)k] = a + k * d;
+        out[(size_t)(n - k)] = c - k * d;
+    }
+    if (n % 2 == 0) out[(size_t)(n / 2)] = (a + c) / 2;
+    return out;
+}
+
+template <typename T>
+static int upload(DevCells &dc, const std::vector<T> &h, const T *&dptr)
+{
+    void *p = nullptr;
+    CUDA_TRY(cudaMalloc(&p, std::max<size_t>(h.size(), 1) * sizeof(T)));
+    dc.allocs.push_back(p);
+    CUDA_TRY(cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    dptr = static_cast<const T *>(p);
+    return TC_OK;
+}
+
+static int validate_construct(const tc_construct *c)
+{
+    if (!c) return fail(TC_EINVAL, "construct is NULL");
+    if (c->nsets < 1 || c->nsets > TC_MAX_SETS) return fail(TC_EINVAL, "construct.nsets out of range");
+    for (int s = 0; s < c->nsets; ++s) {
+        if (!(c->ms2_start[s] >= 0 && c->pp7_start[s] >= 0)) return fail(TC_EINVAL, "construct: loop start must be >= 0");
+        if (!(c->ms2_start[s] < c->ms2_end[s] && c->pp7_start[s] < c->pp7_end[s]))
+            return fail(TC_EINVAL, "construct: loop start must be < loop end");
+    }
+    return TC_OK;
+}
+
+extern "C" {
+
+int tc_version(void) { return TC_VERSION; }
+const char *tc_last_error(void) { return g_err.c_str(); }
+double tc_last_kernel_seconds(void) { return g_last_kernel_s; }
+
+int tc_device_count(int *count)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { *count = 0; return fail(TC_ENODEV, cudaGetErrorString(e)); }
+    *count = n;
+    return TC_OK;
+}
+
+int tc_device_info_get(int device, tc_device_info *out)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) return fail(TC_ENODEV, "no such CUDA device");
+    cudaDeviceProp p;
+    CUDA_TRY(cudaGetDeviceProperties(&p, device));
+    std::memset(out, 0, sizeof(*out));
+    std::strncpy(out->name, p.name, sizeof(out->name) - 1);
+    out->cc_major = p.major; out->cc_minor = p.minor; out->sm_count = p.multiProcessorCount;
+    out->total_mem = (int64_t)p.totalGlobalMem; out->smem_per_block_optin = (int64_t)p.sharedMemPerBlockOptin;
+    return TC_OK;
+}
+
+void tc_opts_default(tc_mcmc_opts *o)
+{
+    std::memset(o, 0, sizeof(*o));
+    o->nsimu = 20000; o->burnintime = 10000; o->adaptint = 100; o->ntry = 2; o->updatesigma = 1;
+    o->burnin_cumulative = 0; o->n_burn = 10000; o->store_chain = 0; o->replay = 0; o->algo = TC_ALGO_TOEPLITZ;
+    o->ngpus = 1;
+    for (int i = 0; i < TC_MAX_GPUS; ++i) o->devices[i] = -1;
+    o->drscale = 5.0; o->adascale = 0.0; o->qcovadj = 1e-8; o->burnin_scale = 10.0; o->N0 = 1.0; o->S20 = 1.0;
+    o->sigma2_0 = 1.0; o->seed = 20201028ULL;
+}
+
+int tc_cells_create(const tc_construct *construct, int ncells, const int32_t *N, const int64_t *off,
+                    const double *t, const double *ms2, const double *pp7, int ndev, const int32_t *devices,
+                    tc_cells **out)
+{
+    if (!out) return fail(TC_EINVAL, "out is NULL");
+    *out = nullptr;
+    int rc = validate_construct(construct);
+    if (rc) return rc;
+    if (ncells < 1 || !N || !off || !t || !ms2 || !pp7) return fail(TC_EINVAL, "empty dataset or NULL array");
+    int ndevs = 0;
+    if (cudaGetDeviceCount(&ndevs) != cudaSuccess || ndevs < 1) return fail(TC_ENODEV, "no CUDA device available (libtcmcmc has no CPU fallback)");
+    if (ndev < 1) ndev = 1;
+    tc_cells *c = new tc_cells();
+    c->cons = *construct;
+    c->ncells = ncells;
+    c->N.assign(N, N + ncells);
+    c->off.resize(ncells + 1);
+    long long tot = 0;
+    for (int i = 0; i < ncells; ++i) {
+        if (N[i] < 3) { delete c; return fail(TC_EINVAL, "cell with fewer than 3 timepoints"); }
+        c->off[i] = tot; tot += N[i];
+        c->Nmax = std::max(c->Nmax, (int)N[i]);
+    }
+    c->off[ncells] = tot;
+    c->t.resize(tot); c->tg.resize(tot); c->dtraw.assign(tot, 0.0); c->dtg.assign(tot, 0.0);
+    c->ms2.resize(tot); c->pp7.resize(tot); c->iw.assign(tot, 0.0); c->ik.assign(tot, -1); c->dmean.resize(ncells);
+    for (int ci = 0; ci < ncells; ++ci) {
+        const int n = N[ci];
+        const double *ts = t + off[ci];
+        double *T = c->t.data() + c->off[ci], *G = c->tg.data() + c->off[ci];
+        std::copy(ts, ts + n, T);
+        std::copy(ms2 + off[ci], ms2 + off[ci] + n, c->ms2.data() + c->off[ci]);
+        std::copy(pp7 + off[ci], pp7 + off[ci] + n, c->pp7.data() + c->off[ci]);
+        for (int i = 0; i + 1 < n; ++i)
+            if (!(ts[i + 1] > ts[i])) { delete c; return fail(TC_EINVAL, "time vector must be strictly increasing"); }
+        double s = 0;                                      // mean(t(2:end)-t(1:end-1))  SumofSquares...m:29
+        for (int i = 0; i + 1 < n; ++i) s += ts[i + 1] - ts[i];
+        const double dt = s / (n - 1);
+        c->dmean[ci] = dt;
+        std::vector<double> g = matlab_colon(ts[0], dt, ts[n - 1]);
+        if ((int)g.size() != n) {
+            delete c;
+            return fail(TC_EDIM, "numel(t(1):dt:t(end)) != numel(t) for cell " + std::to_string(ci) +
+                                     " (MATLAB: arrays have incompatible sizes in ConstantElongationSim R.*dt)");
+        }
+        std::copy(g.begin(), g.end(), G);
+        for (int i = 0; i + 1 < n; ++i) {
+            c->dtraw[c->off[ci] + i] = ts[i + 1] - ts[i];
+            c->dtg[c->off[ci] + i] = G[i + 1] - G[i];
+        }
+        // interp1(t_interp, model, t): bracketing interval + weight per experimental time (:55-56)
+        for (int j = 0; j < n; ++j) {
+            const double z = ts[j];
+            if (!(z >= G[0] && z <= G[n - 1])) continue;      // NaN outside the grid
+            int k = (int)(std::upper_bound(G, G + n, z) - G) - 1;
+            if (k > n - 2) k = n - 2;
+            c->ik[c->off[ci] + j] = k;
+            c->iw[c->off[ci] + j] = (z - G[k]) / (G[k + 1] - G[k]);
+        }
+    }
+    c->dev.resize(ndev);
+    for (int d = 0; d < ndev; ++d) {
+        DevCells &dc = c->dev[d];
+        dc.device = devices ? devices[d] : d;
+        if (dc.device < 0 || dc.device >= ndevs) { tc_cells_destroy(c); return fail(TC_ENODEV, "device index out of range"); }
+        cudaError_t e = cudaSetDevice(dc.device);
+        if (e != cudaSuccess) { tc_cells_destroy(c); return fail(TC_ECUDA, cudaGetErrorString(e)); }
+        dc.d.ncells = ncells;
+        if ((rc = upload(dc, c->N, dc.d.N)) || (rc = upload(dc, c->off, dc.d.off)) || (rc = upload(dc, c->t, dc.d.t)) ||
+            (rc = upload(dc, c->tg, dc.d.tg)) || (rc = upload(dc, c->dtraw, dc.d.dtraw)) ||
+            (rc = upload(dc, c->dtg, dc.d.dtg)) || (rc = upload(dc, c->ms2, dc.d.ms2)) ||
+            (rc = upload(dc, c->pp7, dc.d.pp7)) || (rc = upload(dc, c->iw, dc.d.iw)) ||
+            (rc = upload(dc, c->dmean, dc.d.dmean)) || (rc = upload(dc, c->ik, dc.d.ik))) {
+            std::string m = g_err;
+            tc_cells_destroy(c);
+            return fail(rc, m);
+        }
+    }
+    *out = c;
+    return TC_OK;
+}
+
+void tc_cells_destroy(tc_cells *c)
+{
+    if (!c) return;
+    for (auto &dc : c->dev) {
+        if (dc.device >= 0) cudaSetDevice(dc.device);
+        for (void *p : dc.allocs) cudaFree(p);
+    }
+    delete c;
+}
+
+int tc_cells_t_interp(const tc_cells *c, int cell, double *out, int cap)
+{
+    if (!c || cell < 0 || cell >= c->ncells) return fail(TC_EINVAL, "bad cell index");
+    const int n = c->N[cell];
+    if (cap < n) return fail(TC_EINVAL, "buffer too small");
+    std::copy(c->tg.begin() + c->off[cell], c->tg.begin() + c->off[cell] + n, out);
+    return n;
+}
+
+static const DevCells *find_dev(const tc_cells *c, int device)
+{
+    for (auto &d : c->dev) if (d.device == device) return &d;
+    return nullptr;
+}
+
+static int launch_ss(const tc_cells *c, const DevCells *dc, long long nbatch, const int *d_cell, const double *d_theta,
+                     int ld, int algo, int raw, double *d_ss, double *d_o1, double *d_o2, int ldo, cudaStream_t st)
+{
+    if (algo != TC_ALGO_PAIRS && algo != TC_ALGO_TOEPLITZ) return fail(TC_EINVAL, "unknown algo");
+    if (raw && algo != TC_ALGO_PAIRS) return fail(TC_EINVAL, "the raw (irregular) grid needs TC_ALGO_PAIRS");
+    if (ld < 7 + c->Nmax) return fail(TC_EINVAL, "ld < 7 + max(N)");
+    if (nbatch <= 0) return TC_OK;
+    SsArgs a{};
+    a.cells = dc->d; a.cons = c->cons; a.nbatch = nbatch; a.cell_id = d_cell; a.theta = d_theta; a.ld = ld;
+    a.algo = algo; a.raw_grid = raw; a.ldo = ldo; a.ss_out = d_ss; a.out1 = d_o1; a.out2 = d_o2;
+    const size_t smem = sizeof(double) * (size_t)(cell_doubles(c->Nmax) + work_doubles(c->Nmax) + 7 + c->Nmax + 2);
+    CUDA_TRY(cudaFuncSetAttribute(ss_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int sms = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dc->device));
+    const long long maxgrid = (long long)sms * 64;
+    const int grid = (int)std::min<long long>(nbatch, maxgrid);
+    ss_batch_kernel<<<grid, SS_THREADS, smem, st>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    return TC_OK;
+}
+
+int tc_ss_batch_device(const tc_cells *c, int device, int64_t nbatch, const int32_t *d_cell_id, const double *d_theta,
+                       int ld, int algo, double *d_ss_out, void *stream)
+{
+    if (!c) return fail(TC_EINVAL, "cells is NULL");
+    const DevCells *dc = find_dev(c, device);
+    if (!dc) return fail(TC_EINVAL, "cells not resident on that device");
+    CUDA_TRY(cudaSetDevice(device));
+    return launch_ss(c, dc, nbatch, d_cell_id, d_theta, ld, algo, 0, d_ss_out, nullptr, nullptr, 0, (cudaStream_t)stream);
+}
+
+}  // extern "C"
+
+struct DevBuf {                      // RAII for device scratch
+    std::vector<void *> ptrs;
+    ~DevBuf() { for (void *p : ptrs) cudaFree(p); }
+    template <typename T> cudaError_t alloc(T *&p, size_t n)
+    {
+        void *q = nullptr;
+        cudaError_t e = cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T));
+        if (e == cudaSuccess) { ptrs.push_back(q); p = static_cast<T *>(q); }
+        return e;
+    }
+};
+
+static int ss_host(const tc_cells *c, int64_t nbatch, const int32_t *cell_id, const double *theta, int ld, int algo,
+                   int raw, double *ss_out, double *o1, double *o2, int ldo)
+{
+    if (!c) return fail(TC_EINVAL, "cells is NULL");
+    if (nbatch < 0 || (nbatch > 0 && (!cell_id || !theta))) return fail(TC_EINVAL, "NULL batch arrays");
+    if (nbatch == 0) return TC_OK;
+    for (int64_t b = 0; b < nbatch; ++b)
+        if (cell_id[b] < 0 || cell_id[b] >= c->ncells) return fail(TC_EINVAL, "cell_id out of range");
+    if ((o1 || o2) && ldo < c->Nmax) return fail(TC_EINVAL, "ldo < max(N)");
+    const DevCells *dc = &c->dev[0];
+    CUDA_TRY(cudaSetDevice(dc->device));
+    DevBuf buf;
+    int *d_cell = nullptr; double *d_theta = nullptr, *d_ss = nullptr, *d_o1 = nullptr, *d_o2 = nullptr;
+    CUDA_TRY(buf.alloc(d_cell, nbatch));
+    CUDA_TRY(buf.alloc(d_theta, (size_t)nbatch * ld));
+    if (ss_out) CUDA_TRY(buf.alloc(d_ss, nbatch));
+    if (o1) { CUDA_TRY(buf.alloc(d_o1, (size_t)nbatch * ldo)); CUDA_TRY(buf.alloc(d_o2, (size_t)nbatch * ldo)); }
+    CUDA_TRY(cudaMemcpy(d_cell, cell_id, nbatch * sizeof(int), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d_theta, theta, (size_t)nbatch * ld * sizeof(double), cudaMemcpyHostToDevice));
+    if (o1) { CUDA_TRY(cudaMemset(d_o1, 0, (size_t)nbatch * ldo * sizeof(double))); CUDA_TRY(cudaMemset(d_o2, 0, (size_t)nbatch * ldo * sizeof(double))); }
+    int rc = launch_ss(c, dc, nbatch, d_cell, d_theta, ld, algo, raw, d_ss, d_o1, d_o2, ldo, 0);
+    if (rc) return rc;
+    CUDA_TRY(cudaDeviceSynchronize());
+    if (ss_out) CUDA_TRY(cudaMemcpy(ss_out, d_ss, nbatch * sizeof(double), cudaMemcpyDeviceToHost));
+    if (o1) {
+        CUDA_TRY(cudaMemcpy(o1, d_o1, (size_t)nbatch * ldo * sizeof(double), cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(o2, d_o2, (size_t)nbatch * ldo * sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    return TC_OK;
+}
+
+extern "C" {
+
+int tc_ss_batch(const tc_cells *c, int64_t nbatch, const int32_t *cell_id, const double *theta, int ld, int algo,
+                double *ss_out)
+{
+    if (!ss_out && nbatch > 0) return fail(TC_EINVAL, "ss_out is NULL");
+    return ss_host(c, nbatch, cell_id, theta, ld, algo, 0, ss_out, nullptr, nullptr, 0);
+}
+
+int tc_forward(const tc_cells *c, int64_t nbatch, const int32_t *cell_id, const double *theta, int ld, int on_raw_grid,
+               double *ms2_out, double *pp7_out, int ldo)
+{
+    if (!ms2_out || !pp7_out) return fail(TC_EINVAL, "output is NULL");
+    return ss_host(c, nbatch, cell_id, theta, ld, TC_ALGO_PAIRS, on_raw_grid ? 1 : 0, nullptr, ms2_out, pp7_out, ldo);
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------- mcmc run
+struct DevRun {
+    int device = -1, c0 = 0, c1 = 0;      // chains [c0, c1)
+    DevBuf buf;
+    cudaStream_t st = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    RunArgs a{};
+    ~DevRun()
+    {
+        if (device >= 0) cudaSetDevice(device);
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+        if (st) cudaStreamDestroy(st);
+    }
+};
+
+template <typename T>
+static cudaError_t up(DevBuf &b, T *&d, const T *h, size_t n, cudaStream_t st)
+{
+    cudaError_t e = b.alloc(d, n);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyAsync(d, h, n * sizeof(T), cudaMemcpyHostToDevice, st);
+}
+
+extern "C" {
+
+int tc_mcmc_run(const tc_cells *c, const tc_mcmc_opts *o, int nchains, const int32_t *chain_cell,
+                const uint64_t *chain_uid, int ld, const double *theta0, const double *qcov_diag, const double *low,
+                const double *upp, const double *prior_mu, const double *prior_sig, double *mean, double *std,
+                double *sig, int64_t *counters, double *chain, double *s2chain, const tc_replay *rp)
+{
+    if (!c || !o) return fail(TC_EINVAL, "cells/opts is NULL");
+    if (nchains < 1) return fail(TC_EINVAL, "nchains < 1");
+    if (!chain_cell || !theta0 || !qcov_diag || !low || !upp || !prior_mu || !prior_sig) return fail(TC_EINVAL, "NULL chain input");
+    if (ld < 7 + c->Nmax) return fail(TC_EINVAL, "ld < 7 + max(N)");
+    if (o->nsimu < 1) return fail(TC_EINVAL, "nsimu < 1");
+    if (o->n_burn < 1 || o->n_burn > o->nsimu) return fail(TC_EINVAL, "n_burn must be in [1, nsimu]");
+    if (o->ntry < 1 || o->ntry > 2) return fail(TC_EINVAL, "ntry must be 1 or 2");
+    if (!(o->drscale > 0)) return fail(TC_EINVAL, "drscale must be > 0");
+    if (o->algo != TC_ALGO_PAIRS && o->algo != TC_ALGO_TOEPLITZ) return fail(TC_EINVAL, "unknown algo");
+    if (o->replay && (!rp || !rp->z1 || !rp->u1 || !rp->z2 || !rp->u2 || !rp->chi2)) return fail(TC_EINVAL, "replay streams missing");
+    if (o->store_chain && (!chain || !s2chain)) return fail(TC_EINVAL, "store_chain set but chain/s2chain is NULL");
+    for (int i = 0; i < nchains; ++i)
+        if (chain_cell[i] < 0 || chain_cell[i] >= c->ncells) return fail(TC_EINVAL, "chain_cell out of range");
+    for (size_t i = 0; i < (size_t)nchains; ++i)
+        for (int p = 0; p < 7 + c->N[chain_cell[i]]; ++p)
+            if (!(qcov_diag[i * ld + p] > 0)) return fail(TC_EINVAL, "qcov_diag must be > 0");
+
+    // devices: 'numParPools' => GPU count
+    int ngpus = std::max(1, o->ngpus);
+    std::vector<int> devs;
+    for (int g = 0; g < ngpus; ++g) devs.push_back(o->devices[0] >= 0 ? o->devices[g] : c->dev[std::min<size_t>(g, c->dev.size() - 1)].device);
+    if (o->devices[0] < 0 && ngpus > (int)c->dev.size()) return fail(TC_EINVAL, "ngpus exceeds the devices the cells were uploaded to");
+    for (int d : devs) if (!find_dev(c, d)) return fail(TC_EINVAL, "cells not resident on a requested device");
+    ngpus = std::min(ngpus, nchains);
+
+    const int Nmax = c->Nmax, npmax = 7 + Nmax, npad = (npmax + 3) & ~3;
+    const int ldR = npmax * (npmax + 1) / 2;
+    // does any adaptation with a covariance ever happen?
+    bool do_cov = false;
+    if (o->adaptint > 0)
+        for (long long m = o->adaptint; m <= o->nsimu; m += o->adaptint) if (m >= o->burnintime) { do_cov = true; break; }
+    const int nstore = o->nsimu - (o->n_burn - 1);
+
+    // static partition: contiguous blocks of ~equal work (work ~ N^2 per step)
+    std::vector<double> wk(nchains + 1, 0.0);
+    for (int i = 0; i < nchains; ++i) { const double n = c->N[chain_cell[i]]; wk[i + 1] = wk[i] + n * n; }
+    std::vector<DevRun> runs(ngpus);
+    int prev = 0;
+    for (int g = 0; g < ngpus; ++g) {
+        int end = nchains;
+        if (g + 1 < ngpus) {
+            const double target = wk[nchains] * (g + 1) / ngpus;
+            end = (int)(std::lower_bound(wk.begin(), wk.end(), target) - wk.begin());
+            end = std::max(end, prev + 1);
+            end = std::min(end, nchains - (ngpus - 1 - g));
+        }
+        runs[g].device = devs[g]; runs[g].c0 = prev; runs[g].c1 = end;
+        prev = end;
+    }
+
+    for (auto &r : runs) {
+        const int nc = r.c1 - r.c0;
+        const size_t o0 = (size_t)r.c0;
+        CUDA_TRY(cudaSetDevice(r.device));
+        CUDA_TRY(cudaStreamCreateWithFlags(&r.st, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreate(&r.e0));
+        CUDA_TRY(cudaEventCreate(&r.e1));
+        RunArgs &a = r.a;
+        a.cells = find_dev(c, r.device)->d; a.cons = c->cons;
+        a.nsimu = o->nsimu; a.burnintime = o->burnintime; a.adaptint = o->adaptint; a.ntry = o->ntry;
+        a.updatesigma = o->updatesigma; a.burnin_cumulative = o->burnin_cumulative; a.n_burn = o->n_burn;
+        a.store_chain = o->store_chain; a.replay = o->replay; a.algo = o->algo;
+        a.drscale = o->drscale; a.adascale = o->adascale; a.qcovadj = o->qcovadj; a.burnin_scale = o->burnin_scale;
+        a.N0 = o->N0; a.S20 = o->S20; a.sigma2_0 = o->sigma2_0; a.seed = o->seed;
+        a.nchains = nc; a.ld = ld; a.ldR = ldR; a.do_cov = do_cov ? 1 : 0;
+        int *d_cell; unsigned long long *d_uid; double *d;
+        CUDA_TRY(up(r.buf, d_cell, (const int *)chain_cell + o0, nc, r.st)); a.chain_cell = d_cell;
+        std::vector<unsigned long long> uid(nc);
+        for (int i = 0; i < nc; ++i) uid[i] = chain_uid ? chain_uid[o0 + i] : (unsigned long long)(o0 + i);
+        CUDA_TRY(r.buf.alloc(d_uid, nc));
+        CUDA_TRY(cudaMemcpy(d_uid, uid.data(), nc * sizeof(unsigned long long), cudaMemcpyHostToDevice)); a.chain_uid = d_uid;
+        CUDA_TRY(up(r.buf, d, theta0 + o0 * ld, (size_t)nc * ld, r.st)); a.theta0 = d;
+        CUDA_TRY(up(r.buf, d, qcov_diag + o0 * ld, (size_t)nc * ld, r.st)); a.qcov_diag = d;
+        CUDA_TRY(up(r.buf, d, low + o0 * ld, (size_t)nc * ld, r.st)); a.low = d;
+        CUDA_TRY(up(r.buf, d, upp + o0 * ld, (size_t)nc * ld, r.st)); a.upp = d;
+        CUDA_TRY(up(r.buf, d, prior_mu + o0 * ld, (size_t)nc * ld, r.st)); a.pmu = d;
+        CUDA_TRY(up(r.buf, d, prior_sig + o0 * ld, (size_t)nc * ld, r.st)); a.psig = d;
+        CUDA_TRY(r.buf.alloc(a.mean, (size_t)nc * ld)); CUDA_TRY(cudaMemsetAsync(a.mean, 0, (size_t)nc * ld * 8, r.st));
+        CUDA_TRY(r.buf.alloc(a.std, (size_t)nc * ld)); CUDA_TRY(cudaMemsetAsync(a.std, 0, (size_t)nc * ld * 8, r.st));
+        CUDA_TRY(r.buf.alloc(a.sig, (size_t)nc * 2));
+        CUDA_TRY(r.buf.alloc(a.counters, (size_t)nc * TC_NCOUNTERS));
+        if (o->store_chain) {
+            CUDA_TRY(r.buf.alloc(a.chain, (size_t)nc * nstore * ld));
+            CUDA_TRY(cudaMemsetAsync(a.chain, 0, (size_t)nc * nstore * ld * 8, r.st));
+            CUDA_TRY(r.buf.alloc(a.s2chain, (size_t)nc * o->nsimu));
+        }
+        if (o->replay) {
+            const size_t nz = (size_t)nc * o->nsimu * ld, nu = (size_t)nc * o->nsimu;
+            CUDA_TRY(up(r.buf, d, rp->z1 + o0 * o->nsimu * ld, nz, r.st)); a.z1 = d;
+            CUDA_TRY(up(r.buf, d, rp->z2 + o0 * o->nsimu * ld, nz, r.st)); a.z2 = d;
+            CUDA_TRY(up(r.buf, d, rp->u1 + o0 * o->nsimu, nu, r.st)); a.u1 = d;
+            CUDA_TRY(up(r.buf, d, rp->u2 + o0 * o->nsimu, nu, r.st)); a.u2 = d;
+            CUDA_TRY(up(r.buf, d, rp->chi2 + o0 * o->nsimu, nu, r.st)); a.chi2 = d;
+        }
+        if (rp && rp->flags) CUDA_TRY(r.buf.alloc(a.flags, (size_t)nc * o->nsimu));
+        if (rp && rp->sschain) CUDA_TRY(r.buf.alloc(a.sschain, (size_t)nc * o->nsimu));
+        // scratch
+        CUDA_TRY(r.buf.alloc(a.gR, (size_t)nc * ldR));
+        if (do_cov) {
+            CUDA_TRY(r.buf.alloc(a.gM2, (size_t)nc * ldR));
+            CUDA_TRY(r.buf.alloc(a.gRows, (size_t)nc * o->adaptint * ld));
+            CUDA_TRY(r.buf.alloc(a.gCmean, (size_t)nc * ld));
+        }
+        size_t smem_base = sizeof(double) * (size_t)(cell_doubles(Nmax) + work_doubles(Nmax) + chain_doubles(npmax, npad) + 2);
+        size_t smem_R = sizeof(double) * (size_t)ldR;
+        int optin = 0;
+        CUDA_TRY(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, r.device));
+        a.r_in_smem = (smem_base + smem_R <= (size_t)optin) ? 1 : 0;
+        if (smem_base > (size_t)optin) return fail(TC_EINVAL, "N too large for the shared-memory layout of this build");
+        if (!a.r_in_smem) CUDA_TRY(r.buf.alloc(a.gRw, (size_t)nc * ldR));
+        const size_t smem = smem_base + (a.r_in_smem ? smem_R : 0);
+        CUDA_TRY(cudaFuncSetAttribute(dram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaEventRecord(r.e0, r.st));
+        dram_kernel<<<nc, DRAM_THREADS, smem, r.st>>>(a);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaEventRecord(r.e1, r.st));
+    }
+    double kmax = 0.0;
+    for (auto &r : runs) {
+        const int nc = r.c1 - r.c0;
+        const size_t o0 = (size_t)r.c0;
+        CUDA_TRY(cudaSetDevice(r.device));
+        CUDA_TRY(cudaStreamSynchronize(r.st));
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, r.e0, r.e1));
+        kmax = std::max(kmax, (double)ms * 1e-3);
+        RunArgs &a = r.a;
+        if (mean) CUDA_TRY(cudaMemcpy(mean + o0 * ld, a.mean, (size_t)nc * ld * 8, cudaMemcpyDeviceToHost));
+        if (std) CUDA_TRY(cudaMemcpy(std + o0 * ld, a.std, (size_t)nc * ld * 8, cudaMemcpyDeviceToHost));
+        if (sig) CUDA_TRY(cudaMemcpy(sig + o0 * 2, a.sig, (size_t)nc * 2 * 8, cudaMemcpyDeviceToHost));
+        if (counters) CUDA_TRY(cudaMemcpy(counters + o0 * TC_NCOUNTERS, a.counters, (size_t)nc * TC_NCOUNTERS * 8, cudaMemcpyDeviceToHost));
+        if (o->store_chain) {
+            CUDA_TRY(cudaMemcpy(chain + o0 * nstore * ld, a.chain, (size_t)nc * nstore * ld * 8, cudaMemcpyDeviceToHost));
+            CUDA_TRY(cudaMemcpy(s2chain + o0 * o->nsimu, a.s2chain, (size_t)nc * o->nsimu * 8, cudaMemcpyDeviceToHost));
+        }
+        if (rp && rp->flags) CUDA_TRY(cudaMemcpy(rp->flags + o0 * o->nsimu, a.flags, (size_t)nc * o->nsimu * 4, cudaMemcpyDeviceToHost));
+        if (rp && rp->sschain) CUDA_TRY(cudaMemcpy(rp->sschain + o0 * o->nsimu, a.sschain, (size_t)nc * o->nsimu * 8, cudaMemcpyDeviceToHost));
+    }
+    g_last_kernel_s = kmax;
+    if (counters)
+        for (int i = 0; i < nchains; ++i)
+            if (counters[(size_t)i * TC_NCOUNTERS + TC_CNT_STATUS] != 0)
+                return fail(TC_ESTATE, "ss(theta0) is not finite for chain " + std::to_string(i));
+    return TC_OK;
+}
+
+int tc_rng_dump(uint64_t seed, uint64_t chain_uid, int npar, double chi2_dof, int nsimu, double *z1, double *u1,
+                double *z2, double *u2, double *chi2, int device)
+{
+    if (npar < 1 || nsimu < 1 || !z1 || !u1 || !z2 || !u2 || !chi2) return fail(TC_EINVAL, "bad argument");
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) return fail(TC_ENODEV, "no such CUDA device");
+    CUDA_TRY(cudaSetDevice(device));
+    DevBuf b;
+    double *dz1, *dz2, *du1, *du2, *dc2;
+    CUDA_TRY(b.alloc(dz1, (size_t)nsimu * npar)); CUDA_TRY(b.alloc(dz2, (size_t)nsimu * npar));
+    CUDA_TRY(b.alloc(du1, nsimu)); CUDA_TRY(b.alloc(du2, nsimu)); CUDA_TRY(b.alloc(dc2, nsimu));
+    rng_dump_kernel<<<std::min(nsimu, 1024), 128>>>(seed, chain_uid, npar, chi2_dof, nsimu, dz1, du1, dz2, du2, dc2);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(z1, dz1, (size_t)nsimu * npar * 8, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(z2, dz2, (size_t)nsimu * npar * 8, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(u1, du1, (size_t)nsimu * 8, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(u2, du2, (size_t)nsimu * 8, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(chi2, dc2, (size_t)nsimu * 8, cudaMemcpyDeviceToHost));
+    return TC_OK;
+}
+
+int tc_measure_fp64_peak(int device, double *dfma_per_s, double *sm_clock_mhz)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) return fail(TC_ENODEV, "no such CUDA device");
+    CUDA_TRY(cudaSetDevice(device));
+    int sms = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    const int blocks = sms * 8, threads = 256, iters = 1 << 16;
+    DevBuf b;
+    double *out; long long *clk;
+    CUDA_TRY(b.alloc(out, (size_t)blocks * threads));
+    CUDA_TRY(b.alloc(clk, blocks));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
+    double best = 0, clk_mhz = 0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CUDA_TRY(cudaEventRecord(e0));
+        dfma_peak_kernel<<<blocks, threads>>>(out, clk, iters);
+        CUDA_TRY(cudaEventRecord(e1));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        const double rate = (double)blocks * threads * 8.0 * iters / (ms * 1e-3);
+        if (rate > best) {
+            best = rate;
+            // one wave of 8 CTAs/SM runs concurrently: per-CTA cycles / kernel time ~ SM clock
+            std::vector<long long> h(blocks);
+            CUDA_TRY(cudaMemcpy(h.data(), clk, blocks * sizeof(long long), cudaMemcpyDeviceToHost));
+            long long mx = 0;
+            for (long long v : h) mx = std::max(mx, v);
+            clk_mhz = (double)mx / (ms * 1e-3) * 1e-6;
+        }
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (dfma_per_s) *dfma_per_s = best;
+    if (sm_clock_mhz) *sm_clock_mhz = clk_mhz;
+    return TC_OK;
+}
+
+}  // extern "C"
