@@ -100,7 +100,10 @@ typedef struct tc_mcmc_opts {
 enum {
     TC_CNT_SS_EVALS = 0, TC_CNT_ACC_STAGE1 = 1, TC_CNT_ACC_STAGE2 = 2, TC_CNT_OUT_OF_BOUNDS = 3,
     TC_CNT_ADAPTATIONS = 4, TC_CNT_CHOL_FAIL = 5, TC_CNT_DR_TRIES = 6, TC_CNT_STATUS = 7,
-    TC_NCOUNTERS = 8
+    /* SM cycles thread 0 spent per phase: randomness, proposals, stage-1 ss, delayed rejection,
+       state/sigma2/row write-back, covariance block update, Cholesky (+burn-in scaling), spare */
+    TC_CNT_CYCLES0 = 8,
+    TC_NCOUNTERS = 16
 };
 /* Per-step flag bits returned in `flags` (replay / parity harness) */
 enum { TC_FL_ACCEPT = 1, TC_FL_STAGE2 = 2, TC_FL_OOB1 = 4, TC_FL_DR = 8, TC_FL_OOB2 = 16 };

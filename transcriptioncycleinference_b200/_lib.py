@@ -12,7 +12,7 @@ from . import build as _build
 
 MAX_SETS = 8
 MAX_GPUS = 8
-NCOUNTERS = 8
+NCOUNTERS = 16
 ALGO_PAIRS, ALGO_TOEPLITZ = 0, 1
 CNT_SS_EVALS, CNT_ACC_STAGE1, CNT_ACC_STAGE2, CNT_OUT_OF_BOUNDS = 0, 1, 2, 3
 CNT_ADAPTATIONS, CNT_CHOL_FAIL, CNT_DR_TRIES, CNT_STATUS = 4, 5, 6, 7

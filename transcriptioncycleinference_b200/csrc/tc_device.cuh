@@ -204,8 +204,7 @@ __device__ __forceinline__ double loop_response(double p, double s, double e, do
 // the same integers as the sequential reference order.
 __device__ inline void scan_counts(int N, const double *rd, double *K, bool force_sequential)
 {
-    if (threadIdx.x >= 32) return;
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x & 31;               // called by ONE full warp
     const int n = N - 1;                       // increments rd[0..n-1]
     bool redo = force_sequential;
     if (!force_sequential) {
@@ -224,7 +223,8 @@ __device__ inline void scan_counts(int N, const double *rd, double *K, bool forc
         for (int i = b; i < e; ++i) {
             c = __dadd_rn(c, rd[i]);
             const double f = floor(c);
-            risky |= (c - f < 1e-7) || (f + 1.0 - c < 1e-7);
+            // c == 0: every increment so far is exactly 0 (they are all >= 0) -> exact in any order
+            risky |= (c != 0.0) && ((c - f < 1e-7) || (f + 1.0 - c < 1e-7));
             K[i + 1] = f;
         }
         redo = __any_sync(0xffffffffu, risky);
@@ -275,33 +275,37 @@ __device__ inline double ss_eval(const tc_construct &C, const CellView &cv, cons
     }
     for (int j = tid; j < N; j += nt) { w.F1[j] = 0.0; w.F2[j] = 0.0; }
     __syncthreads();
-    // (b) cumulative integer counts
-    scan_counts(N, w.rd, w.K, seq_scan);
-    __syncthreads();
 
-    // (c) fluorescence per time point, one loop set at a time (the basal clamp sits inside the
-    //     per-set loop in the reference: GetFluorFromPolPos.m:47,57,69)
+    // (b)+(c) warp 0 scans the loading counter while warps 1 and 2 build the response tables of the
+    //     two colours; then every thread sums its time points.  One loop set at a time: the basal
+    //     clamp sits inside the per-set loop in the reference (GetFluorFromPolPos.m:47,57,69).
     const double tv = tau * v;
     const double L1 = C.L_ms2 + tv, L2 = C.L_pp7 + tv;        // :19-20
+    const int warp = tid >> 5, lane = tid & 31;
     for (int s = 0; s < C.nsets; ++s) {
         const double s1 = C.ms2_start[s], e1 = C.ms2_end[s], f1 = C.ms2_loopn[s] / 24.0;
         const double s2 = C.pp7_start[s], e2 = C.pp7_end[s], f2 = C.pp7_loopn[s] / 24.0;
+        if (s == 0 && warp == 0) scan_counts(N, w.rd, w.K, seq_scan);
         if (algo == TC_ALGO_TOEPLITZ) {
-            // lag thresholds of the piecewise response, by exact predicate on p = v*(d*lag)
-            if (tid < 8) {
-                const double xs[8] = {s1, e1, e1, L1, s2, e2, e2, L2};
-                const bool st[8] = {true, false, true, false, true, false, true, false};
-                w.thr[tid] = first_lag(v, cv.d, xs[tid], N, st[tid]);
+            // lag thresholds of the piecewise response, by exact predicate on p = v*(d*lag):
+            // ramp = [la, le), plateau = [lb, lL)
+            if (warp == 1 || warp == 2) {
+                const bool c2 = warp == 2;
+                const double xs = c2 ? s2 : s1, xe = c2 ? e2 : e1, xL = c2 ? L2 : L1, xf = c2 ? f2 : f1;
+                int *thr = w.thr + (c2 ? 4 : 0);
+                if (lane < 4) {
+                    const double x = lane == 0 ? xs : (lane == 3 ? xL : xe);
+                    thr[lane] = first_lag(v, cv.d, x, N, (lane & 1) == 0);   // >s, >=e, >e, >=L
+                }
+                __syncwarp();
+                const int la = thr[0], le = thr[1];
+                double *G = c2 ? w.G2 : w.G1;
+                const double sc = xf / (xe - xs);
+                for (int lag = la + lane; lag < le; lag += 32) G[lag] = (v * (cv.d * (double)lag) - xs) * sc;
             }
             __syncthreads();
             const int la1 = w.thr[0], le1 = w.thr[1], lb1 = w.thr[2], lL1 = w.thr[3];
             const int la2 = w.thr[4], le2 = w.thr[5], lb2 = w.thr[6], lL2 = w.thr[7];
-            for (int lag = tid; lag < N; lag += nt) {          // ramp part of the response table
-                const double p = v * (cv.d * (double)lag);
-                if (lag >= la1 && lag < le1) w.G1[lag] = (p - s1) * f1 / (e1 - s1);
-                if (lag >= la2 && lag < le2) w.G2[lag] = (p - s2) * f2 / (e2 - s2);
-            }
-            __syncthreads();
             for (int j = tid; j < N; j += nt) {
                 double a1 = 0.0, a2 = 0.0;
                 const int h1 = min(le1 - 1, j), h2 = min(le2 - 1, j);
@@ -310,13 +314,14 @@ __device__ inline double ss_eval(const tc_construct &C, const CellView &cv, cons
                 for (int lag = la2; lag <= h2; ++lag)
                     a2 = fma(w.K[j - lag + 1] - w.K[j - lag], w.G2[lag], a2);
                 // plateau: cohorts with lag in [lb, lL) are whole polymerases -> exact count
-                if (j >= lb1) a1 = fma(f1, w.K[j - lb1 + 1] - w.K[max(j - lL1 + 1, 0)], a1);
-                if (j >= lb2) a2 = fma(f2, w.K[j - lb2 + 1] - w.K[max(j - lL2 + 1, 0)], a2);
+                if (j >= lb1 && lb1 < lL1) a1 = fma(f1, w.K[j - lb1 + 1] - w.K[max(j - lL1 + 1, 0)], a1);
+                if (j >= lb2 && lb2 < lL2) a2 = fma(f2, w.K[j - lb2 + 1] - w.K[max(j - lL2 + 1, 0)], a2);
                 double m1 = w.F1[j] + a1, m2 = w.F2[j] + a2;
                 w.F1[j] = m1 < b1 ? b1 : m1;                  // :57
                 w.F2[j] = m2 < b2 ? b2 : m2;                  // :69
             }
         } else {
+            __syncthreads();
             for (int j = tid; j < N; j += nt) {
                 double a1 = 0.0, a2 = 0.0;
                 const double tj = cv.tg[j];

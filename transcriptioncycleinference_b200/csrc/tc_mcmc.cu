@@ -141,7 +141,6 @@ __global__ void __launch_bounds__(DRAM_THREADS) dram_kernel(const __grid_constan
 {
     extern __shared__ __align__(16) double smem[];
     __shared__ double s_sc[8];
-    __shared__ int s_dec[2];
     const int tid = threadIdx.x, nt = blockDim.x;
     const int ch = blockIdx.x;
     if (ch >= a.nchains) return;
@@ -158,6 +157,7 @@ __global__ void __launch_bounds__(DRAM_THREADS) dram_kernel(const __grid_constan
     carve_cell(p, N, cv);
     carve_work(p, N, w);
     cs.x = p; p += npar;   cs.y1 = p; p += npar;   cs.y2 = p; p += npar;
+    p += ((p - smem) & 1);                                 // 16-byte align the interleaved (z1,z2) pairs
     cs.zz = p; p += 2 * npar;
     cs.lo = p; p += npar;  cs.hi = p; p += npar;   cs.pmu = p; p += npar;  cs.pinv = p; p += npar;
     cs.wmean = p; p += npar; cs.wM2 = p; p += npar; cs.rdiag = p; p += npar;
@@ -204,6 +204,9 @@ __global__ void __launch_bounds__(DRAM_THREADS) dram_kernel(const __grid_constan
     double sigma2 = a.sigma2_0;
     long long n_ss = 1, n_acc1 = 0, n_acc2 = 0, n_oob = 0, n_adapt = 0, n_cholfail = 0, n_dr = 0;
     long long rej = 0, reju = 0;
+    long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};            // phase cycles (thread 0): rng, propose, ss1, dr, state, cov, chol, -
+    long long tprev = clock64();
+#define TC_PHASE(i) do { const long long tn__ = clock64(); pc[i] += tn__ - tprev; tprev = tn__; } while (0)
     // s2chain statistics over ALL rows (TranscriptionCycleMCMC.m:302-303), thread 0
     double s2_sum = sigma2, sq_mean = sqrt(sigma2), sq_M2 = 0.0, s2_cnt = 1.0;
     double wcnt = 0.0;                                     // rows folded into the summaries
@@ -241,13 +244,13 @@ __global__ void __launch_bounds__(DRAM_THREADS) dram_kernel(const __grid_constan
     for (int k = 1; k < a.nsimu && !bad0; ++k) {
         const int isimu = k + 1;
         // ---- 1. randomness of this step: z1, z2 (interleaved), u1, u2, chi2
-        double u1, u2, chi2v = 0.0;
+        double u1, u2;
         if (a.replay) {
             const size_t g = ((size_t)ch * a.nsimu + k) * ld;
             for (int i = tid; i < npar; i += nt) { cs.zz[2 * i] = a.z1[g + i]; cs.zz[2 * i + 1] = a.z2[g + i]; }
             u1 = a.u1[(size_t)ch * a.nsimu + k];
             u2 = a.u2[(size_t)ch * a.nsimu + k];
-            if (tid == 0) chi2v = a.chi2[(size_t)ch * a.nsimu + k];
+            if (tid == nt - 1) s_sc[2 + (k & 1)] = a.chi2[(size_t)ch * a.nsimu + k];
         } else {
             for (int q = tid; 2 * q < npar; q += nt) {
                 double za, zb;
@@ -261,9 +264,12 @@ __global__ void __launch_bounds__(DRAM_THREADS) dram_kernel(const __grid_constan
             const u32x4 ru = draw(a.seed, uid, k, RK_U, 0);
             u1 = u01(ru.x, ru.y);
             u2 = u01(ru.z, ru.w);
-            if (tid == 0 && a.updatesigma) chi2v = chi2_draw(a.seed, uid, k, a.N0 + 2.0 * N);
+            // the chi-square draw does not depend on the chain state: the last warp makes it while
+            // the others generate normals; it is consumed after the accept/reject decision
+            if (tid == nt - 1 && a.updatesigma) s_sc[2 + (k & 1)] = chi2_draw(a.seed, uid, k, a.N0 + 2.0 * N);
         }
         __syncthreads();
+        TC_PHASE(0);
         // ---- 2. both proposals in one pass over R:  y1 = x + z1 R,  y2 = x + z2 R / drscale
         double pr1 = 0.0, pr2 = 0.0;
         int oob = 0;
@@ -274,13 +280,28 @@ __global__ void __launch_bounds__(DRAM_THREADS) dram_kernel(const __grid_constan
                 s1 = cs.zz[2 * j] * cs.rdiag[j];
                 s2 = cs.zz[2 * j + 1] * cs.rdiag[j];
             } else {
-                int rk = 0;
-                for (int i = 0; i <= j; ++i) {
-                    const double r = cs.R[rk + (j - i)];
-                    s1 = fma(cs.zz[2 * i], r, s1);
-                    s2 = fma(cs.zz[2 * i + 1], r, s2);
-                    rk += npar - i;
+                // column j of the packed upper factor: R(i,j) at rk(i) + j - i; four independent
+                // partial sums per proposal break the FMA dependence chain
+                double p1[4] = {0, 0, 0, 0}, p2[4] = {0, 0, 0, 0};
+                int rk = j, i = 0;                         // rk = pidx(i, j)
+                for (; i + 3 <= j; i += 4) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const double r = cs.R[rk];
+                        const double2 z = *reinterpret_cast<const double2 *>(cs.zz + 2 * (i + u));
+                        p1[u] = fma(z.x, r, p1[u]);
+                        p2[u] = fma(z.y, r, p2[u]);
+                        rk += npar - (i + u) - 1;
+                    }
                 }
+                for (; i <= j; ++i) {
+                    const double r = cs.R[rk];
+                    p1[0] = fma(cs.zz[2 * i], r, p1[0]);
+                    p2[0] = fma(cs.zz[2 * i + 1], r, p2[0]);
+                    rk += npar - i - 1;
+                }
+                s1 = (p1[0] + p1[1]) + (p1[2] + p1[3]);
+                s2 = (p2[0] + p2[1]) + (p2[2] + p2[3]);
             }
             const double xj = cs.x[j], a1 = xj + s1, a2 = xj + s2 * inv_dr;
             cs.y1[j] = a1;
@@ -295,6 +316,7 @@ __global__ void __launch_bounds__(DRAM_THREADS) dram_kernel(const __grid_constan
         block_sum2(pr1, pr2, w.red);
         const int oob1 = __syncthreads_or(oob & 1), oob2 = __syncthreads_or(oob & 2);
 
+        TC_PHASE(1);
         // ---- 3. stage 1
         int fl = 0, accept = 0;
         double ss1, a12;
@@ -311,6 +333,7 @@ __global__ void __launch_bounds__(DRAM_THREADS) dram_kernel(const __grid_constan
         }
         const double *newp = cs.y1;
         double ssn = ss1, prin = pr1;
+        TC_PHASE(2);
         // ---- 4. delayed rejection with R/drscale
         if (!accept && a.ntry >= 2) {
             fl |= TC_FL_DR; ++n_dr;
@@ -339,6 +362,7 @@ __global__ void __launch_bounds__(DRAM_THREADS) dram_kernel(const __grid_constan
             }
         }
         __syncthreads();
+        TC_PHASE(3);
         if (accept) {
             fl |= TC_FL_ACCEPT;
             for (int i = tid; i < npar; i += nt) cs.x[i] = newp[i];
@@ -346,9 +370,7 @@ __global__ void __launch_bounds__(DRAM_THREADS) dram_kernel(const __grid_constan
         } else { ++rej; ++reju; }
         // ---- 5. sigma2 | ss ~ inv-chi2 (thread 0 draws, broadcast)
         if (a.updatesigma) {
-            if (tid == 0) s_sc[0] = (a.N0 * a.S20 + ss) / chi2v;
-            __syncthreads();
-            sigma2 = s_sc[0];
+            sigma2 = (a.N0 * a.S20 + ss) / s_sc[2 + (k & 1)];
         } else __syncthreads();
         if (tid == 0) {
             s2_cnt += 1.0;
@@ -360,6 +382,7 @@ __global__ void __launch_bounds__(DRAM_THREADS) dram_kernel(const __grid_constan
         }
         emit_row(k);
 
+        TC_PHASE(4);
         // ---- 6. adaptation
         if (a.adaptint > 0 && isimu % a.adaptint == 0) {
             __syncthreads();
@@ -427,6 +450,7 @@ __global__ void __launch_bounds__(DRAM_THREADS) dram_kernel(const __grid_constan
                 cov_n += m;
                 __syncthreads();
             }
+            TC_PHASE(5);
             if (isimu < a.burnintime) {
                 const double rate = a.burnin_cumulative ? (double)rej / isimu : (double)reju / a.adaptint;
                 double f = 1.0;
@@ -457,6 +481,7 @@ __global__ void __launch_bounds__(DRAM_THREADS) dram_kernel(const __grid_constan
                 __syncthreads();
                 reju = 0;
             }
+            TC_PHASE(6);
         }
     }
 
@@ -476,6 +501,7 @@ __global__ void __launch_bounds__(DRAM_THREADS) dram_kernel(const __grid_constan
             c[TC_CNT_SS_EVALS] = n_ss; c[TC_CNT_ACC_STAGE1] = n_acc1; c[TC_CNT_ACC_STAGE2] = n_acc2;
             c[TC_CNT_OUT_OF_BOUNDS] = n_oob; c[TC_CNT_ADAPTATIONS] = n_adapt;
             c[TC_CNT_CHOL_FAIL] = n_cholfail; c[TC_CNT_DR_TRIES] = n_dr; c[TC_CNT_STATUS] = bad0 ? 1 : 0;
+            for (int i = 0; i < 8; ++i) c[TC_CNT_CYCLES0 + i] = pc[i];
         }
     }
 }
