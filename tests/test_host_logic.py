@@ -1,0 +1,142 @@
+"""CPU tests of the host-side mirror: option parsing, per-cell set-up constants, construct registry,
+.mat layouts, and the world_size-2 (gloo) sharding logic."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from transcriptioncycleinference_b200 import constructs, distributed, mcmc, setup_cell
+
+
+def test_defaults_match_reference_code_not_readme():
+    # src/TranscriptionCycleMCMC.m:36-45 (README says numParPools=0, n_steps=200000, t_end=0: SURVEY 0.1 #1)
+    o = mcmc.parse_varargin(())
+    assert (o["numParPools"], o["n_burn"], o["n_steps"], o["ratePriorWidth"]) == (8, 10000, 20000, 50.0)
+    assert o["t_start"] == 0 and o["t_end"] == np.inf and o["loadPrevious"] is False
+    assert o["construct"] == "P2P-MS2v5-LacZ-PP7v4"
+
+
+def test_varargin_case_insensitive_and_presence_only_loadprevious():
+    o = mcmc.parse_varargin(("N_STEPS", 500, "n_Burn", 100, "LOADPREVIOUS", False, "bogus", 3, "t_end", 25.0))
+    assert o["n_steps"] == 500 and o["n_burn"] == 100 and o["t_end"] == 25.0
+    assert o["loadPrevious"] is True          # the value after the name is ignored (:72-74)
+    with pytest.raises(IndexError):
+        mcmc.parse_varargin(("n_steps",))
+
+
+def test_truncate_semantics():
+    t = np.array([0.0, 1.0, 2.0, 3.0, 4.0]); y = np.arange(5.0)
+    a, b, c = setup_cell.truncate(t, y, y, 1.0, 3.0)       # t >= 1 first, t < 3 last
+    assert list(a) == [1.0, 2.0] and list(b) == [1.0, 2.0]
+    a, _, _ = setup_cell.truncate(t, y, y, 0.0, np.inf)
+    assert a.size == 5
+    a, _, _ = setup_cell.truncate(t, y, y, 10.0, np.inf)
+    assert a.size == 0
+
+
+def test_setup_constants_appendix_a():
+    t = np.array([0.0, 0.3, 0.5, 0.9])
+    rng = np.random.default_rng(0)
+    x0 = setup_cell.initial_state(4, rng)
+    assert x0.size == 11 and 1 <= x0[0] <= 3 and 0 <= x0[1] <= 4 and 0 <= x0[2] <= 4
+    assert x0[3] == 10 and x0[4] == 5 and 0 <= x0[5] <= 1 and x0[6] == 15
+    J0 = setup_cell.proposal_variances(t)
+    np.testing.assert_allclose(J0, [0.05, 0.1, 0.4, 1, 1, 0.05, 0.5, 0.5, 0.5, 0.5, 0.5])
+    assert setup_cell.proposal_variances(t, True)[0] == 1e-7
+    lo, hi, mu, sg = setup_cell.bounds_and_priors(4, x0, 50.0)
+    np.testing.assert_array_equal(lo, [0, 0, 0, 0, 0, 0, 0, -30, -30, -30, -30])
+    np.testing.assert_array_equal(hi, [10, 20, 10, 50, 50, 1, 40, 30, 30, 30, 30])
+    assert np.all(np.isinf(sg[:7])) and np.all(sg[7:] == 50) and np.all(mu == 0)
+    lo, hi, _, _ = setup_cell.bounds_and_priors(4, x0, 50.0, load_previous=True)
+    assert abs(lo[0] - (x0[0] - 1e-5)) < 1e-15 and abs(hi[0] - (x0[0] + 1e-5)) < 1e-15
+
+
+def test_construct_registry():
+    c = constructs.get_construct("P2P-MS2v5-LacZ-PP7v4")
+    assert c["L_MS2"] == 6.626 and c["MS2_start"] == [0.024] and c["PP7_end"] == [5.758] and c["MS2_loopn"] == [24.0]
+    with pytest.raises(NameError):
+        constructs.get_construct("no-such-construct")
+    constructs.register_construct("two-sets", 5.0, 5.5, [0.1, 2.0], [1.0, 3.0], [24, 12], [3.2, 4.0], [3.9, 4.9], [24, 24])
+    cc = constructs.to_c("two-sets")
+    assert cc.nsets == 2 and cc.ms2_loopn[1] == 12.0 and cc.L_pp7 == 5.5
+    with pytest.raises(ValueError):
+        constructs.register_construct("bad", 5.0, 5.0, [0.1, 2.0], [1.0], [24, 24], [3.0, 4.0], [3.9, 4.9], [24, 24])
+
+
+def test_matlab_date_and_struct_layout(tmp_path):
+    import datetime
+    import scipy.io as sio
+    assert mcmc.matlab_date(datetime.date(2020, 10, 28)) == "28-Oct-2020"
+    recs = [{f: np.float64(i) for f in mcmc.RESULT_FIELDS} for i in range(3)]
+    for r in recs:
+        r["mean_dR"] = np.zeros((1, 5)); r["sigma_dR"] = np.ones((1, 5))
+    p = tmp_path / "x.mat"
+    sio.savemat(p, dict(MCMCresults=mcmc._struct_array(mcmc.RESULT_FIELDS, recs), DatasetName="TestData"))
+    m = sio.loadmat(p, mat_dtype=True)
+    assert m["MCMCresults"].shape == (1, 3)
+    assert m["MCMCresults"].dtype.names == mcmc.RESULT_FIELDS       # field ORDER of :151-155
+    assert m["MCMCresults"][0, 1]["mean_dR"].shape == (1, 5)
+    assert str(m["DatasetName"][0]) == "TestData"
+
+
+def test_output_field_order_matches_reference_fixture(results_npz, chains_npz):
+    assert tuple(results_npz["field_order"]) == mcmc.RESULT_FIELDS
+    assert tuple(results_npz["plot_field_order"]) == mcmc.PLOT_FIELDS
+    assert tuple(chains_npz["chain_field_order"]) == mcmc.CHAIN_FIELDS
+
+
+def test_partition_contiguous_and_balanced(cells_npz):
+    N = cells_npz["N"]
+    cc = np.repeat(np.arange(299), 64)
+    w = distributed.chain_work(N[cc])
+    for parts in (1, 2, 4, 8):
+        p = distributed.partition(w, parts)
+        assert p[0][0] == 0 and p[-1][1] == cc.size
+        assert all(p[i][1] == p[i + 1][0] for i in range(parts - 1))
+        loads = np.array([w[s:e].sum() for s, e in p])
+        assert loads.max() / loads.mean() < 1.02
+    p = distributed.partition(np.ones(3), 8)                 # fewer units than parts
+    assert sum(e - s for s, e in p) == 3 and all(e - s in (0, 1) for s, e in p)
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    N_of_cell = np.array([5, 9, 7, 12, 6])
+    cc = np.array([0, 0, 1, 2, 3, 3, 4], dtype=np.int32)
+    uid = np.arange(100, 107, dtype=np.uint64)
+    arrays = [np.arange(7 * 3, dtype=np.float64).reshape(7, 3)]
+
+    def run_local(c, arrs, u):           # stand-in for Cells.mcmc_run: results depend only on the chain identity
+        return dict(mean=arrs[0] * 2 + u[:, None].astype(np.float64), counters=np.stack([c, u.astype(np.int64)], 1),
+                    owner=np.full(len(c), rank))
+    out = distributed.fit_sharded(run_local, cc, N_of_cell, arrays, uid, rank, world)
+    q.put((rank, out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_fit_world2_gloo():
+    """world_size 2 over gloo: every rank ends with the full, correctly ordered result, identical to
+    the single-rank result (the data path has no collective; only the final gather)."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    N_of_cell = np.array([5, 9, 7, 12, 6]); cc = np.array([0, 0, 1, 2, 3, 3, 4], dtype=np.int32)
+    uid = np.arange(100, 107, dtype=np.uint64); arr = np.arange(21, dtype=np.float64).reshape(7, 3)
+    expect = arr * 2 + uid[:, None].astype(np.float64)
+    for r in (0, 1):
+        np.testing.assert_array_equal(res[r]["mean"], expect)
+        np.testing.assert_array_equal(res[r]["counters"][:, 0], cc)
+        assert set(res[r]["owner"]) == {0, 1}               # both ranks did work
+        assert np.all(np.diff(res[r]["owner"]) >= 0)         # contiguous blocks
