@@ -1,9 +1,9 @@
 // tc_device.cuh — device-side building blocks of libtcmcmc (sm_100a).
 //
 //  * Philox4x32-10 counter-based RNG, Box-Muller normals, Marsaglia-Tsang chi-square
-//  * CTA-wide reductions on warp shuffles
-//  * the forward model + residual sum of squares for one (cell, theta), evaluated cooperatively by
-//    one CTA out of shared memory.  Behavioural spec: SURVEY.md Appendix B.2, i.e.
+//  * warp-shuffle reductions
+//  * the forward model + residual sum of squares for one (cell, theta), evaluated by ONE WARP (no
+//    block barriers), scratch in shared memory.  Behavioural spec: SURVEY.md Appendix B.2, i.e.
 //      src/SumofSquaresFunction_TranscriptionCycleMCMC.m:28-64,
 //      src/dependencies/ConstantElongationSim.m:33-67,
 //      src/GetFluorFromPolPos.m:18-70            (paths relative to /root/reference).
@@ -18,8 +18,13 @@
 #include "../../include/tcmcmc.h"
 
 namespace tc {
+#ifdef TC_SS_PROFILE
+__device__ long long tc_ss_prof[8];
+#endif
 
 // ------------------------------------------------------------------------------------------ RNG
+__device__ double tc_exp(double x);
+__device__ double tc_log(double x);
 struct u32x4 { uint32_t x, y, z, w; };
 
 __host__ __device__ __forceinline__ void philox_round(uint32_t &c0, uint32_t &c1, uint32_t &c2,
@@ -50,7 +55,7 @@ __host__ __device__ __forceinline__ u32x4 philox4x32_10(uint32_t c0, uint32_t c1
 enum { RK_Z1 = 0, RK_Z2 = 1, RK_U = 2, RK_CHI2 = 3 };
 
 // counter = (slot, step, uid_lo, uid_hi[23:0] << 8 | kind); key = seed
-__device__ __forceinline__ u32x4 draw(uint64_t seed, uint64_t uid, uint32_t step, uint32_t kind,
+__device__ __noinline__ u32x4 draw(uint64_t seed, uint64_t uid, uint32_t step, uint32_t kind,
                                       uint32_t slot)
 {
     return philox4x32_10(slot, step, (uint32_t)uid, ((uint32_t)(uid >> 32) << 8) | kind,
@@ -65,10 +70,10 @@ __device__ __forceinline__ double u01(uint32_t hi, uint32_t lo)
 }
 
 // two standard normals from one Philox block (Box-Muller, FP64)
-__device__ __forceinline__ void normal_pair(const u32x4 &r, double &z0, double &z1)
+__device__ __noinline__ void normal_pair(const u32x4 &r, double &z0, double &z1)
 {
     const double ua = u01(r.x, r.y), ub = u01(r.z, r.w);
-    const double rad = sqrt(-2.0 * log(ua));
+    const double rad = sqrt(-2.0 * tc_log(ua));
     double s, c;
     sincospi(2.0 * ub, &s, &c);
     z0 = rad * c;
@@ -76,7 +81,7 @@ __device__ __forceinline__ void normal_pair(const u32x4 &r, double &z0, double &
 }
 
 // chi-square(dof) = 2*Gamma(dof/2) by Marsaglia-Tsang (dof >= 2); attempt t uses slots 2t, 2t+1.
-__device__ inline double chi2_draw(uint64_t seed, uint64_t uid, uint32_t step, double dof)
+__device__ __noinline__ double chi2_draw(uint64_t seed, uint64_t uid, uint32_t step, double dof)
 {
     const double a = 0.5 * dof;
     const double d = a - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
@@ -91,10 +96,15 @@ __device__ inline double chi2_draw(uint64_t seed, uint64_t uid, uint32_t step, d
         const double u = u01(r1.x, r1.y);
         const double x2 = x * x;
         if (u < 1.0 - 0.0331 * x2 * x2) return 2.0 * d * v;
-        if (log(u) < 0.5 * x2 + d * (1.0 - v + log(v))) return 2.0 * d * v;
+        if (tc_log(u) < 0.5 * x2 + d * (1.0 - v + tc_log(v))) return 2.0 * d * v;
     }
     return 2.0 * d;   // unreachable in practice (acceptance > 0.95 per attempt)
 }
+
+// One out-of-line copy of the long libdevice sequences: the sampler's hot loop has to stay inside
+// the instruction cache (ncu: icc hit rate 58 %, stall_no_instruction dominant before this).
+__device__ __noinline__ double tc_exp(double x) { return exp(x); }
+__device__ __noinline__ double tc_log(double x) { return log(x); }
 
 // ------------------------------------------------------------------------------- reductions
 __device__ __forceinline__ double warp_sum(double v)
@@ -102,20 +112,6 @@ __device__ __forceinline__ double warp_sum(double v)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
-}
-
-// Sum of (a, b) over the CTA, result in every thread.  red: >= 2*32 doubles of shared memory.
-__device__ __forceinline__ void block_sum2(double &a, double &b, double *red)
-{
-    a = warp_sum(a);
-    b = warp_sum(b);
-    const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
-    __syncthreads();                      // red[] free to overwrite
-    if ((threadIdx.x & 31) == 0) { red[2 * w] = a; red[2 * w + 1] = b; }
-    __syncthreads();
-    double sa = 0, sb = 0;
-    for (int i = 0; i < nw; ++i) { sa += red[2 * i]; sb += red[2 * i + 1]; }
-    a = sa; b = sb;
 }
 
 // ------------------------------------------------------------------------- shared-memory views
@@ -128,13 +124,12 @@ struct CellView {        // one cell's constants, staged in shared memory
     double *iw;          // interp1 weight of experimental time j [N]
     int *ik;             // interp1 bracketing index (-1: outside) [N]
 };
-struct Work {            // per-evaluation scratch in shared memory, each [N+1]
-    double *rd, *K, *G1, *G2, *F1, *F2;
+struct Work {            // per-evaluation scratch in shared memory, each [N+2]
+    double *K, *n, *G1, *G2, *F1, *F2;
     int *thr;            // 8 lag thresholds
-    double *red;         // 64 doubles for reductions
 };
 
-__host__ __device__ inline int work_doubles(int N) { return 6 * (N + 2) + 64 + 4; }
+__host__ __device__ inline int work_doubles(int N) { return 6 * (N + 2) + 4 + 1; }
 __host__ __device__ inline int cell_doubles(int N) { return 5 * (N + 1) + (N + 2) / 2 + 1; }
 
 __device__ inline void carve_cell(double *&p, int N, CellView &cv)
@@ -149,14 +144,14 @@ __device__ inline void carve_cell(double *&p, int N, CellView &cv)
 }
 __device__ inline void carve_work(double *&p, int N, Work &w)
 {
-    w.rd = p; p += N + 2;
+    p += (reinterpret_cast<uintptr_t>(p) >> 3) & 1;       // 16-byte align (thr is read as int4)
+    w.thr = reinterpret_cast<int *>(p); p += 4;
     w.K = p; p += N + 2;
+    w.n = p; p += N + 2;
     w.G1 = p; p += N + 2;
     w.G2 = p; p += N + 2;
     w.F1 = p; p += N + 2;
     w.F2 = p; p += N + 2;
-    w.red = p; p += 64;
-    w.thr = reinterpret_cast<int *>(p); p += 4;
 }
 
 struct CellsDev {        // device-resident packed dataset (one per device)
@@ -172,10 +167,10 @@ __device__ inline void load_cell(const CellsDev &cd, int cid, bool raw_grid, Cel
 {
     const int N = cv.N;
     const long long o = cd.off[cid];
-    const double *g = raw_grid ? cd.t : cd.tg;
+    const double *gr = raw_grid ? cd.t : cd.tg;
     const double *dg = raw_grid ? cd.dtraw : cd.dtg;
     for (int i = threadIdx.x; i < N; i += blockDim.x) {
-        cv.tg[i] = g[o + i];
+        cv.tg[i] = gr[o + i];
         cv.dtg[i] = dg[o + i];
         cv.ms2[i] = cd.ms2[o + i];
         cv.pp7[i] = cd.pp7[o + i];
@@ -183,6 +178,21 @@ __device__ inline void load_cell(const CellsDev &cd, int cid, bool raw_grid, Cel
         cv.ik[i] = cd.ik[o + i];
     }
     cv.d = cd.dmean[cid];
+}
+
+// a view straight onto the device-resident dataset (no staging: the batched ssfun kernel reads every
+// element once or twice per evaluation)
+__device__ inline void view_cell(const CellsDev &cd, int cid, bool raw_grid, CellView &cv)
+{
+    const long long o = cd.off[cid];
+    cv.N = cd.N[cid];
+    cv.d = cd.dmean[cid];
+    cv.tg = const_cast<double *>((raw_grid ? cd.t : cd.tg) + o);
+    cv.dtg = const_cast<double *>((raw_grid ? cd.dtraw : cd.dtg) + o);
+    cv.ms2 = const_cast<double *>(cd.ms2 + o);
+    cv.pp7 = const_cast<double *>(cd.pp7 + o);
+    cv.iw = const_cast<double *>(cd.iw + o);
+    cv.ik = const_cast<int *>(cd.ik + o);
 }
 
 // ------------------------------------------------------------------------- forward model pieces
@@ -196,48 +206,77 @@ __device__ __forceinline__ double loop_response(double p, double s, double e, do
     return val;
 }
 
-// Loaded-polymerase counts.  K[0] = 0, K[i+1] = floor(counter after step i)
-// (ConstantElongationSim.m:53-61).  The running sum is taken in the reference's order with
-// separately rounded products (no FMA contraction), because floor() is discontinuous.
-// Fast path: warp 0 scans in parallel; if any partial sum lands within 1e-7 of an integer — where a
-// different association could flip a floor — lane 0 redoes the scan sequentially.  Both paths give
-// the same integers as the sequential reference order.
-__device__ inline void scan_counts(int N, const double *rd, double *K, bool force_sequential)
+// per-step loading increment rho_i*delta_i; zero before onset (the reference `continue`s, which
+// leaves the counter unchanged)                      ConstantElongationSim.m:33-36,57-60
+__device__ __forceinline__ double load_increment(const CellView &cv, const double *th, int i, double R, double ton)
 {
-    const int lane = threadIdx.x & 31;               // called by ONE full warp
-    const int n = N - 1;                       // increments rd[0..n-1]
+    double r = R + th[7 + i];                                 // SumofSquares...m:45
+    r = r < 0.0 ? 0.0 : r;
+    return (cv.tg[i] < ton) ? 0.0 : __dmul_rn(r, cv.dtg[i]);
+}
+
+// the reference's own order: one lane, sequential (rare fallback; kept out of line)
+__device__ __noinline__ void scan_counts_sequential(const CellView &cv, const double *th, double R, double ton, double *K)
+{
+    double c = 0.0;
+    K[0] = 0.0;
+#pragma unroll 1
+    for (int i = 0; i < cv.N - 1; ++i) {
+        c = __dadd_rn(c, load_increment(cv, th, i, R, ton));
+        K[i + 1] = floor(c);
+    }
+}
+
+// Loaded-polymerase counts by ONE warp.  K[0] = 0, K[i+1] = floor(counter after step i), n[i] =
+// K[i+1]-K[i] (cohort loaded in step i)               ConstantElongationSim.m:53-61
+// floor() is discontinuous, so the running sum must give the same integers as the reference's
+// sequential order with separately rounded products (no FMA contraction).  Fast path: 4 interleaved
+// warp scans per pass; if any partial sum lands within 1e-7 of an integer — where a different
+// association could flip a floor — lane 0 redoes the sum sequentially.  Error bound of either
+// order: (N-1) * eps * max(c) < 400 * 1.1e-16 * 3e4 << 1e-7, so the two paths agree otherwise.
+__device__ inline void scan_counts(const CellView &cv, const double *th, double R, double ton, double *K,
+                                   double *nco, bool force_sequential)
+{
+    const int lane = threadIdx.x & 31;
+    const int n = cv.N - 1;                        // increments i = 0..n-1
     bool redo = force_sequential;
     if (!force_sequential) {
-        const int chunk = (n + 31) >> 5;
-        const int b = lane * chunk, e = min(b + chunk, n);
-        double loc = 0.0;
-        for (int i = b; i < e; ++i) loc = __dadd_rn(loc, rd[i]);
-        double incl = loc;                     // inclusive scan of chunk sums over lanes
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const double up = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl = __dadd_rn(incl, up);
-        }
-        double c = __dadd_rn(incl, -loc);      // exclusive prefix for this lane
+        double carry = 0.0;
         bool risky = false;
-        for (int i = b; i < e; ++i) {
-            c = __dadd_rn(c, rd[i]);
-            const double f = floor(c);
-            // c == 0: every increment so far is exactly 0 (they are all >= 0) -> exact in any order
-            risky |= (c != 0.0) && ((c - f < 1e-7) || (f + 1.0 - c < 1e-7));
-            K[i + 1] = f;
+#pragma unroll 1
+        for (int r0 = 0; r0 < n; r0 += 128) {
+            double v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = r0 + 32 * u + lane;
+                v[u] = i < n ? load_increment(cv, th, i, R, ton) : 0.0;
+            }
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const double up = __shfl_up_sync(0xffffffffu, v[u], o);
+                    if (lane >= o) v[u] = __dadd_rn(v[u], up);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = r0 + 32 * u + lane;
+                const double c = __dadd_rn(carry, v[u]);
+                const double f = floor(c);
+                // c == 0: every increment so far is exactly 0 (they are all >= 0): exact in any order
+                risky |= (i < n) && (c != 0.0) && ((c - f < 1e-7) || (f + 1.0 - c < 1e-7));
+                if (i < n) K[i + 1] = f;
+                carry = __dadd_rn(carry, __shfl_sync(0xffffffffu, v[u], 31));
+            }
         }
-        redo = __any_sync(0xffffffffu, risky);
         if (lane == 0) K[0] = 0.0;
+        redo = __any_sync(0xffffffffu, risky);
     }
-    if (redo && lane == 0) {
-        double c = 0.0;
-        K[0] = 0.0;
-        for (int i = 0; i < n; ++i) {
-            c = __dadd_rn(c, rd[i]);
-            K[i + 1] = floor(c);
-        }
-    }
+    if (redo && lane == 0) scan_counts_sequential(cv, th, R, ton, K);
+    __syncwarp();
+#pragma unroll 1
+    for (int i = lane; i < n; i += 32) nco[i] = K[i + 1] - K[i];
 }
 
 // smallest lag in [1, N] with v*(d*lag) > x (strict) or >= x; N when none
@@ -256,96 +295,117 @@ __device__ inline int first_lag(double v, double d, double x, int N, bool strict
     return g;
 }
 
-// The residual sum of squares of one (cell, theta) — SumofSquares...m:1-65 — by the whole CTA.
-// th: theta (shared or global).  On return every thread holds SS.  When out1/out2 != nullptr the
-// model curves [A*MS2, PP7] on the model grid are also written there (tc_forward).
-// All threads of the CTA must call this.
-__device__ inline double ss_eval(const tc_construct &C, const CellView &cv, const double *th,
-                                 Work &w, int algo, bool seq_scan, double *out1, double *out2)
+// TC_ALGO_PAIRS: every (cohort i, time j) pair with the literal response at p = v*(t_j - t_i); any grid
+__device__ __noinline__ void rows_pairs(const CellView &cv, Work &w, int s, double v, double s1, double e1, double L1,
+                                        double f1, double b1, double s2, double e2, double L2, double f2, double b2)
 {
-    const int N = cv.N, tid = threadIdx.x, nt = blockDim.x;
-    const double v = th[0], tau = th[1], ton = th[2], b1 = th[3], b2 = th[4], A = th[5], R = th[6];
-
-    // (a) per-step loading increments rho_i*delta_i; zero before onset (the reference `continue`s,
-    //     which leaves the counter unchanged)               ConstantElongationSim.m:33-36,57-60
-    for (int i = tid; i < N - 1; i += nt) {
-        double r = R + th[7 + i];                             // SumofSquares...m:45
-        r = r < 0.0 ? 0.0 : r;
-        w.rd[i] = (cv.tg[i] < ton) ? 0.0 : __dmul_rn(r, cv.dtg[i]);
+    const int N = cv.N, lane = threadIdx.x & 31;
+#pragma unroll 1
+    for (int j = lane; j < N; j += 32) {
+        double a1 = 0.0, a2 = 0.0;
+        const double tj = cv.tg[j];
+#pragma unroll 2
+        for (int i = 0; i < j; ++i) {
+            const double ni = w.n[i];
+            if (ni > 0.0) {
+                const double p = v * (tj - cv.tg[i]);
+                a1 = fma(ni, loop_response(p, s1, e1, L1, f1), a1);
+                a2 = fma(ni, loop_response(p, s2, e2, L2, f2), a2);
+            }
+        }
+        if (s > 0) { a1 += w.F1[j]; a2 += w.F2[j]; }
+        w.F1[j] = a1 < b1 ? b1 : a1;
+        w.F2[j] = a2 < b2 ? b2 : a2;
     }
-    for (int j = tid; j < N; j += nt) { w.F1[j] = 0.0; w.F2[j] = 0.0; }
-    __syncthreads();
+}
 
-    // (b)+(c) warp 0 scans the loading counter while warps 1 and 2 build the response tables of the
-    //     two colours; then every thread sums its time points.  One loop set at a time: the basal
-    //     clamp sits inside the per-set loop in the reference (GetFluorFromPolPos.m:47,57,69).
+#ifdef TC_SS_PROFILE
+#define SS_MARK(i) do { const long long tn__ = clock64(); if (lane == 0) tc_ss_prof[i] += tn__ - tp__; tp__ = tn__; } while (0)
+#else
+#define SS_MARK(i)
+#endif
+
+// The residual sum of squares of one (cell, theta) — SumofSquares...m:1-65 — by ONE WARP.
+// th: theta (shared or global); w: this warp's private scratch.  On return every lane holds SS.
+// When out1/out2 != nullptr the model curves [A*MS2, PP7] on the model grid are also written there
+// (tc_forward).  All 32 lanes must call this.
+__device__ __noinline__ double ss_eval(const tc_construct &C, const CellView &cv, const double *th, Work &w, int algo,
+                                 bool seq_scan, double *out1, double *out2)
+{
+    const int N = cv.N, lane = threadIdx.x & 31;
+    const double v = th[0], tau = th[1], ton = th[2], b1 = th[3], b2 = th[4], A = th[5], R = th[6];
+#ifdef TC_SS_PROFILE
+    long long tp__ = clock64();
+#endif
+    // (a) loaded-polymerase counts K and cohort sizes n
+    scan_counts(cv, th, R, ton, w.K, w.n, seq_scan);
+    __syncwarp();
+    SS_MARK(0);
+    // (b) fluorescence per time point, one loop set at a time: the basal clamp sits inside the
+    //     per-set loop in the reference (GetFluorFromPolPos.m:47,57,69)
     const double tv = tau * v;
     const double L1 = C.L_ms2 + tv, L2 = C.L_pp7 + tv;        // :19-20
-    const int warp = tid >> 5, lane = tid & 31;
     for (int s = 0; s < C.nsets; ++s) {
         const double s1 = C.ms2_start[s], e1 = C.ms2_end[s], f1 = C.ms2_loopn[s] / 24.0;
         const double s2 = C.pp7_start[s], e2 = C.pp7_end[s], f2 = C.pp7_loopn[s] / 24.0;
-        if (s == 0 && warp == 0) scan_counts(N, w.rd, w.K, seq_scan);
         if (algo == TC_ALGO_TOEPLITZ) {
             // lag thresholds of the piecewise response, by exact predicate on p = v*(d*lag):
-            // ramp = [la, le), plateau = [lb, lL)
-            if (warp == 1 || warp == 2) {
-                const bool c2 = warp == 2;
-                const double xs = c2 ? s2 : s1, xe = c2 ? e2 : e1, xL = c2 ? L2 : L1, xf = c2 ? f2 : f1;
-                int *thr = w.thr + (c2 ? 4 : 0);
-                if (lane < 4) {
-                    const double x = lane == 0 ? xs : (lane == 3 ? xL : xe);
-                    thr[lane] = first_lag(v, cv.d, x, N, (lane & 1) == 0);   // >s, >=e, >e, >=L
-                }
-                __syncwarp();
-                const int la = thr[0], le = thr[1];
-                double *G = c2 ? w.G2 : w.G1;
-                const double sc = xf / (xe - xs);
-                for (int lag = la + lane; lag < le; lag += 32) G[lag] = (v * (cv.d * (double)lag) - xs) * sc;
+            // ramp = [la, le), plateau = [lb, lL); lanes 0-3: MS2, lanes 4-7: PP7
+            if (lane < 8) {
+                const bool c2 = lane >= 4;
+                const int q = lane & 3;
+                const double x = q == 0 ? (c2 ? s2 : s1) : (q == 3 ? (c2 ? L2 : L1) : (c2 ? e2 : e1));
+                w.thr[lane] = first_lag(v, cv.d, x, N, (q & 1) == 0);        // >s, >=e, >e, >=L
             }
-            __syncthreads();
-            const int la1 = w.thr[0], le1 = w.thr[1], lb1 = w.thr[2], lL1 = w.thr[3];
-            const int la2 = w.thr[4], le2 = w.thr[5], lb2 = w.thr[6], lL2 = w.thr[7];
-            for (int j = tid; j < N; j += nt) {
+            __syncwarp();
+            const int4 t1 = *reinterpret_cast<const int4 *>(w.thr), t2 = *reinterpret_cast<const int4 *>(w.thr + 4);
+            const int la1 = t1.x, le1 = t1.y, lb1 = t1.z, lL1 = t1.w;
+            const int la2 = t2.x, le2 = t2.y, lb2 = t2.z, lL2 = t2.w;
+            {   // ramp part of the per-lag response table
+                const double sc1 = f1 / (e1 - s1), sc2 = f2 / (e2 - s2);
+#pragma unroll 1
+                for (int lag = la1 + lane; lag < le1; lag += 32) w.G1[lag] = (v * (cv.d * (double)lag) - s1) * sc1;
+#pragma unroll 1
+                for (int lag = la2 + lane; lag < le2; lag += 32) w.G2[lag] = (v * (cv.d * (double)lag) - s2) * sc2;
+            }
+            __syncwarp();
+            SS_MARK(1);
+#pragma unroll 1
+            for (int j = lane; j < N; j += 32) {
                 double a1 = 0.0, a2 = 0.0;
-                const int h1 = min(le1 - 1, j), h2 = min(le2 - 1, j);
-                for (int lag = la1; lag <= h1; ++lag)
-                    a1 = fma(w.K[j - lag + 1] - w.K[j - lag], w.G1[lag], a1);
-                for (int lag = la2; lag <= h2; ++lag)
-                    a2 = fma(w.K[j - lag + 1] - w.K[j - lag], w.G2[lag], a2);
+                const int len1 = min(le1 - 1, j) - la1 + 1, len2 = min(le2 - 1, j) - la2 + 1;
+                const int len = max(len1, len2);
+                const double *n1p = w.n + (j - la1), *n2p = w.n + (j - la2);
+                const double *g1p = w.G1 + la1, *g2p = w.G2 + la2;
+#pragma unroll 2
+                for (int t = 0; t < len; ++t) {            // the two colours interleaved for ILP
+                    if (t < len1) a1 = fma(n1p[-t], g1p[t], a1);
+                    if (t < len2) a2 = fma(n2p[-t], g2p[t], a2);
+                }
                 // plateau: cohorts with lag in [lb, lL) are whole polymerases -> exact count
                 if (j >= lb1 && lb1 < lL1) a1 = fma(f1, w.K[j - lb1 + 1] - w.K[max(j - lL1 + 1, 0)], a1);
                 if (j >= lb2 && lb2 < lL2) a2 = fma(f2, w.K[j - lb2 + 1] - w.K[max(j - lL2 + 1, 0)], a2);
-                double m1 = w.F1[j] + a1, m2 = w.F2[j] + a2;
-                w.F1[j] = m1 < b1 ? b1 : m1;                  // :57
-                w.F2[j] = m2 < b2 ? b2 : m2;                  // :69
+                if (s > 0) { a1 += w.F1[j]; a2 += w.F2[j]; }
+                w.F1[j] = a1 < b1 ? b1 : a1;                  // :57
+                w.F2[j] = a2 < b2 ? b2 : a2;                  // :69
             }
         } else {
-            __syncthreads();
-            for (int j = tid; j < N; j += nt) {
-                double a1 = 0.0, a2 = 0.0;
-                const double tj = cv.tg[j];
-                for (int i = 0; i < j; ++i) {
-                    const double ni = w.K[i + 1] - w.K[i];
-                    if (ni > 0.0) {
-                        const double p = v * (tj - cv.tg[i]);
-                        a1 = fma(ni, loop_response(p, s1, e1, L1, f1), a1);
-                        a2 = fma(ni, loop_response(p, s2, e2, L2, f2), a2);
-                    }
-                }
-                double m1 = w.F1[j] + a1, m2 = w.F2[j] + a2;
-                w.F1[j] = m1 < b1 ? b1 : m1;
-                w.F2[j] = m2 < b2 ? b2 : m2;
-            }
+            SS_MARK(1);
+            rows_pairs(cv, w, s, v, s1, e1, L1, f1, b1, s2, e2, L2, f2, b2);
         }
-        __syncthreads();
+        __syncwarp();
+        SS_MARK(2);
     }
-    if (out1) for (int j = tid; j < N; j += nt) { out1[j] = A * w.F1[j]; out2[j] = w.F2[j]; }
+    if (out1) {
+#pragma unroll 1
+        for (int j = lane; j < N; j += 32) { out1[j] = A * w.F1[j]; out2[j] = w.F2[j]; }
+    }
 
-    // (d) MS2 *= A, interp1 back to the experimental times, NaN-skipping residual sum of squares
+    // (c) MS2 *= A, interp1 back to the experimental times, NaN-skipping residual sum of squares
     //     SumofSquares...m:51-64
-    double acc = 0.0, dummy = 0.0;
-    for (int j = tid; j < N; j += nt) {
+    double acc = 0.0;
+#pragma unroll 1
+    for (int j = lane; j < N; j += 32) {
         const int k = cv.ik[j];
         if (k >= 0) {
             const double wj = cv.iw[j];
@@ -356,7 +416,10 @@ __device__ inline double ss_eval(const tc_construct &C, const CellView &cv, cons
             if (r2 == r2) acc += r2 * r2;
         }
     }
-    block_sum2(acc, dummy, w.red);
+    SS_MARK(3);
+    acc = warp_sum(acc);
+    SS_MARK(4);
+    __syncwarp();
     return acc;
 }
 

@@ -36,9 +36,12 @@ static int fail(int code, const std::string &msg)
             return fail(TC_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));       \
     } while (0)
 
-#define DRAM_THREADS 128
-#define SS_THREADS 128
-#define COV_RC 8          // rows of the chain block staged per pass of the scatter update
+#define DRAM_THREADS 256   // 8 warps; warp w simulates future step k+w of the chain speculatively
+#define SPEC 8             // steps per speculative batch (= warps per CTA)
+#define SS_WARPS 8
+#define SS_THREADS (32 * SS_WARPS)
+#define COV_RC 8           // rows of the chain block staged per pass of the scatter update
+#define COV_TPT 3          // 4x4 covariance tiles per thread (3*256 >= 595 tiles at npar = 136)
 
 // packed upper-triangular row-major index of (i, j), j >= i
 __host__ __device__ __forceinline__ int pidx(int n, int i, int j) { return i * n - (i * (i - 1)) / 2 + (j - i); }
@@ -50,30 +53,27 @@ struct SsArgs {
     long long nbatch;
     const int *cell_id;
     const double *theta;
-    int ld, algo, raw_grid, ldo;
+    int ld, algo, raw_grid, ldo, wsz;
     double *ss_out, *out1, *out2;
 };
 
+// one warp per (cell, theta): no block barriers, cell data and theta read straight from HBM/L2
 __global__ void __launch_bounds__(SS_THREADS) ss_batch_kernel(const __grid_constant__ SsArgs a)
 {
     extern __shared__ __align__(16) double smem[];
-    for (long long b = blockIdx.x; b < a.nbatch; b += gridDim.x) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *base = smem + (size_t)warp * a.wsz;
+    for (long long b = (long long)blockIdx.x * SS_WARPS + warp; b < a.nbatch; b += (long long)gridDim.x * SS_WARPS) {
         const int cid = a.cell_id[b];
-        const int N = a.cells.N[cid];
-        double *p = smem;
         CellView cv;
         Work w;
-        carve_cell(p, N, cv);
-        carve_work(p, N, w);
-        double *th = p;                                   // [7+N]
-        __syncthreads();                                  // previous iteration done with smem
-        load_cell(a.cells, cid, a.raw_grid != 0, cv);
-        for (int i = threadIdx.x; i < 7 + N; i += blockDim.x) th[i] = a.theta[b * a.ld + i];
-        __syncthreads();
+        view_cell(a.cells, cid, a.raw_grid != 0, cv);
+        double *p = base;
+        carve_work(p, cv.N, w);
         double *o1 = a.out1 ? a.out1 + b * a.ldo : nullptr;
         double *o2 = a.out2 ? a.out2 + b * a.ldo : nullptr;
-        const double ss = ss_eval(a.cons, cv, th, w, a.algo, false, o1, o2);
-        if (threadIdx.x == 0 && a.ss_out) a.ss_out[b] = ss;
+        const double ss = ss_eval(a.cons, cv, a.theta + b * a.ld, w, a.algo, false, o1, o2);
+        if (lane == 0 && a.ss_out) a.ss_out[b] = ss;
     }
 }
 
@@ -87,7 +87,7 @@ struct RunArgs {
     double drscale, adascale, qcovadj, burnin_scale, N0, S20, sigma2_0;
     unsigned long long seed;
     // chains
-    int nchains, ld, r_in_smem, ldR, do_cov;
+    int nchains, ld, ldR, do_cov, wsz;
     const int *chain_cell;
     const unsigned long long *chain_uid;
     const double *theta0, *qcov_diag, *low, *upp, *pmu, *psig;
@@ -98,410 +98,676 @@ struct RunArgs {
     int *flags;
     double *sschain;
     // scratch (global)
-    double *gR, *gRw, *gM2, *gRows, *gCmean;
+    double *gR, *gM2, *gRows, *gCmean;
 };
 
-struct ChainSmem {
-    double *x, *y1, *y2, *zz, *lo, *hi, *pmu, *pinv, *wmean, *wM2, *rdiag, *mb, *dm, *chunk, *R;
-};
+// Shared-memory budget of the sampler (doubles), N = max time points over the dataset.
+//   cell constants | 10 per-parameter vectors | SPEC ring slots of interleaved increments (+8 scalars)
+//   | SPEC per-warp areas (forward-model scratch + the warp's two proposals).
+// The per-warp areas are time-shared: during generation they hold the factor R (copied from HBM/L2
+// for the tensor-core product Z R), during adaptation the covariance row chunk and the Cholesky
+// workspace.
+__host__ __device__ inline int dram_wsz(int N)
+{
+    const int npar = 7 + N, npk = npar * (npar + 1) / 2;
+    int w = work_doubles(N) + 2 * npar + 4;
+    const int need = (npk + SPEC - 1) / SPEC + 2;
+    if (w < need) w = need;
+    return (w + 1) & ~1;
+}
+__host__ __device__ inline int dram_slot(int N) { return 2 * (7 + N) + 2 + 8; }
+__host__ __device__ inline int dram_smem_doubles(int N)
+{
+    return cell_doubles(N) + 10 * (7 + N) + SPEC * dram_slot(N) + SPEC * dram_wsz(N) + 16;
+}
 
-__host__ __device__ inline int chain_doubles(int npar, int npad) { return 13 * npar + npar + COV_RC * npad + 8; }
-
-// in-place upper Cholesky of the packed matrix in Rw (R'R = A); returns false when not PD.
-__device__ bool chol_packed(int n, double *Rw, double *s_piv)
+// In-place upper Cholesky of the packed matrix in Rw (R'R = A) by the whole CTA (two adjacent lanes
+// split the dot product of one element and combine with a shuffle).  Returns false when the matrix
+// is not positive definite.  Left-looking: row j of R from rows k < j.
+__device__ __noinline__ bool chol_packed(int n, double *Rw, double *s_piv)
 {
     const int tid = threadIdx.x, nt = blockDim.x;
+    const int e = tid >> 1, h = tid & 1, ne = nt >> 1;
+#pragma unroll 1
     for (int j = 0; j < n; ++j) {
         const int rj = pidx(n, j, j);
-        // left-looking: s(j,i) = A(j,i) - sum_{k<j} R(k,j) R(k,i), i >= j
-        for (int i = j + tid; i < n; i += nt) {
-            double s = Rw[rj + (i - j)];
-            int rk = 0;                                   // start of packed row k
-            for (int k = 0; k < j; ++k) {
-                s = fma(-Rw[rk + (j - k)], Rw[rk + (i - k)], s);
-                rk += n - k;
+        const int k0 = h ? (j >> 1) : 0, k1 = h ? j : (j >> 1);
+#pragma unroll 1
+        for (int i0 = j; i0 < n; i0 += ne) {
+            const int i = i0 + e;
+            const bool act = i < n;
+            double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+            if (act) {
+                int k = k0, rk = pidx(n, k0, k0);            // start of packed row k
+#pragma unroll 1
+                for (; k + 3 < k1; k += 4) {
+                    const int r1 = rk + n - k, r2 = r1 + n - k - 1, r3 = r2 + n - k - 2;
+                    s0 = fma(Rw[rk + (j - k)], Rw[rk + (i - k)], s0);
+                    s1 = fma(Rw[r1 + (j - k - 1)], Rw[r1 + (i - k - 1)], s1);
+                    s2 = fma(Rw[r2 + (j - k - 2)], Rw[r2 + (i - k - 2)], s2);
+                    s3 = fma(Rw[r3 + (j - k - 3)], Rw[r3 + (i - k - 3)], s3);
+                    rk = r3 + n - k - 3;
+                }
+#pragma unroll 1
+                for (; k < k1; ++k) {
+                    s0 = fma(Rw[rk + (j - k)], Rw[rk + (i - k)], s0);
+                    rk += n - k;
+                }
             }
-            Rw[rj + (i - j)] = s;
-            if (i == j) *s_piv = s;
+            double s = (s0 + s1) + (s2 + s3);
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            if (act && h == 0) {
+                s = Rw[rj + (i - j)] - s;
+                Rw[rj + (i - j)] = s;
+                if (i == j) *s_piv = s;
+            }
         }
         __syncthreads();
         const double piv = *s_piv;
         if (!(piv > 0.0)) return false;                   // uniform: every thread reads the same value
-        const double rjj = sqrt(piv);
+        const double rjj = sqrt(piv), inv = 1.0 / rjj;
+#pragma unroll 1
         for (int i = j + tid; i < n; i += nt) {
             const double s = Rw[rj + (i - j)];
-            Rw[rj + (i - j)] = (i == j) ? rjj : s / rjj;
+            Rw[rj + (i - j)] = (i == j) ? rjj : s * inv;
         }
         __syncthreads();
     }
     return true;
 }
 
-__global__ void __launch_bounds__(DRAM_THREADS) dram_kernel(const __grid_constant__ RunArgs a)
+// D = A * B + D on the FP64 tensor cores: A 8x4 (row), B 4x8 (col), D 8x8.  Lane l holds
+// A[l>>2][l&3], B[l&3][l>>2] and D[l>>2][2*(l&3) + {0,1}].
+__device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// per-step result record of the speculative batch (shared memory)
+struct StepRes { double ssn, prin; int acc, fl, nev, noob; };
+// s2chain statistics over ALL rows (TranscriptionCycleMCMC.m:302-303), thread 0, shared memory
+struct S2Stats { double sum, sq_mean, sq_M2, cnt; };
+
+// Immutable per-chain context, built once in shared memory so that the out-of-line phases below
+// (kept out of line to keep the hot loop inside the instruction cache) can share it.
+struct ChainCtx {
+    int N, npar, npad, npk, ld, slot_sz, wsz, ch, first_row, nstore;
+    unsigned long long uid;
+    double adascale, inv_dr;
+    CellView cv;
+    double *ring, *x, *lo, *hi, *mu, *pinv, *wmean, *wM2, *rdiag, *mb, *dm, *U;
+    double *gRb, *gM2, *gRows, *cmean;
+    __device__ __forceinline__ double *slot_d(int step) const { return ring + (size_t)(step % SPEC) * slot_sz; }
+    __device__ __forceinline__ double *slot_sc(int step) const { return ring + (size_t)(step % SPEC) * slot_sz + (slot_sz - 8); }
+    // warp wq's proposals live behind its forward-model scratch
+    __device__ __forceinline__ double *warp_y(int wq, int which) const
+    {
+        double *q = U + (size_t)wq * wsz;
+        Work tmp;
+        carve_work(q, N, tmp);
+        q += (reinterpret_cast<uintptr_t>(q) >> 3) & 1;
+        return which ? q + npar + (npar & 1) : q;
+    }
+};
+
+// Book-keeping of `cnt` consecutive chain rows r0.. that all equal xs: summaries (Welford, m equal
+// values at once), optional chain storage, covariance block buffer.  Returns the new summary count.
+__device__ __noinline__ double emit_rows(const RunArgs &a, const ChainCtx &cx, int r0, int cnt, const double *xs, double wcnt)
+{
+    const int tid = threadIdx.x, npar = cx.npar;
+    const int rs = max(r0, cx.first_row), m = r0 + cnt - rs;          // rows that enter the summaries
+    if (m > 0) {
+        const double nn = wcnt + m, f1 = m / nn, f2 = wcnt * m / nn;
+#pragma unroll 1
+        for (int i = tid; i < npar; i += DRAM_THREADS) {
+            const double xi = xs[i], d1 = xi - cx.wmean[i];
+            cx.wmean[i] = fma(d1, f1, cx.wmean[i]);
+            cx.wM2[i] = fma(d1 * d1, f2, cx.wM2[i]);
+        }
+        wcnt = nn;
+        if (a.store_chain && a.chain) {
+#pragma unroll 1
+            for (int r = rs; r < r0 + cnt; ++r) {
+                double *dst = a.chain + ((size_t)cx.ch * cx.nstore + (r - cx.first_row)) * cx.ld;
+#pragma unroll 1
+                for (int i = tid; i < npar; i += DRAM_THREADS) dst[i] = xs[i];
+            }
+        }
+    }
+    if (a.do_cov) {
+#pragma unroll 1
+        for (int r = r0; r < r0 + cnt; ++r) {
+            double *dst = cx.gRows + (size_t)(r % a.adaptint) * cx.ld;
+#pragma unroll 1
+            for (int i = tid; i < npar; i += DRAM_THREADS) dst[i] = xs[i];
+        }
+#pragma unroll 1
+        for (int i = tid; i < npar; i += DRAM_THREADS) cx.mb[i] = fma((double)cnt, xs[i], cx.mb[i]);
+    }
+    return wcnt;
+}
+
+// per-row scalars (thread 0): s2chain statistics and the optional per-step outputs
+__device__ __noinline__ void emit_s2(const RunArgs &a, const ChainCtx &cx, S2Stats *st, int r, double s2, double ssr, int fl)
+{
+    st->cnt += 1.0;
+    st->sum += s2;
+    const double sq = sqrt(s2), d1 = sq - st->sq_mean;
+    st->sq_mean += d1 / st->cnt;
+    st->sq_M2 = fma(d1, sq - st->sq_mean, st->sq_M2);
+    if (a.store_chain && a.s2chain) a.s2chain[(size_t)cx.ch * a.nsimu + r] = s2;
+    if (a.flags) a.flags[(size_t)cx.ch * a.nsimu + r] = fl;
+    if (a.sschain) a.sschain[(size_t)cx.ch * a.nsimu + r] = ssr;
+}
+
+// Randomness and proposal increments for steps [g0, g0+nnew): Philox normals z1, z2 (interleaved in
+// the ring slot), u1, u2, chi2, the two norms entering q1, then the increments z1 R and z2 R/drscale
+// in place.  With a full factor, ALL ring slots go through one pass over R on the FP64 tensor cores
+// ([8 x npar] x [npar x npar] mma.sync m8n8k4; A rows = ring slots, old slots are not written back).
+__device__ __noinline__ void generate(const RunArgs &a, const ChainCtx &cx, int g0, int nnew, bool r_diag)
+{
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, npar = cx.npar;
+    double *Rs = cx.U;
+    if (!r_diag) {
+        // stage R into shared memory (aliasing the per-warp areas) while the randomness is drawn
+        const unsigned sbase = (unsigned)__cvta_generic_to_shared(Rs);
+#pragma unroll 1
+        for (int c = tid; 2 * c < cx.npk; c += DRAM_THREADS)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + 16u * c), "l"(cx.gRb + 2 * c) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    if (a.replay) {
+#pragma unroll 1
+        for (int sidx = 0; sidx < nnew; ++sidx) {
+            const int st = g0 + sidx;
+            double *dz = cx.slot_d(st), *sc = cx.slot_sc(st);
+            const size_t g = ((size_t)cx.ch * a.nsimu + st) * cx.ld;
+#pragma unroll 1
+            for (int i = tid; i < npar; i += DRAM_THREADS) { dz[2 * i] = a.z1[g + i]; dz[2 * i + 1] = a.z2[g + i]; }
+            if (tid == 0) {
+                sc[0] = a.u1[(size_t)cx.ch * a.nsimu + st]; sc[1] = a.u2[(size_t)cx.ch * a.nsimu + st];
+                sc[2] = a.chi2[(size_t)cx.ch * a.nsimu + st];
+            }
+        }
+    } else {
+        const int npairs = (npar + 1) >> 1, per = 2 * npairs + 1;    // work items per step: normal pairs + (u, chi2)
+#pragma unroll 1
+        for (int it = tid; it < nnew * per; it += DRAM_THREADS) {
+            const int sidx = it / per, q2 = it - sidx * per, st = g0 + sidx;
+            double *dz = cx.slot_d(st), *sc = cx.slot_sc(st);
+            if (q2 == 2 * npairs) {
+                const u32x4 ru = draw(a.seed, cx.uid, st, RK_U, 0);
+                sc[0] = u01(ru.x, ru.y);
+                sc[1] = u01(ru.z, ru.w);
+                sc[2] = a.updatesigma ? chi2_draw(a.seed, cx.uid, st, a.N0 + 2.0 * cx.N) : 1.0;
+            } else {
+                const int kind = q2 >= npairs ? 1 : 0, q = q2 - kind * npairs;
+                double za, zb;
+                normal_pair(draw(a.seed, cx.uid, st, kind ? RK_Z2 : RK_Z1, q), za, zb);
+                dz[4 * q + kind] = za;
+                if (2 * q + 1 < npar) dz[4 * q + 2 + kind] = zb;
+            }
+        }
+    }
+    if (!r_diag) asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    // q1 = -1/2 (|(y1-y2) R^-1|^2 - |(y1-x) R^-1|^2) = -1/2 (|z1 - z2/drscale|^2 - |z1|^2): from z, before the
+    // increments overwrite it
+    if (warp < nnew) {
+        const double *dz = cx.slot_d(g0 + warp);
+        double n1 = 0.0, n0 = 0.0;
+#pragma unroll 1
+        for (int i = lane; i < npar; i += 32) {
+            const double za = dz[2 * i], d = za - dz[2 * i + 1] * cx.inv_dr;
+            n1 = fma(d, d, n1);
+            n0 = fma(za, za, n0);
+        }
+        n1 = warp_sum(n1); n0 = warp_sum(n0);
+        if (lane == 0) { double *sc = cx.slot_sc(g0 + warp); sc[3] = n1; sc[4] = n0; }
+    }
+    if (r_diag) {
+        __syncthreads();
+#pragma unroll 1
+        for (int sidx = 0; sidx < nnew; ++sidx) {
+            double *dz = cx.slot_d(g0 + sidx);
+#pragma unroll 1
+            for (int j = tid; j < npar; j += DRAM_THREADS) {
+                const double r = cx.rdiag[j];
+                dz[2 * j] *= r;
+                dz[2 * j + 1] *= r * cx.inv_dr;
+            }
+        }
+    } else {
+        const int NT = (npar + 7) >> 3;
+        double r1[4][2], r2[4][2];
+        int rt[4];
+        int nres = 0;
+        const int ar = lane >> 2, ak = lane & 3;                 // A[row = slot][k], B[k][col]
+        const double *arow = cx.ring + (size_t)ar * cx.slot_sz;
+#pragma unroll 1
+        for (int pp = warp; pp < (NT + 1) / 2 && nres < 3; pp += SPEC) {   // <= 4 tiles per warp: npar <= 256
+#pragma unroll
+            for (int side = 0; side < 2; ++side) {
+                const int nt = side ? NT - 1 - pp : pp;
+                if (side && nt == pp) break;
+                const int n0c = 8 * nt, j = n0c + ar;          // B column of this lane
+                double c10 = 0, c11 = 0, c20 = 0, c21 = 0;
+                const int kmax = min(n0c + 8, npar);             // rows i < kmax can reach these columns
+#pragma unroll 2
+                for (int k0 = 0; k0 < kmax; k0 += 4) {
+                    const int i = k0 + ak;
+                    const double bv = (i <= j && j < npar) ? Rs[pidx(npar, i, j)] : 0.0;
+                    double2 az = make_double2(0.0, 0.0);
+                    if (i < npar) az = *reinterpret_cast<const double2 *>(arow + 2 * i);
+                    dmma_m8n8k4(c10, c11, az.x, bv);
+                    dmma_m8n8k4(c20, c21, az.y, bv);
+                }
+                r1[nres][0] = c10; r1[nres][1] = c11; r2[nres][0] = c20; r2[nres][1] = c21; rt[nres] = nt;
+                ++nres;
+            }
+        }
+        __syncthreads();                                         // everyone is done reading z
+        const bool is_new = ((ar - g0) % SPEC + SPEC) % SPEC < nnew;   // slot ar holds a new step?
+        double *orow = cx.ring + (size_t)ar * cx.slot_sz;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (q < nres && is_new) {
+                const int jc = 8 * rt[q] + 2 * ak;
+                if (jc < npar) { orow[2 * jc] = r1[q][0]; orow[2 * jc + 1] = r2[q][0] * cx.inv_dr; }
+                if (jc + 1 < npar) { orow[2 * jc + 2] = r1[q][1]; orow[2 * jc + 3] = r2[q][1] * cx.inv_dr; }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// One DRAM step (both proposal stages) by ONE warp for step `st`, from state x with (ss, pri), seeing
+// sigma2 = s2p.  Result in *res.   mcmcstat DRAM: SURVEY.md 3.2.
+__device__ __noinline__ void dram_step_warp(const RunArgs &a, const ChainCtx &cx, int st, double ss, double pri, double s2p,
+                                            Work &w, double *y1, double *y2, StepRes *res)
+{
+    const int lane = threadIdx.x & 31, npar = cx.npar;
+    const double2 *dd = reinterpret_cast<const double2 *>(cx.slot_d(st));
+    const double *sc = cx.slot_sc(st);
+    double pr1 = 0.0, pr2 = 0.0;
+    unsigned oob = 0;
+#pragma unroll 1
+    for (int j = lane; j < npar; j += 32) {
+        const double2 dj = dd[j];
+        const double xj = cx.x[j], a1 = xj + dj.x, a2 = xj + dj.y;
+        y1[j] = a1;
+        y2[j] = a2;
+        const double lo = cx.lo[j], hi = cx.hi[j];
+        if (a1 < lo || a1 > hi) oob |= 1u;
+        if (a2 < lo || a2 > hi) oob |= 2u;
+        const double e1 = (a1 - cx.mu[j]) * cx.pinv[j], e2 = (a2 - cx.mu[j]) * cx.pinv[j];
+        pr1 = fma(e1, e1, pr1);
+        pr2 = fma(e2, e2, pr2);
+    }
+    pr1 = warp_sum(pr1); pr2 = warp_sum(pr2);
+    oob = __reduce_or_sync(0xffffffffu, oob);
+    __syncwarp();
+    int fl = 0, accept = 0, nev = 0, noob = 0;
+    double ss1, a12;
+    if (oob & 1u) {
+        ss1 = INFINITY; pr1 = 0.0; a12 = 0.0; fl |= TC_FL_OOB1; ++noob;
+    } else {
+        ss1 = ss_eval(a.cons, cx.cv, y1, w, a.algo, false, nullptr, nullptr);
+        ++nev;
+        a12 = tc_exp(-0.5 * ((ss1 - ss) / s2p + pr1 - pri));
+        if (a12 <= 0.0) accept = 0;
+        else if (a12 >= 1.0) accept = 1;
+        else accept = a12 > sc[0];
+    }
+    double ssn = ss1, prin = pr1;
+    if (!accept && a.ntry >= 2) {                                // delayed rejection with R/drscale
+        fl |= TC_FL_DR;
+        if (oob & 2u) {
+            fl |= TC_FL_OOB2; ++noob;
+        } else {
+            const double ss2 = ss_eval(a.cons, cx.cv, y2, w, a.algo, false, nullptr, nullptr);
+            ++nev;
+            double a32 = tc_exp(-0.5 * ((ss1 - ss2) / s2p + pr1 - pr2));
+            a32 = a32 > 1.0 ? 1.0 : a32;
+            if (!(a32 >= 0.0)) a32 = 0.0;
+            const double l2 = -0.5 * ((ss2 - ss) / s2p + pr2 - pri);
+            const double q1 = -0.5 * (sc[3] - sc[4]);
+            double a13 = tc_exp(l2 + q1) * (1.0 - a32) / (1.0 - a12);
+            a13 = a13 > 1.0 ? 1.0 : a13;
+            if ((a13 >= 1.0) || (a13 > sc[1])) { accept = 2; fl |= TC_FL_STAGE2; ssn = ss2; prin = pr2; }
+        }
+    }
+    if (accept) fl |= TC_FL_ACCEPT;
+    if (lane == 0) { res->acc = accept; res->fl = fl; res->nev = nev; res->noob = noob; res->ssn = ssn; res->prin = prin; }
+}
+
+// Adaptation after the step with isimu (a multiple of adaptint): fold the last adaptint rows into the
+// running covariance (Chan's block update, 4x4 register tiles), then either burn-in scaling or
+// R = chol(cov + qcovadj I) * adascale.  Returns 0: R unchanged / scaled, 1: new full factor, 2: Cholesky failed.
+__device__ __noinline__ int adapt(const RunArgs &a, const ChainCtx &cx, int isimu, double cov_n, double rate, bool r_diag,
+                                  double *s_piv)
+{
+    const int tid = threadIdx.x, npar = cx.npar, npad = cx.npad, ld = cx.ld, npk = cx.npk;
+    double *chunk = cx.U, *Rs = cx.U;
+    if (a.do_cov) {
+        const int m = a.adaptint;
+#pragma unroll 1
+        for (int i = tid; i < npar; i += DRAM_THREADS) {
+            const double mbi = cx.mb[i] / m;
+            cx.mb[i] = mbi;
+            cx.dm[i] = mbi - cx.cmean[i];
+        }
+        const double fcorr = cov_n * m / (cov_n + m);
+        const int ntile = (npar + 3) >> 2, T = ntile * (ntile + 1) / 2;
+#pragma unroll 1
+        for (int base = 0; base < T; base += COV_TPT * DRAM_THREADS) {
+            int bi[COV_TPT], bj[COV_TPT];
+            bool on[COV_TPT];
+            double acc[COV_TPT][16];
+#pragma unroll
+            for (int u = 0; u < COV_TPT; ++u) {
+                const int tix = base + u * DRAM_THREADS + tid;
+                on[u] = tix < T;
+                int rem = on[u] ? tix : 0, b = 0;
+                while (rem >= ntile - b) { rem -= ntile - b; ++b; }
+                bi[u] = b; bj[u] = b + rem;
+#pragma unroll
+                for (int e = 0; e < 16; ++e) acc[u][e] = 0.0;
+            }
+#pragma unroll 1
+            for (int r0 = 0; r0 < m; r0 += COV_RC) {
+                const int rc = min(COV_RC, m - r0);
+                __syncthreads();
+#pragma unroll 1
+                for (int r = 0; r < rc; ++r)
+#pragma unroll 1
+                    for (int c = tid; c < npad; c += DRAM_THREADS)
+                        chunk[r * npad + c] = c < npar ? cx.gRows[(size_t)(r0 + r) * ld + c] - cx.mb[c] : 0.0;
+                __syncthreads();
+#pragma unroll
+                for (int u = 0; u < COV_TPT; ++u) {
+                    if (!on[u]) continue;
+#pragma unroll 1
+                    for (int r = 0; r < rc; ++r) {
+                        const double2 *ra = reinterpret_cast<const double2 *>(chunk + r * npad + 4 * bi[u]);
+                        const double2 *rb = reinterpret_cast<const double2 *>(chunk + r * npad + 4 * bj[u]);
+                        const double2 a0 = ra[0], a1 = ra[1], b0 = rb[0], b1 = rb[1];
+                        const double av[4] = {a0.x, a0.y, a1.x, a1.y}, bv[4] = {b0.x, b0.y, b1.x, b1.y};
+#pragma unroll
+                        for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+                            for (int jj = 0; jj < 4; ++jj) acc[u][4 * ii + jj] = fma(av[ii], bv[jj], acc[u][4 * ii + jj]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < COV_TPT; ++u) {
+                if (!on[u]) continue;
+                double old[16];
+#pragma unroll
+                for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const int pp = 4 * bi[u] + ii, qq = 4 * bj[u] + jj;
+                        old[4 * ii + jj] = (pp <= qq && qq < npar) ? cx.gM2[pidx(npar, pp, qq)] : 0.0;
+                    }
+#pragma unroll
+                for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const int pp = 4 * bi[u] + ii, qq = 4 * bj[u] + jj;
+                        if (pp <= qq && qq < npar)
+                            cx.gM2[pidx(npar, pp, qq)] = old[4 * ii + jj] + acc[u][4 * ii + jj] + fcorr * cx.dm[pp] * cx.dm[qq];
+                    }
+            }
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int i = tid; i < npar; i += DRAM_THREADS) { cx.cmean[i] += cx.dm[i] * (m / (cov_n + m)); cx.mb[i] = 0.0; }
+        cov_n += m;
+        __syncthreads();
+    }
+    int ret = 0;
+    if (isimu < a.burnintime) {
+        double f = 1.0;
+        if (rate > 0.95) f = 1.0 / a.burnin_scale;
+        else if (rate < 0.05) f = a.burnin_scale;
+        if (f != 1.0) {
+            if (r_diag) {
+#pragma unroll 1
+                for (int i = tid; i < npar; i += DRAM_THREADS) cx.rdiag[i] *= f;
+            } else {
+#pragma unroll 1
+                for (int i = tid; i < npk; i += DRAM_THREADS) cx.gRb[i] *= f;
+            }
+        }
+    } else {
+        // R = chol(cov + qcovadj I) * adascale, factorised in shared memory, kept in HBM/L2
+        const double invn = 1.0 / (cov_n - 1.0);
+#pragma unroll 1
+        for (int i = tid; i < npk; i += DRAM_THREADS) Rs[i] = cx.gM2[i] * invn;
+        __syncthreads();
+#pragma unroll 1
+        for (int i = tid; i < npar; i += DRAM_THREADS) Rs[pidx(npar, i, i)] += a.qcovadj;
+        __syncthreads();
+        const bool ok = chol_packed(npar, Rs, s_piv);
+        __syncthreads();
+        if (ok) {
+#pragma unroll 1
+            for (int i = tid; i < npk; i += DRAM_THREADS) cx.gRb[i] = Rs[i] * cx.adascale;
+            ret = 1;
+        } else {
+            ret = 2;                                                // R unchanged
+        }
+    }
+    __syncthreads();
+    return ret;
+}
+
+// The device-resident DRAM sampler: one CTA per chain, SPEC future steps per batch.
+//
+// DRAM is sequential, but a step that rejects leaves the state untouched, and at the acceptance
+// rates of this model (8-30 %) most do.  So the CTA simulates the next SPEC steps AT ONCE, warp w
+// running step k+w in full (both proposal stages, forward model, accept/reject) under the
+// hypothesis "nothing before me accepted"; the batch is then cut after the first step that did
+// accept, that prefix is committed, and the later warps' work is discarded.  The chain produced is
+// exactly the sequential one (same Philox draws per step; the replay tests compare it flag by flag
+// with the CPU oracle).  The randomness and the proposal increments z R do not depend on the state,
+// so they are generated once per step, ahead of use, into a ring of SPEC slots.
+__global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_constant__ RunArgs a)
 {
     extern __shared__ __align__(16) double smem[];
-    __shared__ double s_sc[8];
-    const int tid = threadIdx.x, nt = blockDim.x;
+    __shared__ StepRes s_res[SPEC];
+    __shared__ ChainCtx cx;
+    __shared__ S2Stats s_s2;
+    __shared__ double s_sc[4];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ch = blockIdx.x;
     if (ch >= a.nchains) return;
     const int cid = a.chain_cell[ch];
     const int N = a.cells.N[cid];
-    const int npar = 7 + N, npad = (npar + 3) & ~3, ld = a.ld;
-    const unsigned long long uid = a.chain_uid ? a.chain_uid[ch] : (unsigned long long)ch;
-    const int npk = npar * (npar + 1) / 2;
+    const int npar = 7 + N;
 
-    double *p = smem;
-    CellView cv;
+    // ---- carve shared memory, publish the context
+    {
+        double *p = smem;
+        CellView cv;
+        carve_cell(p, N, cv);
+        p += (reinterpret_cast<uintptr_t>(p) >> 3) & 1;
+        if (tid == 0) {
+            cx.N = N; cx.npar = npar; cx.npad = (npar + 3) & ~3; cx.npk = npar * (npar + 1) / 2; cx.ld = a.ld;
+            cx.slot_sz = dram_slot(N); cx.wsz = a.wsz; cx.ch = ch; cx.first_row = a.n_burn - 1;
+            cx.nstore = a.nsimu - (a.n_burn - 1);
+            cx.uid = a.chain_uid ? a.chain_uid[ch] : (unsigned long long)ch;
+            cx.adascale = a.adascale > 0.0 ? a.adascale : 2.4 / sqrt((double)npar);
+            cx.inv_dr = 1.0 / a.drscale;
+            cx.cv = cv; cx.cv.d = a.cells.dmean[cid];
+            cx.ring = p; p += SPEC * dram_slot(N);
+            cx.x = p; p += npar;     cx.lo = p; p += npar;    cx.hi = p; p += npar;   cx.mu = p; p += npar;
+            cx.pinv = p; p += npar;  cx.wmean = p; p += npar; cx.wM2 = p; p += npar;  cx.rdiag = p; p += npar;
+            cx.mb = p; p += npar;    cx.dm = p; p += npar;
+            p += (reinterpret_cast<uintptr_t>(p) >> 3) & 1;
+            cx.U = p;
+            cx.gRb = a.gR + (size_t)ch * a.ldR;                 // the factor R lives in HBM/L2 (packed upper)
+            cx.gM2 = a.gM2 ? a.gM2 + (size_t)ch * a.ldR : nullptr;
+            cx.gRows = a.gRows ? a.gRows + (size_t)ch * (size_t)a.adaptint * a.ld : nullptr;
+            cx.cmean = a.gCmean ? a.gCmean + (size_t)ch * a.ld : nullptr;
+            s_s2.sum = 0.0; s_s2.sq_mean = 0.0; s_s2.sq_M2 = 0.0; s_s2.cnt = 0.0;
+        }
+        load_cell(a.cells, cid, false, cv);
+    }
+    __syncthreads();
+    // this warp's private area: forward-model scratch + its two proposals
     Work w;
-    ChainSmem cs;
-    carve_cell(p, N, cv);
-    carve_work(p, N, w);
-    cs.x = p; p += npar;   cs.y1 = p; p += npar;   cs.y2 = p; p += npar;
-    p += ((p - smem) & 1);                                 // 16-byte align the interleaved (z1,z2) pairs
-    cs.zz = p; p += 2 * npar;
-    cs.lo = p; p += npar;  cs.hi = p; p += npar;   cs.pmu = p; p += npar;  cs.pinv = p; p += npar;
-    cs.wmean = p; p += npar; cs.wM2 = p; p += npar; cs.rdiag = p; p += npar;
-    cs.mb = p; p += npar;  cs.dm = p; p += npar;
-    p += ((p - smem) & 1);                                 // 16-byte align the chunk
-    cs.chunk = p; p += COV_RC * npad;
-    cs.R = a.r_in_smem ? p : a.gRw + (size_t)ch * a.ldR;
-    double *gRb = a.gR + (size_t)ch * a.ldR;               // R backup (restored on a failed Cholesky)
-    double *gM2 = a.gM2 ? a.gM2 + (size_t)ch * a.ldR : nullptr;
-    double *gRows = a.gRows ? a.gRows + (size_t)ch * (size_t)a.adaptint * ld : nullptr;
-
-    load_cell(a.cells, cid, false, cv);
-    const double adascale = a.adascale > 0.0 ? a.adascale : 2.4 / sqrt((double)npar);
-    for (int i = tid; i < npar; i += nt) {
-        const size_t g = (size_t)ch * ld + i;
-        cs.x[i] = a.theta0[g];
-        cs.lo[i] = a.low[g];
-        cs.hi[i] = a.upp[g];
-        cs.pmu[i] = a.pmu[g];
+    {
+        double *wp = cx.U + (size_t)warp * cx.wsz;
+        carve_work(wp, N, w);
+    }
+    double *y1 = cx.warp_y(warp, 0), *y2 = cx.warp_y(warp, 1);
+#pragma unroll 1
+    for (int i = tid; i < npar; i += DRAM_THREADS) {
+        const size_t g = (size_t)ch * a.ld + i;
+        cx.x[i] = a.theta0[g];
+        cx.lo[i] = a.low[g];
+        cx.hi[i] = a.upp[g];
+        cx.mu[i] = a.pmu[g];
         const double sg = a.psig[g];
-        cs.pinv[i] = isinf(sg) ? 0.0 : 1.0 / sg;
-        cs.rdiag[i] = sqrt(a.qcov_diag[g]);                // chol(diag(J0))
-        cs.wmean[i] = 0.0;
-        cs.wM2[i] = 0.0;
+        cx.pinv[i] = isinf(sg) ? 0.0 : 1.0 / sg;
+        cx.rdiag[i] = sqrt(a.qcov_diag[g]);                // chol(diag(J0))
+        cx.wmean[i] = 0.0;
+        cx.wM2[i] = 0.0;
+        cx.mb[i] = 0.0;
+        if (a.do_cov) cx.cmean[i] = 0.0;
+    }
+    if (a.do_cov) {
+#pragma unroll 1
+        for (int i = tid; i < cx.npk; i += DRAM_THREADS) cx.gM2[i] = 0.0;
     }
     __syncthreads();
 
-    // ---- state
+    // ---- chain state (uniform across the CTA)
     bool r_diag = true;
     double cov_n = 0.0;                                    // rows folded into (cmean, M2) so far
-    double *cmean = a.gCmean ? a.gCmean + (size_t)ch * ld : nullptr;
-    if (a.do_cov) {
-        for (int i = tid; i < npk; i += nt) gM2[i] = 0.0;
-        for (int i = tid; i < npar; i += nt) cmean[i] = 0.0;
-    }
-    double ss = ss_eval(a.cons, cv, cs.x, w, a.algo, false, nullptr, nullptr);
-    double pri;
-    {
-        double s = 0.0, d0 = 0.0;
-        for (int i = tid; i < npar; i += nt) { const double e = (cs.x[i] - cs.pmu[i]) * cs.pinv[i]; s += e * e; }
-        block_sum2(s, d0, w.red);
-        pri = s;
-    }
-    double sigma2 = a.sigma2_0;
-    long long n_ss = 1, n_acc1 = 0, n_acc2 = 0, n_oob = 0, n_adapt = 0, n_cholfail = 0, n_dr = 0;
+    double ss, pri, sigma2 = a.sigma2_0;
+    long long n_ss = 1, n_acc1 = 0, n_acc2 = 0, n_oob = 0, n_adapt = 0, n_cholfail = 0, n_dr = 0, n_spec = 0;
     long long rej = 0, reju = 0;
-    long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};            // phase cycles (thread 0): rng, propose, ss1, dr, state, cov, chol, -
+    double wcnt = 0.0;                                     // rows folded into the summaries
+    long long pc[5] = {0, 0, 0, 0, 0};                     // phase cycles (thread 0)
     long long tprev = clock64();
 #define TC_PHASE(i) do { const long long tn__ = clock64(); pc[i] += tn__ - tprev; tprev = tn__; } while (0)
-    // s2chain statistics over ALL rows (TranscriptionCycleMCMC.m:302-303), thread 0
-    double s2_sum = sigma2, sq_mean = sqrt(sigma2), sq_M2 = 0.0, s2_cnt = 1.0;
-    double wcnt = 0.0;                                     // rows folded into the summaries
-    const int first_row = a.n_burn - 1;                    // chain(n_burn:end,:) in 0-based rows
-    const int nstore = a.nsimu - first_row;
+
+    // ---- row 0: x0
+    {
+        ss = ss_eval(a.cons, cx.cv, cx.x, w, a.algo, false, nullptr, nullptr);   // every warp, same value
+        double s = 0.0;
+#pragma unroll 1
+        for (int i = lane; i < npar; i += 32) { const double e = (cx.x[i] - cx.mu[i]) * cx.pinv[i]; s += e * e; }
+        pri = warp_sum(s);
+    }
     const bool bad0 = !isfinite(ss);
+    __syncthreads();
+    if (!bad0) {
+        wcnt = emit_rows(a, cx, 0, 1, cx.x, wcnt);
+        if (tid == 0) emit_s2(a, cx, &s_s2, 0, sigma2, ss, 0);
+    }
+    __syncthreads();
 
-    auto emit_row = [&](int k) {
-        // row k of the chain = current state: summaries, optional storage, covariance block buffer
-        if (k >= first_row) {
-            wcnt += 1.0;
-            for (int i = tid; i < npar; i += nt) {
-                const double xi = cs.x[i], d1 = xi - cs.wmean[i];
-                const double m = cs.wmean[i] + d1 / wcnt;
-                cs.wmean[i] = m;
-                cs.wM2[i] = fma(d1, xi - m, cs.wM2[i]);
-            }
-            if (a.store_chain && a.chain) {
-                double *dst = a.chain + ((size_t)ch * nstore + (k - first_row)) * ld;
-                for (int i = tid; i < npar; i += nt) dst[i] = cs.x[i];
-            }
-        }
-        if (a.do_cov) {
-            double *dst = gRows + (size_t)(k % a.adaptint) * ld;
-            for (int i = tid; i < npar; i += nt) dst[i] = cs.x[i];
-        }
-        if (tid == 0) {
-            if (a.store_chain && a.s2chain) a.s2chain[(size_t)ch * a.nsimu + k] = sigma2;
-            if (a.sschain) a.sschain[(size_t)ch * a.nsimu + k] = ss;
-        }
-    };
-    emit_row(0);
-    if (tid == 0 && a.flags) a.flags[(size_t)ch * a.nsimu] = 0;
+    int k = 1;                 // next step to decide
+    int gen_upto = 1;          // increments are ready for steps [k, gen_upto)
+#pragma unroll 1
+    while (k < a.nsimu && !bad0) {
+        // the batch never crosses an adaptation: the step whose isimu = st+1 is a multiple of adaptint
+        // is the last one that may use the current R
+        int lim = min(k + SPEC, a.nsimu);
+        if (a.adaptint > 0) lim = min(lim, ((k + a.adaptint) / a.adaptint) * a.adaptint);   // exclusive step bound
+        const int nb = lim - k;
 
-    for (int k = 1; k < a.nsimu && !bad0; ++k) {
-        const int isimu = k + 1;
-        // ---- 1. randomness of this step: z1, z2 (interleaved), u1, u2, chi2
-        double u1, u2;
-        if (a.replay) {
-            const size_t g = ((size_t)ch * a.nsimu + k) * ld;
-            for (int i = tid; i < npar; i += nt) { cs.zz[2 * i] = a.z1[g + i]; cs.zz[2 * i + 1] = a.z2[g + i]; }
-            u1 = a.u1[(size_t)ch * a.nsimu + k];
-            u2 = a.u2[(size_t)ch * a.nsimu + k];
-            if (tid == nt - 1) s_sc[2 + (k & 1)] = a.chi2[(size_t)ch * a.nsimu + k];
-        } else {
-            for (int q = tid; 2 * q < npar; q += nt) {
-                double za, zb;
-                normal_pair(draw(a.seed, uid, k, RK_Z1, q), za, zb);
-                cs.zz[4 * q] = za;
-                if (2 * q + 1 < npar) cs.zz[4 * q + 2] = zb;
-                normal_pair(draw(a.seed, uid, k, RK_Z2, q), za, zb);
-                cs.zz[4 * q + 1] = za;
-                if (2 * q + 1 < npar) cs.zz[4 * q + 3] = zb;
-            }
-            const u32x4 ru = draw(a.seed, uid, k, RK_U, 0);
-            u1 = u01(ru.x, ru.y);
-            u2 = u01(ru.z, ru.w);
-            // the chi-square draw does not depend on the chain state: the last warp makes it while
-            // the others generate normals; it is consumed after the accept/reject decision
-            if (tid == nt - 1 && a.updatesigma) s_sc[2 + (k & 1)] = chi2_draw(a.seed, uid, k, a.N0 + 2.0 * N);
+        if (gen_upto < lim) { generate(a, cx, gen_upto, lim - gen_upto, r_diag); gen_upto = lim; }
+        if (tid == 0) TC_PHASE(0);
+
+        // speculation: warp w runs step k+w assuming steps k..k+w-1 rejected; the sigma2 it sees is the
+        // draw made at the end of step k+w-1 from the (unchanged) ss
+        if (warp < nb) {
+            double s2p = sigma2;
+            if (warp > 0 && a.updatesigma) s2p = (a.N0 * a.S20 + ss) / cx.slot_sc(k + warp - 1)[2];
+            dram_step_warp(a, cx, k + warp, ss, pri, s2p, w, y1, y2, &s_res[warp]);
         }
         __syncthreads();
-        TC_PHASE(0);
-        // ---- 2. both proposals in one pass over R:  y1 = x + z1 R,  y2 = x + z2 R / drscale
-        double pr1 = 0.0, pr2 = 0.0;
-        int oob = 0;
-        const double inv_dr = 1.0 / a.drscale;
-        for (int j = tid; j < npar; j += nt) {
-            double s1 = 0.0, s2 = 0.0;
-            if (r_diag) {
-                s1 = cs.zz[2 * j] * cs.rdiag[j];
-                s2 = cs.zz[2 * j + 1] * cs.rdiag[j];
-            } else {
-                // column j of the packed upper factor: R(i,j) at rk(i) + j - i; four independent
-                // partial sums per proposal break the FMA dependence chain
-                double p1[4] = {0, 0, 0, 0}, p2[4] = {0, 0, 0, 0};
-                int rk = j, i = 0;                         // rk = pidx(i, j)
-                for (; i + 3 <= j; i += 4) {
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const double r = cs.R[rk];
-                        const double2 z = *reinterpret_cast<const double2 *>(cs.zz + 2 * (i + u));
-                        p1[u] = fma(z.x, r, p1[u]);
-                        p2[u] = fma(z.y, r, p2[u]);
-                        rk += npar - (i + u) - 1;
-                    }
-                }
-                for (; i <= j; ++i) {
-                    const double r = cs.R[rk];
-                    p1[0] = fma(cs.zz[2 * i], r, p1[0]);
-                    p2[0] = fma(cs.zz[2 * i + 1], r, p2[0]);
-                    rk += npar - i - 1;
-                }
-                s1 = (p1[0] + p1[1]) + (p1[2] + p1[3]);
-                s2 = (p2[0] + p2[1]) + (p2[2] + p2[3]);
-            }
-            const double xj = cs.x[j], a1 = xj + s1, a2 = xj + s2 * inv_dr;
-            cs.y1[j] = a1;
-            cs.y2[j] = a2;
-            const double lo = cs.lo[j], hi = cs.hi[j];
-            if (a1 < lo || a1 > hi) oob |= 1;
-            if (a2 < lo || a2 > hi) oob |= 2;
-            const double e1 = (a1 - cs.pmu[j]) * cs.pinv[j], e2 = (a2 - cs.pmu[j]) * cs.pinv[j];
-            pr1 = fma(e1, e1, pr1);
-            pr2 = fma(e2, e2, pr2);
-        }
-        block_sum2(pr1, pr2, w.red);
-        const int oob1 = __syncthreads_or(oob & 1), oob2 = __syncthreads_or(oob & 2);
+        if (tid == 0) TC_PHASE(1);
 
-        TC_PHASE(1);
-        // ---- 3. stage 1
-        int fl = 0, accept = 0;
-        double ss1, a12;
-        if (oob1) {
-            ss1 = INFINITY; pr1 = 0.0; a12 = 0.0; fl |= TC_FL_OOB1; ++n_oob;
-        } else {
-            ss1 = ss_eval(a.cons, cv, cs.y1, w, a.algo, false, nullptr, nullptr);
-            ++n_ss;
-            a12 = exp(-0.5 * ((ss1 - ss) / sigma2 + pr1 - pri));
-            if (a12 <= 0.0) accept = 0;
-            else if (a12 >= 1.0) accept = 1;
-            else accept = a12 > u1;
-            if (accept) ++n_acc1;
+        // resolve: commit up to and including the first accepting step
+        int first = nb;
+#pragma unroll 1
+        for (int q = nb - 1; q >= 0; --q) if (s_res[q].acc) first = q;
+        const int ncommit = first < nb ? first + 1 : nb;
+#pragma unroll 1
+        for (int q = 0; q < nb; ++q) {
+            if (q < ncommit) { n_ss += s_res[q].nev; n_oob += s_res[q].noob; if (s_res[q].fl & TC_FL_DR) ++n_dr; }
+            n_spec += s_res[q].nev;
         }
-        const double *newp = cs.y1;
-        double ssn = ss1, prin = pr1;
-        TC_PHASE(2);
-        // ---- 4. delayed rejection with R/drscale
-        if (!accept && a.ntry >= 2) {
-            fl |= TC_FL_DR; ++n_dr;
-            if (oob2) {
-                fl |= TC_FL_OOB2; ++n_oob;
-            } else {
-                const double ss2 = ss_eval(a.cons, cv, cs.y2, w, a.algo, false, nullptr, nullptr);
-                ++n_ss;
-                double a32 = exp(-0.5 * ((ss1 - ss2) / sigma2 + pr1 - pr2));
-                a32 = a32 > 1.0 ? 1.0 : a32;
-                if (!(a32 >= 0.0)) a32 = 0.0;
-                const double l2 = -0.5 * ((ss2 - ss) / sigma2 + pr2 - pri);
-                // q1 = -1/2 (|(y1-y2) R^-1|^2 - |(y1-x) R^-1|^2) = -1/2 (|z1 - z2/drscale|^2 - |z1|^2)
-                double n1 = 0.0, n0 = 0.0;
-                for (int i = tid; i < npar; i += nt) {
-                    const double za = cs.zz[2 * i], d = za - cs.zz[2 * i + 1] * inv_dr;
-                    n1 = fma(d, d, n1);
-                    n0 = fma(za, za, n0);
+        const int nrej = first < nb ? first : nb;                     // leading rejected steps: rows equal x
+        rej += nrej; reju += nrej;
+        if (nrej > 0) {
+            wcnt = emit_rows(a, cx, k, nrej, cx.x, wcnt);
+            if (tid == 0) {
+#pragma unroll 1
+                for (int q = 0; q < nrej; ++q) {
+                    const double s2 = a.updatesigma ? (a.N0 * a.S20 + ss) / cx.slot_sc(k + q)[2] : sigma2;
+                    emit_s2(a, cx, &s_s2, k + q, s2, ss, s_res[q].fl);
                 }
-                block_sum2(n1, n0, w.red);
-                const double q1 = -0.5 * (n1 - n0);
-                double a13 = exp(l2 + q1) * (1.0 - a32) / (1.0 - a12);
-                a13 = a13 > 1.0 ? 1.0 : a13;
-                const int acc2 = (a13 >= 1.0) || (a13 > u2);
-                if (acc2) { accept = 1; fl |= TC_FL_STAGE2; newp = cs.y2; ssn = ss2; prin = pr2; ++n_acc2; }
             }
+            if (a.updatesigma) sigma2 = (a.N0 * a.S20 + ss) / cx.slot_sc(k + nrej - 1)[2];
         }
-        __syncthreads();
-        TC_PHASE(3);
-        if (accept) {
-            fl |= TC_FL_ACCEPT;
-            for (int i = tid; i < npar; i += nt) cs.x[i] = newp[i];
-            ss = ssn; pri = prin;
-        } else { ++rej; ++reju; }
-        // ---- 5. sigma2 | ss ~ inv-chi2 (thread 0 draws, broadcast)
-        if (a.updatesigma) {
-            sigma2 = (a.N0 * a.S20 + ss) / s_sc[2 + (k & 1)];
-        } else __syncthreads();
-        if (tid == 0) {
-            s2_cnt += 1.0;
-            s2_sum += sigma2;
-            const double sq = sqrt(sigma2), d1 = sq - sq_mean;
-            sq_mean += d1 / s2_cnt;
-            sq_M2 = fma(d1, sq - sq_mean, sq_M2);
-            if (a.flags) a.flags[(size_t)ch * a.nsimu + k] = fl;
-        }
-        emit_row(k);
-
-        TC_PHASE(4);
-        // ---- 6. adaptation
-        if (a.adaptint > 0 && isimu % a.adaptint == 0) {
+        if (first < nb) {
+            // the accepting warp's proposal becomes the state
+            const double *ya = cx.warp_y(first, s_res[first].acc == 2 ? 1 : 0);
             __syncthreads();
-            if (a.do_cov) {
-                // fold rows [isimu-adaptint, isimu) into the running (cmean, M2): Chan's block update
-                const int m = a.adaptint;
-                for (int i = tid; i < npar; i += nt) {
-                    double s = 0.0;
-                    for (int r = 0; r < m; ++r) s += gRows[(size_t)r * ld + i];
-                    const double mb = s / m;
-                    cs.mb[i] = mb;
-                    cs.dm[i] = mb - cmean[i];
-                }
-                const double fcorr = cov_n * m / (cov_n + m);
-                const int ntile = (npar + 3) >> 2, T = ntile * (ntile + 1) / 2;
-                for (int base = 0; base < T; base += 2 * nt) {
-                    int tix[2] = {base + tid, base + nt + tid}, bi[2], bj[2];
-                    double acc[2][16];
-#pragma unroll
-                    for (int u = 0; u < 2; ++u) {
-                        int rem = tix[u] < T ? tix[u] : 0, b = 0;
-                        while (rem >= ntile - b) { rem -= ntile - b; ++b; }
-                        bi[u] = b; bj[u] = b + rem;
-#pragma unroll
-                        for (int e = 0; e < 16; ++e) acc[u][e] = 0.0;
-                    }
-                    for (int r0 = 0; r0 < m; r0 += COV_RC) {
-                        const int rc = min(COV_RC, m - r0);
-                        __syncthreads();
-                        for (int e = tid; e < rc * npad; e += nt) {
-                            const int r = e / npad, c = e - r * npad;
-                            cs.chunk[e] = c < npar ? gRows[(size_t)(r0 + r) * ld + c] - cs.mb[c] : 0.0;
-                        }
-                        __syncthreads();
-#pragma unroll
-                        for (int u = 0; u < 2; ++u) {
-                            if (tix[u] >= T) continue;
-                            for (int r = 0; r < rc; ++r) {
-                                const double2 *ra = reinterpret_cast<const double2 *>(cs.chunk + r * npad + 4 * bi[u]);
-                                const double2 *rb = reinterpret_cast<const double2 *>(cs.chunk + r * npad + 4 * bj[u]);
-                                const double2 a0 = ra[0], a1 = ra[1], b0 = rb[0], b1 = rb[1];
-                                const double av[4] = {a0.x, a0.y, a1.x, a1.y}, bv[4] = {b0.x, b0.y, b1.x, b1.y};
-#pragma unroll
-                                for (int ii = 0; ii < 4; ++ii)
-#pragma unroll
-                                    for (int jj = 0; jj < 4; ++jj) acc[u][4 * ii + jj] = fma(av[ii], bv[jj], acc[u][4 * ii + jj]);
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int u = 0; u < 2; ++u) {
-                        if (tix[u] >= T) continue;
-#pragma unroll
-                        for (int ii = 0; ii < 4; ++ii)
-#pragma unroll
-                            for (int jj = 0; jj < 4; ++jj) {
-                                const int pp = 4 * bi[u] + ii, qq = 4 * bj[u] + jj;
-                                if (pp <= qq && qq < npar)
-                                    gM2[pidx(npar, pp, qq)] += acc[u][4 * ii + jj] + fcorr * cs.dm[pp] * cs.dm[qq];
-                            }
-                    }
-                }
-                __syncthreads();
-                for (int i = tid; i < npar; i += nt) cmean[i] += cs.dm[i] * (m / (cov_n + m));
-                cov_n += m;
-                __syncthreads();
-            }
-            TC_PHASE(5);
-            if (isimu < a.burnintime) {
-                const double rate = a.burnin_cumulative ? (double)rej / isimu : (double)reju / a.adaptint;
-                double f = 1.0;
-                if (rate > 0.95) f = 1.0 / a.burnin_scale;
-                else if (rate < 0.05) f = a.burnin_scale;
-                if (f != 1.0) {
-                    if (r_diag) for (int i = tid; i < npar; i += nt) cs.rdiag[i] *= f;
-                    else for (int i = tid; i < npk; i += nt) { cs.R[i] *= f; gRb[i] = cs.R[i]; }
-                    __syncthreads();
-                }
-                reju = 0;
-            } else {
-                // R = chol(cov + qcovadj I) * adascale
-                for (int i = tid; i < npk; i += nt) cs.R[i] = gM2[i] / (cov_n - 1.0);
-                __syncthreads();
-                for (int i = tid; i < npar; i += nt) cs.R[pidx(npar, i, i)] += a.qcovadj;
-                __syncthreads();
-                const bool ok = chol_packed(npar, cs.R, &s_sc[1]);
-                __syncthreads();
-                if (ok) {
-                    for (int i = tid; i < npk; i += nt) { const double r = cs.R[i] * adascale; cs.R[i] = r; gRb[i] = r; }
-                    r_diag = false;
-                    ++n_adapt;
-                } else {
-                    ++n_cholfail;
-                    if (!r_diag) for (int i = tid; i < npk; i += nt) cs.R[i] = gRb[i];
-                }
-                __syncthreads();
-                reju = 0;
-            }
-            TC_PHASE(6);
+#pragma unroll 1
+            for (int i = tid; i < npar; i += DRAM_THREADS) cx.x[i] = ya[i];
+            ss = s_res[first].ssn; pri = s_res[first].prin;
+            if (s_res[first].acc == 1) ++n_acc1; else ++n_acc2;
+            if (a.updatesigma) sigma2 = (a.N0 * a.S20 + ss) / cx.slot_sc(k + first)[2];
+            __syncthreads();
+            wcnt = emit_rows(a, cx, k + first, 1, cx.x, wcnt);
+            if (tid == 0) emit_s2(a, cx, &s_s2, k + first, sigma2, ss, s_res[first].fl);
+        }
+        k += ncommit;
+        __syncthreads();
+        if (tid == 0) TC_PHASE(2);
+
+        // adaptation after the step with isimu = k, a multiple of adaptint
+        if (a.adaptint > 0 && k % a.adaptint == 0) {
+            const double rate = a.burnin_cumulative ? (double)rej / k : (double)reju / a.adaptint;
+            const int rc = adapt(a, cx, k, cov_n, rate, r_diag, &s_sc[0]);
+            if (a.do_cov) cov_n += a.adaptint;
+            if (rc == 1) { r_diag = false; ++n_adapt; }
+            else if (rc == 2) ++n_cholfail;
+            reju = 0;
+            if (tid == 0) TC_PHASE(3);
         }
     }
 
     // ---- summaries (TranscriptionCycleMCMC.m:286-303)
     __syncthreads();
-    for (int i = tid; i < npar; i += nt) {
-        if (a.mean) a.mean[(size_t)ch * ld + i] = cs.wmean[i];
-        if (a.std) a.std[(size_t)ch * ld + i] = wcnt > 0 ? sqrt(cs.wM2[i] / wcnt) : 0.0;
+#pragma unroll 1
+    for (int i = tid; i < npar; i += DRAM_THREADS) {
+        if (a.mean) a.mean[(size_t)ch * a.ld + i] = bad0 ? 0.0 : cx.wmean[i];
+        if (a.std) a.std[(size_t)ch * a.ld + i] = (!bad0 && wcnt > 0) ? sqrt(cx.wM2[i] / wcnt) : 0.0;
     }
     if (tid == 0) {
         if (a.sig) {
-            a.sig[2 * (size_t)ch] = sqrt(s2_sum / s2_cnt);
-            a.sig[2 * (size_t)ch + 1] = sqrt(sq_M2 / s2_cnt);
+            a.sig[2 * (size_t)ch] = bad0 ? 0.0 : sqrt(s_s2.sum / s_s2.cnt);
+            a.sig[2 * (size_t)ch + 1] = bad0 ? 0.0 : sqrt(s_s2.sq_M2 / s_s2.cnt);
         }
         if (a.counters) {
             long long *c = a.counters + (size_t)ch * TC_NCOUNTERS;
             c[TC_CNT_SS_EVALS] = n_ss; c[TC_CNT_ACC_STAGE1] = n_acc1; c[TC_CNT_ACC_STAGE2] = n_acc2;
             c[TC_CNT_OUT_OF_BOUNDS] = n_oob; c[TC_CNT_ADAPTATIONS] = n_adapt;
             c[TC_CNT_CHOL_FAIL] = n_cholfail; c[TC_CNT_DR_TRIES] = n_dr; c[TC_CNT_STATUS] = bad0 ? 1 : 0;
-            for (int i = 0; i < 8; ++i) c[TC_CNT_CYCLES0 + i] = pc[i];
+            for (int i = 0; i < 4; ++i) c[TC_CNT_CYCLES0 + i] = pc[i];
+            c[TC_CNT_CYCLES0 + 4] = 0; c[TC_CNT_CYCLES0 + 5] = 0; c[TC_CNT_CYCLES0 + 6] = 0;
+            c[TC_CNT_CYCLES0 + 7] = n_spec;
         }
     }
 }
@@ -769,12 +1035,13 @@ static int launch_ss(const tc_cells *c, const DevCells *dc, long long nbatch, co
     SsArgs a{};
     a.cells = dc->d; a.cons = c->cons; a.nbatch = nbatch; a.cell_id = d_cell; a.theta = d_theta; a.ld = ld;
     a.algo = algo; a.raw_grid = raw; a.ldo = ldo; a.ss_out = d_ss; a.out1 = d_o1; a.out2 = d_o2;
-    const size_t smem = sizeof(double) * (size_t)(cell_doubles(c->Nmax) + work_doubles(c->Nmax) + 7 + c->Nmax + 2);
+    a.wsz = (work_doubles(c->Nmax) + 3) & ~1;
+    const size_t smem = sizeof(double) * (size_t)a.wsz * SS_WARPS;
     CUDA_TRY(cudaFuncSetAttribute(ss_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int sms = 0;
     CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dc->device));
-    const long long maxgrid = (long long)sms * 64;
-    const int grid = (int)std::min<long long>(nbatch, maxgrid);
+    const long long want = (nbatch + SS_WARPS - 1) / SS_WARPS, maxgrid = (long long)sms * 16;
+    const int grid = (int)std::min<long long>(want, maxgrid);
     ss_batch_kernel<<<grid, SS_THREADS, smem, st>>>(a);
     CUDA_TRY(cudaGetLastError());
     return TC_OK;
@@ -910,7 +1177,7 @@ int tc_mcmc_run(const tc_cells *c, const tc_mcmc_opts *o, int nchains, const int
     ngpus = std::min(ngpus, nchains);
 
     const int Nmax = c->Nmax, npmax = 7 + Nmax, npad = (npmax + 3) & ~3;
-    const int ldR = npmax * (npmax + 1) / 2;
+    const int ldR = (npmax * (npmax + 1) / 2 + 1) & ~1;    // even: 16-byte cp.async granules
     // does any adaptation with a covariance ever happen?
     bool do_cov = false;
     if (o->adaptint > 0)
@@ -987,14 +1254,13 @@ int tc_mcmc_run(const tc_cells *c, const tc_mcmc_opts *o, int nchains, const int
             CUDA_TRY(r.buf.alloc(a.gRows, (size_t)nc * o->adaptint * ld));
             CUDA_TRY(r.buf.alloc(a.gCmean, (size_t)nc * ld));
         }
-        size_t smem_base = sizeof(double) * (size_t)(cell_doubles(Nmax) + work_doubles(Nmax) + chain_doubles(npmax, npad) + 2);
-        size_t smem_R = sizeof(double) * (size_t)ldR;
+        a.wsz = dram_wsz(Nmax);
+        const size_t smem = sizeof(double) * (size_t)dram_smem_doubles(Nmax);
         int optin = 0;
         CUDA_TRY(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, r.device));
-        a.r_in_smem = (smem_base + smem_R <= (size_t)optin) ? 1 : 0;
-        if (smem_base > (size_t)optin) return fail(TC_EINVAL, "N too large for the shared-memory layout of this build");
-        if (!a.r_in_smem) CUDA_TRY(r.buf.alloc(a.gRw, (size_t)nc * ldR));
-        const size_t smem = smem_base + (a.r_in_smem ? smem_R : 0);
+        if (smem > (size_t)optin || npmax > 256)
+            return fail(TC_EINVAL, "max(N) = " + std::to_string(Nmax) + " is too large for the shared-memory layout of this build "
+                                   "(the Cholesky workspace of the proposal factor must fit in one SM)");
         CUDA_TRY(cudaFuncSetAttribute(dram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CUDA_TRY(cudaEventRecord(r.e0, r.st));
         dram_kernel<<<nc, DRAM_THREADS, smem, r.st>>>(a);
