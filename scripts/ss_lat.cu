@@ -1,4 +1,4 @@
-// Single-CTA latency of ss_eval (development aid): cycles per evaluation, one CTA resident.
+// Single-warp latency of ss_eval (development aid): cycles per evaluation, one warp resident.
 #define TC_SS_PROFILE
 #include <cstdio>
 #include <vector>
@@ -8,14 +8,13 @@
 using namespace tc;
 __global__ void k(tc_construct C, int N, int algo, int reps, double *out, long long *cyc)
 {
-    extern __shared__ __align__(16) double smem[];
-    double *p = smem; CellView cv; Work w;
-    carve_cell(p, N, cv); carve_work(p, N, w);
-    double *th = p;
+    SmemCell cv; Work w;
+    int o = carve_cell(0, N, cv); o = carve_work(o, N, w);
+    double *th = tc_smem + o; const int o_th = o;
     const double d = 0.2521;
     for (int i = threadIdx.x; i < N; i += blockDim.x) {
-        cv.tg[i] = d * i; cv.dtg[i] = d; cv.ms2[i] = (i % 3 == 0) ? NAN : 0.02 * i; cv.pp7[i] = 0.05 * i;
-        cv.iw[i] = 0.3; cv.ik[i] = min(i, N - 2);
+        tc_smem[cv.o_tg + i] = d * i; tc_smem[cv.o_dtg + i] = d; tc_smem[cv.o_ms2 + i] = (i % 3 == 0) ? NAN : 0.02 * i; tc_smem[cv.o_pp7 + i] = 0.05 * i;
+        tc_smem[cv.o_iw + i] = 0.3; reinterpret_cast<int *>(tc_smem + cv.o_ik)[i] = min(i, N - 2);
     }
     cv.d = d;
     for (int i = threadIdx.x; i < 7 + N; i += blockDim.x) th[i] = 0.0;
@@ -25,7 +24,7 @@ __global__ void k(tc_construct C, int N, int algo, int reps, double *out, long l
     __syncthreads();
     double acc = 0;
     long long t0 = clock64();
-    for (int r = 0; r < reps; ++r) { th[1] = 2.0 + 1e-3 * (r & 7); acc += ss_eval(C, cv, th, w, algo, false, nullptr, nullptr); }
+    for (int r = 0; r < reps; ++r) { th[1] = 2.0 + 1e-3 * (r & 7); acc += ss_eval(C, cv, SmemVec{o_th}, w, algo, false, nullptr, nullptr); __syncwarp(); }
     long long t1 = clock64();
     if (threadIdx.x == 0) { out[0] = acc; cyc[0] = (t1 - t0) / reps; }
 }
@@ -34,12 +33,12 @@ int main()
     tc_construct C{}; C.nsets = 1; C.L_ms2 = C.L_pp7 = 6.626; C.ms2_start[0] = 0.024; C.ms2_end[0] = 1.299; C.ms2_loopn[0] = 24;
     C.pp7_start[0] = 4.292; C.pp7_end[0] = 5.758; C.pp7_loopn[0] = 24;
     double *out; long long *cyc; cudaMallocManaged(&out, 8); cudaMallocManaged(&cyc, 8);
-    for (int N : {120, 400}) for (int algo : {1, 0}) for (int nt : {128, 256}) {
+    for (int N : {120, 400}) for (int algo : {1, 0}) for (int nt : {32}) {
         size_t sm = sizeof(double) * (cell_doubles(N) + work_doubles(N) + 7 + N + 2);
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         k<<<1, nt, sm>>>(C, N, algo, 200, out, cyc); cudaDeviceSynchronize();
         long long pr[8]; cudaMemcpyFromSymbol(pr, tc_ss_prof, sizeof(pr)); long long z[8] = {0}; cudaMemcpyToSymbol(tc_ss_prof, z, sizeof(z));
-        printf("N=%d algo=%d threads=%d: %lld cycles/eval (ss=%g) phases: rd %lld scan/tables %lld rows %lld resid %lld reduce %lld %s\n", N, algo, nt, cyc[0], out[0] / 200,
+        printf("N=%d algo=%d threads=%d: %lld cycles/eval (ss=%g) phases: scan %lld tables %lld rows %lld resid %lld reduce %lld %s\n", N, algo, nt, cyc[0], out[0] / 200,
                pr[0] / 200, pr[1] / 200, pr[2] / 200, pr[3] / 200, pr[4] / 200, cudaGetErrorString(cudaGetLastError()));
     }
     return 0;

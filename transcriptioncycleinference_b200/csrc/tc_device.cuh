@@ -73,7 +73,7 @@ __device__ __forceinline__ double u01(uint32_t hi, uint32_t lo)
 __device__ __noinline__ void normal_pair(const u32x4 &r, double &z0, double &z1)
 {
     const double ua = u01(r.x, r.y), ub = u01(r.z, r.w);
-    const double rad = sqrt(-2.0 * tc_log(ua));
+    const double rad = sqrt(-2.0 * log(ua));     // inlined here: overlaps with sincospi below
     double s, c;
     sincospi(2.0 * ub, &s, &c);
     z0 = rad * c;
@@ -115,43 +115,74 @@ __device__ __forceinline__ double warp_sum(double v)
 }
 
 // ------------------------------------------------------------------------- shared-memory views
-struct CellView {        // one cell's constants, staged in shared memory
-    int N;
-    double d;            // mean(diff(t))                       SumofSquares...m:29
-    double *tg;          // grid the model runs on (t_interp, or raw t)  [N]
-    double *dtg;         // tg[i+1]-tg[i]                        [N]   ConstantElongationSim.m:43-45
-    double *ms2, *pp7;   // data, NaN = missing                  [N]
-    double *iw;          // interp1 weight of experimental time j [N]
-    int *ik;             // interp1 bracketing index (-1: outside) [N]
+// All dynamic shared memory of the library's kernels is this one array.  The forward model addresses
+// it by OFFSET (in doubles), never through generic pointers, so that every access compiles to
+// LDS/STS with an immediate offset instead of a generic LD/ST plus pointer traffic through local
+// memory (measured: ~2x on the latency of one evaluation).
+extern __shared__ __align__(16) double tc_smem[];
+
+struct SmemVec {          // a vector in shared memory
+    int off;
+    __device__ __forceinline__ double operator[](int i) const { return tc_smem[off + i]; }
 };
-struct Work {            // per-evaluation scratch in shared memory, each [N+2]
-    double *K, *n, *G1, *G2, *F1, *F2;
-    int *thr;            // 8 lag thresholds
+struct GlobVec {          // a vector in global memory
+    const double *p;
+    __device__ __forceinline__ double operator[](int i) const { return p[i]; }
+};
+
+struct SmemCell {         // one cell's constants staged in shared memory (offsets into tc_smem)
+    int N;
+    double d;             // mean(diff(t))                       SumofSquares...m:29
+    int o_tg, o_dtg, o_ms2, o_pp7, o_iw, o_ik;
+    __device__ __forceinline__ double tg(int i) const { return tc_smem[o_tg + i]; }     // model grid
+    __device__ __forceinline__ double dtg(int i) const { return tc_smem[o_dtg + i]; }   // tg[i+1]-tg[i]
+    __device__ __forceinline__ double ms2(int i) const { return tc_smem[o_ms2 + i]; }   // data, NaN = missing
+    __device__ __forceinline__ double pp7(int i) const { return tc_smem[o_pp7 + i]; }
+    __device__ __forceinline__ double iw(int i) const { return tc_smem[o_iw + i]; }     // interp1 weight
+    __device__ __forceinline__ int ik(int i) const { return reinterpret_cast<const int *>(tc_smem + o_ik)[i]; }
+};
+struct GlobCell {         // the same view straight onto the device-resident dataset
+    int N;
+    double d;
+    const double *p_tg, *p_dtg, *p_ms2, *p_pp7, *p_iw;
+    const int *p_ik;
+    __device__ __forceinline__ double tg(int i) const { return p_tg[i]; }
+    __device__ __forceinline__ double dtg(int i) const { return p_dtg[i]; }
+    __device__ __forceinline__ double ms2(int i) const { return p_ms2[i]; }
+    __device__ __forceinline__ double pp7(int i) const { return p_pp7[i]; }
+    __device__ __forceinline__ double iw(int i) const { return p_iw[i]; }
+    __device__ __forceinline__ int ik(int i) const { return p_ik[i]; }
+};
+struct Work {             // one warp's forward-model scratch (offsets into tc_smem), each [N+2]
+    int K, n, G1, G2, F1, F2, thr;
 };
 
 __host__ __device__ inline int work_doubles(int N) { return 6 * (N + 2) + 4 + 1; }
 __host__ __device__ inline int cell_doubles(int N) { return 5 * (N + 1) + (N + 2) / 2 + 1; }
 
-__device__ inline void carve_cell(double *&p, int N, CellView &cv)
+// carve from offset `o` (doubles); returns the next free offset
+__device__ inline int carve_cell(int o, int N, SmemCell &cv)
 {
     cv.N = N;
-    cv.tg = p; p += N + 1;
-    cv.dtg = p; p += N + 1;
-    cv.ms2 = p; p += N + 1;
-    cv.pp7 = p; p += N + 1;
-    cv.iw = p; p += N + 1;
-    cv.ik = reinterpret_cast<int *>(p); p += (N + 2) / 2 + 1;
+    cv.o_tg = o; o += N + 1;
+    cv.o_dtg = o; o += N + 1;
+    cv.o_ms2 = o; o += N + 1;
+    cv.o_pp7 = o; o += N + 1;
+    cv.o_iw = o; o += N + 1;
+    cv.o_ik = o; o += (N + 2) / 2 + 1;
+    return o;
 }
-__device__ inline void carve_work(double *&p, int N, Work &w)
+__device__ inline int carve_work(int o, int N, Work &w)
 {
-    p += (reinterpret_cast<uintptr_t>(p) >> 3) & 1;       // 16-byte align (thr is read as int4)
-    w.thr = reinterpret_cast<int *>(p); p += 4;
-    w.K = p; p += N + 2;
-    w.n = p; p += N + 2;
-    w.G1 = p; p += N + 2;
-    w.G2 = p; p += N + 2;
-    w.F1 = p; p += N + 2;
-    w.F2 = p; p += N + 2;
+    o += o & 1;                                            // 16-byte align (thr is read as int4)
+    w.thr = o; o += 4;
+    w.K = o; o += N + 2;
+    w.n = o; o += N + 2;
+    w.G1 = o; o += N + 2;
+    w.G2 = o; o += N + 2;
+    w.F1 = o; o += N + 2;
+    w.F2 = o; o += N + 2;
+    return o;
 }
 
 struct CellsDev {        // device-resident packed dataset (one per device)
@@ -162,37 +193,38 @@ struct CellsDev {        // device-resident packed dataset (one per device)
     const int *ik;
 };
 
-// stage cell `cid` into shared memory; raw_grid selects the raw experimental times as model grid
-__device__ inline void load_cell(const CellsDev &cd, int cid, bool raw_grid, CellView &cv)
+// stage cell `cid` into shared memory (whole CTA); raw_grid selects the raw experimental times
+__device__ inline void load_cell(const CellsDev &cd, int cid, bool raw_grid, SmemCell &cv)
 {
     const int N = cv.N;
     const long long o = cd.off[cid];
     const double *gr = raw_grid ? cd.t : cd.tg;
     const double *dg = raw_grid ? cd.dtraw : cd.dtg;
+    int *ikp = reinterpret_cast<int *>(tc_smem + cv.o_ik);
+#pragma unroll 1
     for (int i = threadIdx.x; i < N; i += blockDim.x) {
-        cv.tg[i] = gr[o + i];
-        cv.dtg[i] = dg[o + i];
-        cv.ms2[i] = cd.ms2[o + i];
-        cv.pp7[i] = cd.pp7[o + i];
-        cv.iw[i] = cd.iw[o + i];
-        cv.ik[i] = cd.ik[o + i];
+        tc_smem[cv.o_tg + i] = gr[o + i];
+        tc_smem[cv.o_dtg + i] = dg[o + i];
+        tc_smem[cv.o_ms2 + i] = cd.ms2[o + i];
+        tc_smem[cv.o_pp7 + i] = cd.pp7[o + i];
+        tc_smem[cv.o_iw + i] = cd.iw[o + i];
+        ikp[i] = cd.ik[o + i];
     }
     cv.d = cd.dmean[cid];
 }
-
-// a view straight onto the device-resident dataset (no staging: the batched ssfun kernel reads every
-// element once or twice per evaluation)
-__device__ inline void view_cell(const CellsDev &cd, int cid, bool raw_grid, CellView &cv)
+__device__ inline GlobCell view_cell(const CellsDev &cd, int cid, bool raw_grid)
 {
     const long long o = cd.off[cid];
+    GlobCell cv;
     cv.N = cd.N[cid];
     cv.d = cd.dmean[cid];
-    cv.tg = const_cast<double *>((raw_grid ? cd.t : cd.tg) + o);
-    cv.dtg = const_cast<double *>((raw_grid ? cd.dtraw : cd.dtg) + o);
-    cv.ms2 = const_cast<double *>(cd.ms2 + o);
-    cv.pp7 = const_cast<double *>(cd.pp7 + o);
-    cv.iw = const_cast<double *>(cd.iw + o);
-    cv.ik = const_cast<int *>(cd.ik + o);
+    cv.p_tg = (raw_grid ? cd.t : cd.tg) + o;
+    cv.p_dtg = (raw_grid ? cd.dtraw : cd.dtg) + o;
+    cv.p_ms2 = cd.ms2 + o;
+    cv.p_pp7 = cd.pp7 + o;
+    cv.p_iw = cd.iw + o;
+    cv.p_ik = cd.ik + o;
+    return cv;
 }
 
 // ------------------------------------------------------------------------- forward model pieces
@@ -208,22 +240,24 @@ __device__ __forceinline__ double loop_response(double p, double s, double e, do
 
 // per-step loading increment rho_i*delta_i; zero before onset (the reference `continue`s, which
 // leaves the counter unchanged)                      ConstantElongationSim.m:33-36,57-60
-__device__ __forceinline__ double load_increment(const CellView &cv, const double *th, int i, double R, double ton)
+template <class Cell, class Vec>
+__device__ __forceinline__ double load_increment(const Cell &cv, const Vec &th, int i, double R, double ton)
 {
     double r = R + th[7 + i];                                 // SumofSquares...m:45
     r = r < 0.0 ? 0.0 : r;
-    return (cv.tg[i] < ton) ? 0.0 : __dmul_rn(r, cv.dtg[i]);
+    return (cv.tg(i) < ton) ? 0.0 : __dmul_rn(r, cv.dtg(i));
 }
 
 // the reference's own order: one lane, sequential (rare fallback; kept out of line)
-__device__ __noinline__ void scan_counts_sequential(const CellView &cv, const double *th, double R, double ton, double *K)
+template <class Cell, class Vec>
+__device__ __noinline__ void scan_counts_sequential(Cell cv, Vec th, double R, double ton, int oK)
 {
     double c = 0.0;
-    K[0] = 0.0;
+    tc_smem[oK] = 0.0;
 #pragma unroll 1
     for (int i = 0; i < cv.N - 1; ++i) {
         c = __dadd_rn(c, load_increment(cv, th, i, R, ton));
-        K[i + 1] = floor(c);
+        tc_smem[oK + i + 1] = floor(c);
     }
 }
 
@@ -234,18 +268,19 @@ __device__ __noinline__ void scan_counts_sequential(const CellView &cv, const do
 // warp scans per pass; if any partial sum lands within 1e-7 of an integer — where a different
 // association could flip a floor — lane 0 redoes the sum sequentially.  Error bound of either
 // order: (N-1) * eps * max(c) < 400 * 1.1e-16 * 3e4 << 1e-7, so the two paths agree otherwise.
-__device__ inline void scan_counts(const CellView &cv, const double *th, double R, double ton, double *K,
-                                   double *nco, bool force_sequential)
+template <class Cell, class Vec>
+__device__ __forceinline__ void scan_counts(const Cell &cv, const Vec &th, double R, double ton, const Work &w,
+                                            bool force_sequential)
 {
     const int lane = threadIdx.x & 31;
     const int n = cv.N - 1;                        // increments i = 0..n-1
     bool redo = force_sequential;
     if (!force_sequential) {
-        double carry = 0.0;
+        double carry = 0.0, fprev = 0.0;           // fprev: floor of the last element of the previous row
         bool risky = false;
 #pragma unroll 1
         for (int r0 = 0; r0 < n; r0 += 128) {
-            double v[4];
+            double v[4], tot[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int i = r0 + 32 * u + lane;
@@ -260,62 +295,73 @@ __device__ inline void scan_counts(const CellView &cv, const double *th, double 
                 }
             }
 #pragma unroll
+            for (int u = 0; u < 4; ++u) tot[u] = __shfl_sync(0xffffffffu, v[u], 31);
+#pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int i = r0 + 32 * u + lane;
                 const double c = __dadd_rn(carry, v[u]);
                 const double f = floor(c);
                 // c == 0: every increment so far is exactly 0 (they are all >= 0): exact in any order
                 risky |= (i < n) && (c != 0.0) && ((c - f < 1e-7) || (f + 1.0 - c < 1e-7));
-                if (i < n) K[i + 1] = f;
-                carry = __dadd_rn(carry, __shfl_sync(0xffffffffu, v[u], 31));
+                // cohort size = f - (floor of the previous element): lane-1 of this row, or the end of the previous row
+                double fl = __shfl_up_sync(0xffffffffu, f, 1);
+                if (lane == 0) fl = fprev;
+                if (i < n) { tc_smem[w.K + i + 1] = f; tc_smem[w.n + i] = f - fl; }
+                fprev = __shfl_sync(0xffffffffu, f, 31);
+                carry = __dadd_rn(carry, tot[u]);
             }
         }
-        if (lane == 0) K[0] = 0.0;
+        if (lane == 0) tc_smem[w.K] = 0.0;
         redo = __any_sync(0xffffffffu, risky);
     }
-    if (redo && lane == 0) scan_counts_sequential(cv, th, R, ton, K);
-    __syncwarp();
+    if (redo) {
+        if (lane == 0) scan_counts_sequential(cv, th, R, ton, w.K);
+        __syncwarp();
 #pragma unroll 1
-    for (int i = lane; i < n; i += 32) nco[i] = K[i + 1] - K[i];
+        for (int i = lane; i < n; i += 32) tc_smem[w.n + i] = tc_smem[w.K + i + 1] - tc_smem[w.K + i];
+    }
 }
 
-// smallest lag in [1, N] with v*(d*lag) > x (strict) or >= x; N when none
-__device__ inline int first_lag(double v, double d, double x, int N, bool strict)
+// smallest lag in [1, N] with v*(d*lag) > x (strict) or >= x; N when none.  inv_vd = 1/(v d) only seeds
+// the guess; membership is always decided by the exact predicate on p = v*(d*lag).
+__device__ __forceinline__ int first_lag(double v, double d, double inv_vd, double x, int N, bool strict)
 {
-    const double vd = v * d;
-    if (!(vd > 0.0)) return N;
-    double q = floor(x / vd);
+    if (!(v * d > 0.0)) return N;
+    const double q = floor(x * inv_vd);
     int g = q < 1.0 ? 1 : (q > (double)N ? N : (int)q);
     auto pred = [&](int lag) {
         const double p = v * (d * (double)lag);
         return strict ? (p > x) : (p >= x);
     };
+#pragma unroll 1
     while (g > 1 && pred(g - 1)) --g;
+#pragma unroll 1
     while (g < N && !pred(g)) ++g;
     return g;
 }
 
 // TC_ALGO_PAIRS: every (cohort i, time j) pair with the literal response at p = v*(t_j - t_i); any grid
-__device__ __noinline__ void rows_pairs(const CellView &cv, Work &w, int s, double v, double s1, double e1, double L1,
+template <class Cell>
+__device__ __noinline__ void rows_pairs(Cell cv, Work w, int s, double v, double s1, double e1, double L1,
                                         double f1, double b1, double s2, double e2, double L2, double f2, double b2)
 {
     const int N = cv.N, lane = threadIdx.x & 31;
 #pragma unroll 1
     for (int j = lane; j < N; j += 32) {
         double a1 = 0.0, a2 = 0.0;
-        const double tj = cv.tg[j];
+        const double tj = cv.tg(j);
 #pragma unroll 2
         for (int i = 0; i < j; ++i) {
-            const double ni = w.n[i];
+            const double ni = tc_smem[w.n + i];
             if (ni > 0.0) {
-                const double p = v * (tj - cv.tg[i]);
+                const double p = v * (tj - cv.tg(i));
                 a1 = fma(ni, loop_response(p, s1, e1, L1, f1), a1);
                 a2 = fma(ni, loop_response(p, s2, e2, L2, f2), a2);
             }
         }
-        if (s > 0) { a1 += w.F1[j]; a2 += w.F2[j]; }
-        w.F1[j] = a1 < b1 ? b1 : a1;
-        w.F2[j] = a2 < b2 ? b2 : a2;
+        if (s > 0) { a1 += tc_smem[w.F1 + j]; a2 += tc_smem[w.F2 + j]; }
+        tc_smem[w.F1 + j] = a1 < b1 ? b1 : a1;
+        tc_smem[w.F2 + j] = a2 < b2 ? b2 : a2;
     }
 }
 
@@ -326,11 +372,13 @@ __device__ __noinline__ void rows_pairs(const CellView &cv, Work &w, int s, doub
 #endif
 
 // The residual sum of squares of one (cell, theta) — SumofSquares...m:1-65 — by ONE WARP.
-// th: theta (shared or global); w: this warp's private scratch.  On return every lane holds SS.
+// Cell / Vec say where the cell constants and theta live (shared memory in the sampler, global memory
+// in the batched ssfun kernel); w is this warp's private scratch.  On return every lane holds SS.
 // When out1/out2 != nullptr the model curves [A*MS2, PP7] on the model grid are also written there
 // (tc_forward).  All 32 lanes must call this.
-__device__ __noinline__ double ss_eval(const tc_construct &C, const CellView &cv, const double *th, Work &w, int algo,
-                                 bool seq_scan, double *out1, double *out2)
+template <class Cell, class Vec>
+__device__ __noinline__ double ss_eval(const tc_construct &C, Cell cv, Vec th, Work w, int algo, bool seq_scan,
+                                       double *out1, double *out2)
 {
     const int N = cv.N, lane = threadIdx.x & 31;
     const double v = th[0], tau = th[1], ton = th[2], b1 = th[3], b2 = th[4], A = th[5], R = th[6];
@@ -338,56 +386,78 @@ __device__ __noinline__ double ss_eval(const tc_construct &C, const CellView &cv
     long long tp__ = clock64();
 #endif
     // (a) loaded-polymerase counts K and cohort sizes n
-    scan_counts(cv, th, R, ton, w.K, w.n, seq_scan);
+    scan_counts(cv, th, R, ton, w, seq_scan);
     __syncwarp();
     SS_MARK(0);
     // (b) fluorescence per time point, one loop set at a time: the basal clamp sits inside the
     //     per-set loop in the reference (GetFluorFromPolPos.m:47,57,69)
     const double tv = tau * v;
     const double L1 = C.L_ms2 + tv, L2 = C.L_pp7 + tv;        // :19-20
+#pragma unroll 1
     for (int s = 0; s < C.nsets; ++s) {
-        const double s1 = C.ms2_start[s], e1 = C.ms2_end[s], f1 = C.ms2_loopn[s] / 24.0;
-        const double s2 = C.pp7_start[s], e2 = C.pp7_end[s], f2 = C.pp7_loopn[s] / 24.0;
+        const double s1 = C.ms2_start[s], e1 = C.ms2_end[s], f1 = C.ms2_loopn[s] * (1.0 / 24.0);
+        const double s2 = C.pp7_start[s], e2 = C.pp7_end[s], f2 = C.pp7_loopn[s] * (1.0 / 24.0);
         if (algo == TC_ALGO_TOEPLITZ) {
             // lag thresholds of the piecewise response, by exact predicate on p = v*(d*lag):
             // ramp = [la, le), plateau = [lb, lL); lanes 0-3: MS2, lanes 4-7: PP7
+            int *thr = reinterpret_cast<int *>(tc_smem + w.thr);
             if (lane < 8) {
+                const double inv_vd = 1.0 / (v * cv.d);
                 const bool c2 = lane >= 4;
                 const int q = lane & 3;
                 const double x = q == 0 ? (c2 ? s2 : s1) : (q == 3 ? (c2 ? L2 : L1) : (c2 ? e2 : e1));
-                w.thr[lane] = first_lag(v, cv.d, x, N, (q & 1) == 0);        // >s, >=e, >e, >=L
+                thr[lane] = first_lag(v, cv.d, inv_vd, x, N, (q & 1) == 0);        // >s, >=e, >e, >=L
             }
+            const double sc1 = f1 / (e1 - s1), sc2 = f2 / (e2 - s2);      // overlaps with the lanes above
             __syncwarp();
-            const int4 t1 = *reinterpret_cast<const int4 *>(w.thr), t2 = *reinterpret_cast<const int4 *>(w.thr + 4);
+            const int4 t1 = *reinterpret_cast<const int4 *>(thr), t2 = *reinterpret_cast<const int4 *>(thr + 4);
             const int la1 = t1.x, le1 = t1.y, lb1 = t1.z, lL1 = t1.w;
             const int la2 = t2.x, le2 = t2.y, lb2 = t2.z, lL2 = t2.w;
-            {   // ramp part of the per-lag response table
-                const double sc1 = f1 / (e1 - s1), sc2 = f2 / (e2 - s2);
+            // ramp part of the per-lag response table
 #pragma unroll 1
-                for (int lag = la1 + lane; lag < le1; lag += 32) w.G1[lag] = (v * (cv.d * (double)lag) - s1) * sc1;
+            for (int lag = la1 + lane; lag < le1; lag += 32) tc_smem[w.G1 + lag] = (v * (cv.d * (double)lag) - s1) * sc1;
 #pragma unroll 1
-                for (int lag = la2 + lane; lag < le2; lag += 32) w.G2[lag] = (v * (cv.d * (double)lag) - s2) * sc2;
-            }
+            for (int lag = la2 + lane; lag < le2; lag += 32) tc_smem[w.G2 + lag] = (v * (cv.d * (double)lag) - s2) * sc2;
             __syncwarp();
             SS_MARK(1);
+            // four time points per lane at once (unroll-and-jam): 8 independent FMA chains, the
+            // response table is read once per lag
 #pragma unroll 1
-            for (int j = lane; j < N; j += 32) {
-                double a1 = 0.0, a2 = 0.0;
-                const int len1 = min(le1 - 1, j) - la1 + 1, len2 = min(le2 - 1, j) - la2 + 1;
-                const int len = max(len1, len2);
-                const double *n1p = w.n + (j - la1), *n2p = w.n + (j - la2);
-                const double *g1p = w.G1 + la1, *g2p = w.G2 + la2;
-#pragma unroll 2
-                for (int t = 0; t < len; ++t) {            // the two colours interleaved for ILP
-                    if (t < len1) a1 = fma(n1p[-t], g1p[t], a1);
-                    if (t < len2) a2 = fma(n2p[-t], g2p[t], a2);
+            for (int jb = lane; jb < N; jb += 128) {
+                double a1[4], a2[4];
+                int l1[4], l2[4], len = 0;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int j = jb + 32 * u;
+                    a1[u] = 0.0; a2[u] = 0.0;
+                    l1[u] = j < N ? min(le1 - 1, j) - la1 + 1 : 0;
+                    l2[u] = j < N ? min(le2 - 1, j) - la2 + 1 : 0;
+                    len = max(len, max(l1[u], l2[u]));
                 }
-                // plateau: cohorts with lag in [lb, lL) are whole polymerases -> exact count
-                if (j >= lb1 && lb1 < lL1) a1 = fma(f1, w.K[j - lb1 + 1] - w.K[max(j - lL1 + 1, 0)], a1);
-                if (j >= lb2 && lb2 < lL2) a2 = fma(f2, w.K[j - lb2 + 1] - w.K[max(j - lL2 + 1, 0)], a2);
-                if (s > 0) { a1 += w.F1[j]; a2 += w.F2[j]; }
-                w.F1[j] = a1 < b1 ? b1 : a1;                  // :57
-                w.F2[j] = a2 < b2 ? b2 : a2;                  // :69
+                const int n1o = w.n + (jb - la1), n2o = w.n + (jb - la2);
+#pragma unroll 1
+                for (int t = 0; t < len; ++t) {
+                    const double g1 = la1 + t < le1 ? tc_smem[w.G1 + la1 + t] : 0.0;
+                    const double g2 = la2 + t < le2 ? tc_smem[w.G2 + la2 + t] : 0.0;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (t < l1[u]) a1[u] = fma(tc_smem[n1o + 32 * u - t], g1, a1[u]);
+                        if (t < l2[u]) a2[u] = fma(tc_smem[n2o + 32 * u - t], g2, a2[u]);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int j = jb + 32 * u;
+                    if (j < N) {
+                        double c1 = a1[u], c2 = a2[u];
+                        // plateau: cohorts with lag in [lb, lL) are whole polymerases -> exact count
+                        if (j >= lb1 && lb1 < lL1) c1 = fma(f1, tc_smem[w.K + j - lb1 + 1] - tc_smem[w.K + max(j - lL1 + 1, 0)], c1);
+                        if (j >= lb2 && lb2 < lL2) c2 = fma(f2, tc_smem[w.K + j - lb2 + 1] - tc_smem[w.K + max(j - lL2 + 1, 0)], c2);
+                        if (s > 0) { c1 += tc_smem[w.F1 + j]; c2 += tc_smem[w.F2 + j]; }
+                        tc_smem[w.F1 + j] = c1 < b1 ? b1 : c1;                  // :57
+                        tc_smem[w.F2 + j] = c2 < b2 ? b2 : c2;                  // :69
+                    }
+                }
             }
         } else {
             SS_MARK(1);
@@ -398,23 +468,30 @@ __device__ __noinline__ double ss_eval(const tc_construct &C, const CellView &cv
     }
     if (out1) {
 #pragma unroll 1
-        for (int j = lane; j < N; j += 32) { out1[j] = A * w.F1[j]; out2[j] = w.F2[j]; }
+        for (int j = lane; j < N; j += 32) { out1[j] = A * tc_smem[w.F1 + j]; out2[j] = tc_smem[w.F2 + j]; }
     }
 
     // (c) MS2 *= A, interp1 back to the experimental times, NaN-skipping residual sum of squares
     //     SumofSquares...m:51-64
     double acc = 0.0;
 #pragma unroll 1
-    for (int j = lane; j < N; j += 32) {
-        const int k = cv.ik[j];
-        if (k >= 0) {
-            const double wj = cv.iw[j];
-            const double m1 = A * w.F1[k], m1n = A * w.F1[k + 1];
-            const double r1 = cv.ms2[j] - (m1 + wj * (m1n - m1));
-            const double r2 = cv.pp7[j] - (w.F2[k] + wj * (w.F2[k + 1] - w.F2[k]));
-            if (r1 == r1) acc += r1 * r1;                      // nansum
-            if (r2 == r2) acc += r2 * r2;
+    for (int jb = lane; jb < N; jb += 128) {
+        double pa[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = jb + 32 * u;
+            const int k = j < N ? cv.ik(j) : -1;
+            if (k >= 0) {
+                const double wj = cv.iw(j);
+                const double m1 = A * tc_smem[w.F1 + k], m1n = A * tc_smem[w.F1 + k + 1];
+                const double r1 = cv.ms2(j) - (m1 + wj * (m1n - m1));
+                const double f2k = tc_smem[w.F2 + k];
+                const double r2 = cv.pp7(j) - (f2k + wj * (tc_smem[w.F2 + k + 1] - f2k));
+                if (r1 == r1) pa[u] = fma(r1, r1, pa[u]);                      // nansum
+                if (r2 == r2) pa[u] = fma(r2, r2, pa[u]);
+            }
         }
+        acc += (pa[0] + pa[1]) + (pa[2] + pa[3]);
     }
     SS_MARK(3);
     acc = warp_sum(acc);

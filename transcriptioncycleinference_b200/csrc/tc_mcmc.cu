@@ -60,19 +60,17 @@ struct SsArgs {
 // one warp per (cell, theta): no block barriers, cell data and theta read straight from HBM/L2
 __global__ void __launch_bounds__(SS_THREADS) ss_batch_kernel(const __grid_constant__ SsArgs a)
 {
-    extern __shared__ __align__(16) double smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double *base = smem + (size_t)warp * a.wsz;
+    const int base = warp * a.wsz;                          // this warp's scratch (offset into tc_smem)
+#pragma unroll 1
     for (long long b = (long long)blockIdx.x * SS_WARPS + warp; b < a.nbatch; b += (long long)gridDim.x * SS_WARPS) {
         const int cid = a.cell_id[b];
-        CellView cv;
+        const GlobCell cv = view_cell(a.cells, cid, a.raw_grid != 0);
         Work w;
-        view_cell(a.cells, cid, a.raw_grid != 0, cv);
-        double *p = base;
-        carve_work(p, cv.N, w);
+        carve_work(base, cv.N, w);
         double *o1 = a.out1 ? a.out1 + b * a.ldo : nullptr;
         double *o2 = a.out2 ? a.out2 + b * a.ldo : nullptr;
-        const double ss = ss_eval(a.cons, cv, a.theta + b * a.ld, w, a.algo, false, o1, o2);
+        const double ss = ss_eval(a.cons, cv, GlobVec{a.theta + b * a.ld}, w, a.algo, false, o1, o2);
         if (lane == 0 && a.ss_out) a.ss_out[b] = ss;
     }
 }
@@ -98,7 +96,10 @@ struct RunArgs {
     int *flags;
     double *sschain;
     // scratch (global)
-    double *gR, *gM2, *gRows, *gCmean;
+    double *gR, *gM2, *gRows, *gCmean, *gState;
+    // time slicing
+    int seglen, nitems;
+    int *queue, *done;
 };
 
 // Shared-memory budget of the sampler (doubles), N = max time points over the dataset.
@@ -187,7 +188,7 @@ __device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, do
 // per-step result record of the speculative batch (shared memory)
 struct StepRes { double ssn, prin; int acc, fl, nev, noob; };
 // s2chain statistics over ALL rows (TranscriptionCycleMCMC.m:302-303), thread 0, shared memory
-struct S2Stats { double sum, sq_mean, sq_M2, cnt; };
+struct S2Stats { double sum, sq_sum, cnt, pad; };      // sum s2, sum sqrt(s2), rows
 
 // Immutable per-chain context, built once in shared memory so that the out-of-line phases below
 // (kept out of line to keep the hot loop inside the instruction cache) can share it.
@@ -195,19 +196,19 @@ struct ChainCtx {
     int N, npar, npad, npk, ld, slot_sz, wsz, ch, first_row, nstore;
     unsigned long long uid;
     double adascale, inv_dr;
-    CellView cv;
+    SmemCell cv;
+    int o_x, o_U;                                       // offsets (doubles) of x and of the per-warp areas in tc_smem
     double *ring, *x, *lo, *hi, *mu, *pinv, *wmean, *wM2, *rdiag, *mb, *dm, *U;
     double *gRb, *gM2, *gRows, *cmean;
     __device__ __forceinline__ double *slot_d(int step) const { return ring + (size_t)(step % SPEC) * slot_sz; }
     __device__ __forceinline__ double *slot_sc(int step) const { return ring + (size_t)(step % SPEC) * slot_sz + (slot_sz - 8); }
-    // warp wq's proposals live behind its forward-model scratch
-    __device__ __forceinline__ double *warp_y(int wq, int which) const
+    // warp wq's two proposals live behind its forward-model scratch (offset into tc_smem)
+    __device__ __forceinline__ int warp_y(int wq, int which) const
     {
-        double *q = U + (size_t)wq * wsz;
         Work tmp;
-        carve_work(q, N, tmp);
-        q += (reinterpret_cast<uintptr_t>(q) >> 3) & 1;
-        return which ? q + npar + (npar & 1) : q;
+        int o = carve_work(o_U + wq * wsz, N, tmp);
+        o += o & 1;
+        return which ? o + npar + (npar & 1) : o;
     }
 };
 
@@ -248,17 +249,25 @@ __device__ __noinline__ double emit_rows(const RunArgs &a, const ChainCtx &cx, i
     return wcnt;
 }
 
-// per-row scalars (thread 0): s2chain statistics and the optional per-step outputs
-__device__ __noinline__ void emit_s2(const RunArgs &a, const ChainCtx &cx, S2Stats *st, int r, double s2, double ssr, int fl)
+// Per-row scalars of `cnt` committed rows r0.. by the lanes of warp 0 (one row per lane, cnt <= SPEC):
+// sigma2 of the row, s2chain statistics (sum s2, sum sqrt(s2)) and the optional per-step outputs.
+// Rows before `first` keep (ss_old); row `first` (if < cnt) carries the accepted (ss_new).
+__device__ __noinline__ void emit_s2(const RunArgs &a, const ChainCtx &cx, S2Stats *st, const StepRes *res, int r0, int cnt,
+                                     int first, double ss_old, double ss_new, double sigma2_fixed)
 {
-    st->cnt += 1.0;
-    st->sum += s2;
-    const double sq = sqrt(s2), d1 = sq - st->sq_mean;
-    st->sq_mean += d1 / st->cnt;
-    st->sq_M2 = fma(d1, sq - st->sq_mean, st->sq_M2);
-    if (a.store_chain && a.s2chain) a.s2chain[(size_t)cx.ch * a.nsimu + r] = s2;
-    if (a.flags) a.flags[(size_t)cx.ch * a.nsimu + r] = fl;
-    if (a.sschain) a.sschain[(size_t)cx.ch * a.nsimu + r] = ssr;
+    const int lane = threadIdx.x & 31;
+    double s2 = 0.0, sq = 0.0;
+    if (lane < cnt) {
+        const int r = r0 + lane;
+        const double ssr = lane < first ? ss_old : ss_new;
+        s2 = (a.updatesigma && r > 0) ? (a.N0 * a.S20 + ssr) / cx.slot_sc(r)[2] : sigma2_fixed;
+        sq = sqrt(s2);
+        if (a.store_chain && a.s2chain) a.s2chain[(size_t)cx.ch * a.nsimu + r] = s2;
+        if (a.flags) a.flags[(size_t)cx.ch * a.nsimu + r] = res ? res[lane].fl : 0;
+        if (a.sschain) a.sschain[(size_t)cx.ch * a.nsimu + r] = ssr;
+    }
+    s2 = warp_sum(s2); sq = warp_sum(sq);
+    if (lane == 0) { st->sum += s2; st->sq_sum += sq; st->cnt += cnt; }
 }
 
 // Randomness and proposal increments for steps [g0, g0+nnew): Philox normals z1, z2 (interleaved in
@@ -385,7 +394,7 @@ __device__ __noinline__ void generate(const RunArgs &a, const ChainCtx &cx, int 
 // One DRAM step (both proposal stages) by ONE warp for step `st`, from state x with (ss, pri), seeing
 // sigma2 = s2p.  Result in *res.   mcmcstat DRAM: SURVEY.md 3.2.
 __device__ __noinline__ void dram_step_warp(const RunArgs &a, const ChainCtx &cx, int st, double ss, double pri, double s2p,
-                                            Work &w, double *y1, double *y2, StepRes *res)
+                                            Work w, int y1, int y2, StepRes *res)
 {
     const int lane = threadIdx.x & 31, npar = cx.npar;
     const double2 *dd = reinterpret_cast<const double2 *>(cx.slot_d(st));
@@ -396,8 +405,8 @@ __device__ __noinline__ void dram_step_warp(const RunArgs &a, const ChainCtx &cx
     for (int j = lane; j < npar; j += 32) {
         const double2 dj = dd[j];
         const double xj = cx.x[j], a1 = xj + dj.x, a2 = xj + dj.y;
-        y1[j] = a1;
-        y2[j] = a2;
+        tc_smem[y1 + j] = a1;
+        tc_smem[y2 + j] = a2;
         const double lo = cx.lo[j], hi = cx.hi[j];
         if (a1 < lo || a1 > hi) oob |= 1u;
         if (a2 < lo || a2 > hi) oob |= 2u;
@@ -413,7 +422,7 @@ __device__ __noinline__ void dram_step_warp(const RunArgs &a, const ChainCtx &cx
     if (oob & 1u) {
         ss1 = INFINITY; pr1 = 0.0; a12 = 0.0; fl |= TC_FL_OOB1; ++noob;
     } else {
-        ss1 = ss_eval(a.cons, cx.cv, y1, w, a.algo, false, nullptr, nullptr);
+        ss1 = ss_eval(a.cons, cx.cv, SmemVec{y1}, w, a.algo, false, nullptr, nullptr);
         ++nev;
         a12 = tc_exp(-0.5 * ((ss1 - ss) / s2p + pr1 - pri));
         if (a12 <= 0.0) accept = 0;
@@ -426,7 +435,7 @@ __device__ __noinline__ void dram_step_warp(const RunArgs &a, const ChainCtx &cx
         if (oob & 2u) {
             fl |= TC_FL_OOB2; ++noob;
         } else {
-            const double ss2 = ss_eval(a.cons, cx.cv, y2, w, a.algo, false, nullptr, nullptr);
+            const double ss2 = ss_eval(a.cons, cx.cv, SmemVec{y2}, w, a.algo, false, nullptr, nullptr);
             ++nev;
             double a32 = tc_exp(-0.5 * ((ss1 - ss2) / s2p + pr1 - pr2));
             a32 = a32 > 1.0 ? 1.0 : a32;
@@ -456,7 +465,7 @@ __device__ __noinline__ int adapt(const RunArgs &a, const ChainCtx &cx, int isim
         for (int i = tid; i < npar; i += DRAM_THREADS) {
             const double mbi = cx.mb[i] / m;
             cx.mb[i] = mbi;
-            cx.dm[i] = mbi - cx.cmean[i];
+            cx.dm[i] = mbi - __ldcg(cx.cmean + i);
         }
         const double fcorr = cov_n * m / (cov_n + m);
         const int ntile = (npar + 3) >> 2, T = ntile * (ntile + 1) / 2;
@@ -483,7 +492,7 @@ __device__ __noinline__ int adapt(const RunArgs &a, const ChainCtx &cx, int isim
                 for (int r = 0; r < rc; ++r)
 #pragma unroll 1
                     for (int c = tid; c < npad; c += DRAM_THREADS)
-                        chunk[r * npad + c] = c < npar ? cx.gRows[(size_t)(r0 + r) * ld + c] - cx.mb[c] : 0.0;
+                        chunk[r * npad + c] = c < npar ? __ldcg(cx.gRows + (size_t)(r0 + r) * ld + c) - cx.mb[c] : 0.0;
                 __syncthreads();
 #pragma unroll
                 for (int u = 0; u < COV_TPT; ++u) {
@@ -510,7 +519,7 @@ __device__ __noinline__ int adapt(const RunArgs &a, const ChainCtx &cx, int isim
 #pragma unroll
                     for (int jj = 0; jj < 4; ++jj) {
                         const int pp = 4 * bi[u] + ii, qq = 4 * bj[u] + jj;
-                        old[4 * ii + jj] = (pp <= qq && qq < npar) ? cx.gM2[pidx(npar, pp, qq)] : 0.0;
+                        old[4 * ii + jj] = (pp <= qq && qq < npar) ? __ldcg(cx.gM2 + pidx(npar, pp, qq)) : 0.0;
                     }
 #pragma unroll
                 for (int ii = 0; ii < 4; ++ii)
@@ -524,7 +533,7 @@ __device__ __noinline__ int adapt(const RunArgs &a, const ChainCtx &cx, int isim
         }
         __syncthreads();
 #pragma unroll 1
-        for (int i = tid; i < npar; i += DRAM_THREADS) { cx.cmean[i] += cx.dm[i] * (m / (cov_n + m)); cx.mb[i] = 0.0; }
+        for (int i = tid; i < npar; i += DRAM_THREADS) { cx.cmean[i] = __ldcg(cx.cmean + i) + cx.dm[i] * (m / (cov_n + m)); cx.mb[i] = 0.0; }
         cov_n += m;
         __syncthreads();
     }
@@ -539,14 +548,14 @@ __device__ __noinline__ int adapt(const RunArgs &a, const ChainCtx &cx, int isim
                 for (int i = tid; i < npar; i += DRAM_THREADS) cx.rdiag[i] *= f;
             } else {
 #pragma unroll 1
-                for (int i = tid; i < npk; i += DRAM_THREADS) cx.gRb[i] *= f;
+                for (int i = tid; i < npk; i += DRAM_THREADS) cx.gRb[i] = __ldcg(cx.gRb + i) * f;
             }
         }
     } else {
         // R = chol(cov + qcovadj I) * adascale, factorised in shared memory, kept in HBM/L2
         const double invn = 1.0 / (cov_n - 1.0);
 #pragma unroll 1
-        for (int i = tid; i < npk; i += DRAM_THREADS) Rs[i] = cx.gM2[i] * invn;
+        for (int i = tid; i < npk; i += DRAM_THREADS) Rs[i] = __ldcg(cx.gM2 + i) * invn;
         __syncthreads();
 #pragma unroll 1
         for (int i = tid; i < npar; i += DRAM_THREADS) Rs[pidx(npar, i, i)] += a.qcovadj;
@@ -575,199 +584,268 @@ __device__ __noinline__ int adapt(const RunArgs &a, const ChainCtx &cx, int isim
 // exactly the sequential one (same Philox draws per step; the replay tests compare it flag by flag
 // with the CPU oracle).  The randomness and the proposal increments z R do not depend on the state,
 // so they are generated once per step, ahead of use, into a ring of SPEC slots.
+// Saved state of a chain between two time slices (doubles): see dram_kernel.
+//   [0..15] scalars | [16..31] counters (as doubles' bit patterns via long long) | x | wmean | wM2 | rdiag
+__host__ __device__ inline int state_doubles(int ld) { return 32 + 4 * ld; }
+
 __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_constant__ RunArgs a)
 {
-    extern __shared__ __align__(16) double smem[];
     __shared__ StepRes s_res[SPEC];
     __shared__ ChainCtx cx;
     __shared__ S2Stats s_s2;
     __shared__ double s_sc[4];
+    __shared__ int s_item, s_done;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int ch = blockIdx.x;
-    if (ch >= a.nchains) return;
-    const int cid = a.chain_cell[ch];
-    const int N = a.cells.N[cid];
-    const int npar = 7 + N;
 
-    // ---- carve shared memory, publish the context
-    {
-        double *p = smem;
-        CellView cv;
-        carve_cell(p, N, cv);
-        p += (reinterpret_cast<uintptr_t>(p) >> 3) & 1;
-        if (tid == 0) {
-            cx.N = N; cx.npar = npar; cx.npad = (npar + 3) & ~3; cx.npk = npar * (npar + 1) / 2; cx.ld = a.ld;
-            cx.slot_sz = dram_slot(N); cx.wsz = a.wsz; cx.ch = ch; cx.first_row = a.n_burn - 1;
-            cx.nstore = a.nsimu - (a.n_burn - 1);
-            cx.uid = a.chain_uid ? a.chain_uid[ch] : (unsigned long long)ch;
-            cx.adascale = a.adascale > 0.0 ? a.adascale : 2.4 / sqrt((double)npar);
-            cx.inv_dr = 1.0 / a.drscale;
-            cx.cv = cv; cx.cv.d = a.cells.dmean[cid];
-            cx.ring = p; p += SPEC * dram_slot(N);
-            cx.x = p; p += npar;     cx.lo = p; p += npar;    cx.hi = p; p += npar;   cx.mu = p; p += npar;
-            cx.pinv = p; p += npar;  cx.wmean = p; p += npar; cx.wM2 = p; p += npar;  cx.rdiag = p; p += npar;
-            cx.mb = p; p += npar;    cx.dm = p; p += npar;
-            p += (reinterpret_cast<uintptr_t>(p) >> 3) & 1;
-            cx.U = p;
-            cx.gRb = a.gR + (size_t)ch * a.ldR;                 // the factor R lives in HBM/L2 (packed upper)
-            cx.gM2 = a.gM2 ? a.gM2 + (size_t)ch * a.ldR : nullptr;
-            cx.gRows = a.gRows ? a.gRows + (size_t)ch * (size_t)a.adaptint * a.ld : nullptr;
-            cx.cmean = a.gCmean ? a.gCmean + (size_t)ch * a.ld : nullptr;
-            s_s2.sum = 0.0; s_s2.sq_mean = 0.0; s_s2.sq_M2 = 0.0; s_s2.cnt = 0.0;
+    // Persistent CTAs pull (time slice, chain) items from a global queue, slice-major, so that any
+    // number of chains shares the resident CTAs evenly (299 chains on 296 CTA slots would otherwise
+    // cost two full waves).  A slice ends on an adaptation boundary, where the ring is empty and the
+    // factor R / covariance already live in HBM; the rest of the chain state is a few vectors.
+#pragma unroll 1
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_item = atomicAdd(a.queue, 1);
+        __syncthreads();
+        const int item = s_item;
+        if (item >= a.nitems) break;
+        const int ch = item % a.nchains, seg = item / a.nchains;
+        const int k_end = min(a.nsimu, (seg + 1) * a.seglen);
+        const bool last_seg = k_end >= a.nsimu;
+        if (seg > 0) {
+            // the previous slice of this chain may still be running on another CTA (it was dequeued
+            // before this one, so it is resident and making progress)
+            if (tid == 0) {
+                int d;
+                while ((d = atomicAdd(a.done + ch, 0)) < seg) __nanosleep(500);
+                s_done = d;
+            }
+            __syncthreads();
+            __threadfence();
+            if (s_done >= (1 << 30)) continue;          // the chain ended early (ss(x0) not finite)
         }
-        load_cell(a.cells, cid, false, cv);
-    }
-    __syncthreads();
-    // this warp's private area: forward-model scratch + its two proposals
-    Work w;
-    {
-        double *wp = cx.U + (size_t)warp * cx.wsz;
-        carve_work(wp, N, w);
-    }
-    double *y1 = cx.warp_y(warp, 0), *y2 = cx.warp_y(warp, 1);
-#pragma unroll 1
-    for (int i = tid; i < npar; i += DRAM_THREADS) {
-        const size_t g = (size_t)ch * a.ld + i;
-        cx.x[i] = a.theta0[g];
-        cx.lo[i] = a.low[g];
-        cx.hi[i] = a.upp[g];
-        cx.mu[i] = a.pmu[g];
-        const double sg = a.psig[g];
-        cx.pinv[i] = isinf(sg) ? 0.0 : 1.0 / sg;
-        cx.rdiag[i] = sqrt(a.qcov_diag[g]);                // chol(diag(J0))
-        cx.wmean[i] = 0.0;
-        cx.wM2[i] = 0.0;
-        cx.mb[i] = 0.0;
-        if (a.do_cov) cx.cmean[i] = 0.0;
-    }
-    if (a.do_cov) {
-#pragma unroll 1
-        for (int i = tid; i < cx.npk; i += DRAM_THREADS) cx.gM2[i] = 0.0;
-    }
-    __syncthreads();
+        const int cid = a.chain_cell[ch];
+        const int N = a.cells.N[cid];
+        const int npar = 7 + N;
+        double *gst = a.gState + (size_t)ch * state_doubles(a.ld);
 
-    // ---- chain state (uniform across the CTA)
-    bool r_diag = true;
-    double cov_n = 0.0;                                    // rows folded into (cmean, M2) so far
-    double ss, pri, sigma2 = a.sigma2_0;
-    long long n_ss = 1, n_acc1 = 0, n_acc2 = 0, n_oob = 0, n_adapt = 0, n_cholfail = 0, n_dr = 0, n_spec = 0;
-    long long rej = 0, reju = 0;
-    double wcnt = 0.0;                                     // rows folded into the summaries
-    long long pc[5] = {0, 0, 0, 0, 0};                     // phase cycles (thread 0)
-    long long tprev = clock64();
+        // ---- carve shared memory (offsets in doubles into tc_smem), publish the context
+        {
+            SmemCell cv;
+            int o = carve_cell(0, N, cv);
+            o += o & 1;
+            if (tid == 0) {
+                cx.N = N; cx.npar = npar; cx.npad = (npar + 3) & ~3; cx.npk = npar * (npar + 1) / 2; cx.ld = a.ld;
+                cx.slot_sz = dram_slot(N); cx.wsz = a.wsz; cx.ch = ch; cx.first_row = a.n_burn - 1;
+                cx.nstore = a.nsimu - (a.n_burn - 1);
+                cx.uid = a.chain_uid ? a.chain_uid[ch] : (unsigned long long)ch;
+                cx.adascale = a.adascale > 0.0 ? a.adascale : 2.4 / sqrt((double)npar);
+                cx.inv_dr = 1.0 / a.drscale;
+                cx.cv = cv; cx.cv.d = a.cells.dmean[cid];
+                cx.ring = tc_smem + o; o += SPEC * dram_slot(N);
+                cx.o_x = o;
+                cx.x = tc_smem + o; o += npar;     cx.lo = tc_smem + o; o += npar;    cx.hi = tc_smem + o; o += npar;
+                cx.mu = tc_smem + o; o += npar;    cx.pinv = tc_smem + o; o += npar;  cx.wmean = tc_smem + o; o += npar;
+                cx.wM2 = tc_smem + o; o += npar;   cx.rdiag = tc_smem + o; o += npar; cx.mb = tc_smem + o; o += npar;
+                cx.dm = tc_smem + o; o += npar;
+                o += o & 1;
+                cx.o_U = o;
+                cx.U = tc_smem + o;
+                cx.gRb = a.gR + (size_t)ch * a.ldR;                 // the factor R lives in HBM/L2 (packed upper)
+                cx.gM2 = a.gM2 ? a.gM2 + (size_t)ch * a.ldR : nullptr;
+                cx.gRows = a.gRows ? a.gRows + (size_t)ch * (size_t)a.adaptint * a.ld : nullptr;
+                cx.cmean = a.gCmean ? a.gCmean + (size_t)ch * a.ld : nullptr;
+            }
+            load_cell(a.cells, cid, false, cv);
+        }
+        __syncthreads();
+        // this warp's private area: forward-model scratch + its two proposals
+        Work w;
+        carve_work(cx.o_U + warp * cx.wsz, N, w);
+        const int y1 = cx.warp_y(warp, 0), y2 = cx.warp_y(warp, 1);
+#pragma unroll 1
+        for (int i = tid; i < npar; i += DRAM_THREADS) {
+            const size_t g = (size_t)ch * a.ld + i;
+            cx.lo[i] = a.low[g];
+            cx.hi[i] = a.upp[g];
+            cx.mu[i] = a.pmu[g];
+            const double sg = a.psig[g];
+            cx.pinv[i] = isinf(sg) ? 0.0 : 1.0 / sg;
+            cx.mb[i] = 0.0;
+            if (seg == 0) {
+                cx.x[i] = a.theta0[g];
+                cx.rdiag[i] = sqrt(a.qcov_diag[g]);            // chol(diag(J0))
+                cx.wmean[i] = 0.0;
+                cx.wM2[i] = 0.0;
+                if (a.do_cov) cx.cmean[i] = 0.0;
+            } else {
+                cx.x[i] = __ldcg(gst + 32 + i);
+                cx.wmean[i] = __ldcg(gst + 32 + a.ld + i);
+                cx.wM2[i] = __ldcg(gst + 32 + 2 * a.ld + i);
+                cx.rdiag[i] = __ldcg(gst + 32 + 3 * a.ld + i);
+            }
+        }
+        if (seg == 0 && a.do_cov) {
+#pragma unroll 1
+            for (int i = tid; i < cx.npk; i += DRAM_THREADS) cx.gM2[i] = 0.0;
+        }
+
+        // ---- chain state (uniform across the CTA)
+        bool r_diag = true, bad0 = false;
+        double cov_n = 0.0;                                    // rows folded into (cmean, M2) so far
+        double ss = 0.0, pri = 0.0, sigma2 = a.sigma2_0;
+        long long n_ss = 1, n_acc1 = 0, n_acc2 = 0, n_oob = 0, n_adapt = 0, n_cholfail = 0, n_dr = 0, n_spec = 0;
+        long long rej = 0, reju = 0;
+        double wcnt = 0.0;                                     // rows folded into the summaries
+        long long pc[4] = {0, 0, 0, 0};                        // phase cycles (thread 0)
+        int k;                                                 // next step to decide
+        if (seg > 0) {
+            ss = __ldcg(gst + 0); pri = __ldcg(gst + 1); sigma2 = __ldcg(gst + 2); cov_n = __ldcg(gst + 3);
+            wcnt = __ldcg(gst + 4); r_diag = __ldcg(gst + 5) != 0.0;
+            if (tid == 0) { s_s2.sum = __ldcg(gst + 6); s_s2.sq_sum = __ldcg(gst + 7); s_s2.cnt = __ldcg(gst + 9); }
+            const long long *gc = reinterpret_cast<const long long *>(gst + 16);
+            n_ss = __ldcg(gc + 0); n_acc1 = __ldcg(gc + 1); n_acc2 = __ldcg(gc + 2); n_oob = __ldcg(gc + 3);
+            n_adapt = __ldcg(gc + 4); n_cholfail = __ldcg(gc + 5); n_dr = __ldcg(gc + 6); n_spec = __ldcg(gc + 7);
+            rej = __ldcg(gc + 8);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) pc[i] = __ldcg(gc + 9 + i);
+            k = seg * a.seglen;
+        }
+        __syncthreads();
+        long long tprev = clock64();
 #define TC_PHASE(i) do { const long long tn__ = clock64(); pc[i] += tn__ - tprev; tprev = tn__; } while (0)
 
-    // ---- row 0: x0
-    {
-        ss = ss_eval(a.cons, cx.cv, cx.x, w, a.algo, false, nullptr, nullptr);   // every warp, same value
-        double s = 0.0;
+        if (seg == 0) {
+            // ---- row 0: x0
+            ss = ss_eval(a.cons, cx.cv, SmemVec{cx.o_x}, w, a.algo, false, nullptr, nullptr);   // every warp, same value
+            double s = 0.0;
 #pragma unroll 1
-        for (int i = lane; i < npar; i += 32) { const double e = (cx.x[i] - cx.mu[i]) * cx.pinv[i]; s += e * e; }
-        pri = warp_sum(s);
-    }
-    const bool bad0 = !isfinite(ss);
-    __syncthreads();
-    if (!bad0) {
-        wcnt = emit_rows(a, cx, 0, 1, cx.x, wcnt);
-        if (tid == 0) emit_s2(a, cx, &s_s2, 0, sigma2, ss, 0);
-    }
-    __syncthreads();
-
-    int k = 1;                 // next step to decide
-    int gen_upto = 1;          // increments are ready for steps [k, gen_upto)
-#pragma unroll 1
-    while (k < a.nsimu && !bad0) {
-        // the batch never crosses an adaptation: the step whose isimu = st+1 is a multiple of adaptint
-        // is the last one that may use the current R
-        int lim = min(k + SPEC, a.nsimu);
-        if (a.adaptint > 0) lim = min(lim, ((k + a.adaptint) / a.adaptint) * a.adaptint);   // exclusive step bound
-        const int nb = lim - k;
-
-        if (gen_upto < lim) { generate(a, cx, gen_upto, lim - gen_upto, r_diag); gen_upto = lim; }
-        if (tid == 0) TC_PHASE(0);
-
-        // speculation: warp w runs step k+w assuming steps k..k+w-1 rejected; the sigma2 it sees is the
-        // draw made at the end of step k+w-1 from the (unchanged) ss
-        if (warp < nb) {
-            double s2p = sigma2;
-            if (warp > 0 && a.updatesigma) s2p = (a.N0 * a.S20 + ss) / cx.slot_sc(k + warp - 1)[2];
-            dram_step_warp(a, cx, k + warp, ss, pri, s2p, w, y1, y2, &s_res[warp]);
-        }
-        __syncthreads();
-        if (tid == 0) TC_PHASE(1);
-
-        // resolve: commit up to and including the first accepting step
-        int first = nb;
-#pragma unroll 1
-        for (int q = nb - 1; q >= 0; --q) if (s_res[q].acc) first = q;
-        const int ncommit = first < nb ? first + 1 : nb;
-#pragma unroll 1
-        for (int q = 0; q < nb; ++q) {
-            if (q < ncommit) { n_ss += s_res[q].nev; n_oob += s_res[q].noob; if (s_res[q].fl & TC_FL_DR) ++n_dr; }
-            n_spec += s_res[q].nev;
-        }
-        const int nrej = first < nb ? first : nb;                     // leading rejected steps: rows equal x
-        rej += nrej; reju += nrej;
-        if (nrej > 0) {
-            wcnt = emit_rows(a, cx, k, nrej, cx.x, wcnt);
-            if (tid == 0) {
-#pragma unroll 1
-                for (int q = 0; q < nrej; ++q) {
-                    const double s2 = a.updatesigma ? (a.N0 * a.S20 + ss) / cx.slot_sc(k + q)[2] : sigma2;
-                    emit_s2(a, cx, &s_s2, k + q, s2, ss, s_res[q].fl);
-                }
+            for (int i = lane; i < npar; i += 32) { const double e = (cx.x[i] - cx.mu[i]) * cx.pinv[i]; s += e * e; }
+            pri = warp_sum(s);
+            bad0 = !isfinite(ss);
+            if (tid == 0) { s_s2.sum = 0.0; s_s2.sq_sum = 0.0; s_s2.cnt = 0.0; }
+            __syncthreads();
+            if (!bad0) {
+                wcnt = emit_rows(a, cx, 0, 1, cx.x, wcnt);
+                if (warp == 0) emit_s2(a, cx, &s_s2, nullptr, 0, 1, 1, ss, ss, sigma2);
             }
-            if (a.updatesigma) sigma2 = (a.N0 * a.S20 + ss) / cx.slot_sc(k + nrej - 1)[2];
-        }
-        if (first < nb) {
-            // the accepting warp's proposal becomes the state
-            const double *ya = cx.warp_y(first, s_res[first].acc == 2 ? 1 : 0);
             __syncthreads();
+            k = 1;
+        }
+
+        int gen_upto = k;          // increments are ready for steps [k, gen_upto)
 #pragma unroll 1
-            for (int i = tid; i < npar; i += DRAM_THREADS) cx.x[i] = ya[i];
-            ss = s_res[first].ssn; pri = s_res[first].prin;
-            if (s_res[first].acc == 1) ++n_acc1; else ++n_acc2;
-            if (a.updatesigma) sigma2 = (a.N0 * a.S20 + ss) / cx.slot_sc(k + first)[2];
+        while (k < k_end && !bad0) {
+            // the batch never crosses an adaptation: the step whose isimu = st+1 is a multiple of adaptint
+            // is the last one that may use the current R
+            int lim = min(k + SPEC, k_end);
+            if (a.adaptint > 0) lim = min(lim, ((k + a.adaptint) / a.adaptint) * a.adaptint);   // exclusive step bound
+            const int nb = lim - k;
+
+            if (gen_upto < lim) { generate(a, cx, gen_upto, lim - gen_upto, r_diag); gen_upto = lim; }
+            if (tid == 0) TC_PHASE(0);
+
+            // speculation: warp w runs step k+w assuming steps k..k+w-1 rejected; the sigma2 it sees is the
+            // draw made at the end of step k+w-1 from the (unchanged) ss
+            if (warp < nb) {
+                double s2p = sigma2;
+                if (warp > 0 && a.updatesigma) s2p = (a.N0 * a.S20 + ss) / cx.slot_sc(k + warp - 1)[2];
+                dram_step_warp(a, cx, k + warp, ss, pri, s2p, w, y1, y2, &s_res[warp]);
+            }
             __syncthreads();
-            wcnt = emit_rows(a, cx, k + first, 1, cx.x, wcnt);
-            if (tid == 0) emit_s2(a, cx, &s_s2, k + first, sigma2, ss, s_res[first].fl);
+            if (tid == 0) TC_PHASE(1);
+
+            // resolve: commit up to and including the first accepting step
+            int first = nb;
+#pragma unroll 1
+            for (int q = nb - 1; q >= 0; --q) if (s_res[q].acc) first = q;
+            const int ncommit = first < nb ? first + 1 : nb;
+#pragma unroll 1
+            for (int q = 0; q < nb; ++q) {
+                if (q < ncommit) { n_ss += s_res[q].nev; n_oob += s_res[q].noob; if (s_res[q].fl & TC_FL_DR) ++n_dr; }
+                n_spec += s_res[q].nev;
+            }
+            const int nrej = first < nb ? first : nb;                     // leading rejected steps: rows equal x
+            rej += nrej; reju += nrej;
+            const double ss_old = ss;
+            if (nrej > 0) wcnt = emit_rows(a, cx, k, nrej, cx.x, wcnt);
+            if (first < nb) {
+                // the accepting warp's proposal becomes the state
+                const double *ya = tc_smem + cx.warp_y(first, s_res[first].acc == 2 ? 1 : 0);
+                __syncthreads();
+#pragma unroll 1
+                for (int i = tid; i < npar; i += DRAM_THREADS) cx.x[i] = ya[i];
+                ss = s_res[first].ssn; pri = s_res[first].prin;
+                if (s_res[first].acc == 1) ++n_acc1; else ++n_acc2;
+                __syncthreads();
+                wcnt = emit_rows(a, cx, k + first, 1, cx.x, wcnt);
+            }
+            if (warp == 0) emit_s2(a, cx, &s_s2, s_res, k, ncommit, first, ss_old, ss, sigma2);
+            if (a.updatesigma) sigma2 = (a.N0 * a.S20 + ss) / cx.slot_sc(k + ncommit - 1)[2];
+            k += ncommit;
+            __syncthreads();
+            if (tid == 0) TC_PHASE(2);
+
+            // adaptation after the step with isimu = k, a multiple of adaptint
+            if (a.adaptint > 0 && k % a.adaptint == 0) {
+                const double rate = a.burnin_cumulative ? (double)rej / k : (double)reju / a.adaptint;
+                const int rc = adapt(a, cx, k, cov_n, rate, r_diag, &s_sc[0]);
+                if (a.do_cov) cov_n += a.adaptint;
+                if (rc == 1) { r_diag = false; ++n_adapt; }
+                else if (rc == 2) ++n_cholfail;
+                reju = 0;
+                if (tid == 0) TC_PHASE(3);
+            }
         }
-        k += ncommit;
+
         __syncthreads();
-        if (tid == 0) TC_PHASE(2);
-
-        // adaptation after the step with isimu = k, a multiple of adaptint
-        if (a.adaptint > 0 && k % a.adaptint == 0) {
-            const double rate = a.burnin_cumulative ? (double)rej / k : (double)reju / a.adaptint;
-            const int rc = adapt(a, cx, k, cov_n, rate, r_diag, &s_sc[0]);
-            if (a.do_cov) cov_n += a.adaptint;
-            if (rc == 1) { r_diag = false; ++n_adapt; }
-            else if (rc == 2) ++n_cholfail;
-            reju = 0;
-            if (tid == 0) TC_PHASE(3);
-        }
-    }
-
-    // ---- summaries (TranscriptionCycleMCMC.m:286-303)
-    __syncthreads();
+        if (!last_seg && !bad0) {
+            // ---- park the chain: the next slice may run on any CTA
 #pragma unroll 1
-    for (int i = tid; i < npar; i += DRAM_THREADS) {
-        if (a.mean) a.mean[(size_t)ch * a.ld + i] = bad0 ? 0.0 : cx.wmean[i];
-        if (a.std) a.std[(size_t)ch * a.ld + i] = (!bad0 && wcnt > 0) ? sqrt(cx.wM2[i] / wcnt) : 0.0;
-    }
-    if (tid == 0) {
-        if (a.sig) {
-            a.sig[2 * (size_t)ch] = bad0 ? 0.0 : sqrt(s_s2.sum / s_s2.cnt);
-            a.sig[2 * (size_t)ch + 1] = bad0 ? 0.0 : sqrt(s_s2.sq_M2 / s_s2.cnt);
+            for (int i = tid; i < npar; i += DRAM_THREADS) {
+                gst[32 + i] = cx.x[i];
+                gst[32 + a.ld + i] = cx.wmean[i];
+                gst[32 + 2 * a.ld + i] = cx.wM2[i];
+                gst[32 + 3 * a.ld + i] = cx.rdiag[i];
+            }
+            if (tid == 0) {
+                gst[0] = ss; gst[1] = pri; gst[2] = sigma2; gst[3] = cov_n; gst[4] = wcnt; gst[5] = r_diag ? 1.0 : 0.0;
+                gst[6] = s_s2.sum; gst[7] = s_s2.sq_sum; gst[8] = 0.0; gst[9] = s_s2.cnt;
+                long long *gc = reinterpret_cast<long long *>(gst + 16);
+                gc[0] = n_ss; gc[1] = n_acc1; gc[2] = n_acc2; gc[3] = n_oob; gc[4] = n_adapt; gc[5] = n_cholfail; gc[6] = n_dr;
+                gc[7] = n_spec; gc[8] = rej;
+                for (int i = 0; i < 4; ++i) gc[9 + i] = pc[i];
+            }
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) atomicExch(a.done + ch, seg + 1);
+            continue;
         }
-        if (a.counters) {
-            long long *c = a.counters + (size_t)ch * TC_NCOUNTERS;
-            c[TC_CNT_SS_EVALS] = n_ss; c[TC_CNT_ACC_STAGE1] = n_acc1; c[TC_CNT_ACC_STAGE2] = n_acc2;
-            c[TC_CNT_OUT_OF_BOUNDS] = n_oob; c[TC_CNT_ADAPTATIONS] = n_adapt;
-            c[TC_CNT_CHOL_FAIL] = n_cholfail; c[TC_CNT_DR_TRIES] = n_dr; c[TC_CNT_STATUS] = bad0 ? 1 : 0;
-            for (int i = 0; i < 4; ++i) c[TC_CNT_CYCLES0 + i] = pc[i];
-            c[TC_CNT_CYCLES0 + 4] = 0; c[TC_CNT_CYCLES0 + 5] = 0; c[TC_CNT_CYCLES0 + 6] = 0;
-            c[TC_CNT_CYCLES0 + 7] = n_spec;
+
+        // ---- summaries (TranscriptionCycleMCMC.m:286-303); a chain whose ss(x0) is not finite ends here
+#pragma unroll 1
+        for (int i = tid; i < npar; i += DRAM_THREADS) {
+            if (a.mean) a.mean[(size_t)ch * a.ld + i] = bad0 ? 0.0 : cx.wmean[i];
+            if (a.std) a.std[(size_t)ch * a.ld + i] = (!bad0 && wcnt > 0) ? sqrt(cx.wM2[i] / wcnt) : 0.0;
+        }
+        if (tid == 0) {
+            if (a.sig) {
+                // sqrt(mean(s2chain)); std(sqrt(s2chain),1) = sqrt(E[s2] - E[sqrt(s2)]^2)   (:302-303)
+                const double m2 = s_s2.sum / s_s2.cnt, m1 = s_s2.sq_sum / s_s2.cnt;
+                a.sig[2 * (size_t)ch] = bad0 ? 0.0 : sqrt(m2);
+                a.sig[2 * (size_t)ch + 1] = bad0 ? 0.0 : sqrt(fmax(m2 - m1 * m1, 0.0));
+            }
+            if (a.counters) {
+                long long *c = a.counters + (size_t)ch * TC_NCOUNTERS;
+                c[TC_CNT_SS_EVALS] = n_ss; c[TC_CNT_ACC_STAGE1] = n_acc1; c[TC_CNT_ACC_STAGE2] = n_acc2;
+                c[TC_CNT_OUT_OF_BOUNDS] = n_oob; c[TC_CNT_ADAPTATIONS] = n_adapt;
+                c[TC_CNT_CHOL_FAIL] = n_cholfail; c[TC_CNT_DR_TRIES] = n_dr; c[TC_CNT_STATUS] = bad0 ? 1 : 0;
+                for (int i = 0; i < 4; ++i) c[TC_CNT_CYCLES0 + i] = pc[i];
+                c[TC_CNT_CYCLES0 + 4] = 0; c[TC_CNT_CYCLES0 + 5] = 0; c[TC_CNT_CYCLES0 + 6] = 0;
+                c[TC_CNT_CYCLES0 + 7] = n_spec;
+            }
+            // a failed chain must not block the (never issued) later slices: mark everything done
+            __threadfence();
+            atomicExch(a.done + ch, 1 << 30);
         }
     }
 }
@@ -1262,8 +1340,27 @@ int tc_mcmc_run(const tc_cells *c, const tc_mcmc_opts *o, int nchains, const int
             return fail(TC_EINVAL, "max(N) = " + std::to_string(Nmax) + " is too large for the shared-memory layout of this build "
                                    "(the Cholesky workspace of the proposal factor must fit in one SM)");
         CUDA_TRY(cudaFuncSetAttribute(dram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // time slices: a multiple of adaptint, ~32 per chain; persistent grid = resident CTA slots
+        {
+            const int unit = o->adaptint > 0 ? o->adaptint : 1;
+            long long sl = ((long long)o->nsimu + 31) / 32;
+            sl = ((sl + unit - 1) / unit) * unit;
+            a.seglen = (int)std::max<long long>(sl, unit);
+            const int nseg = (o->nsimu + a.seglen - 1) / a.seglen;
+            a.nitems = nseg * nc;
+            CUDA_TRY(r.buf.alloc(a.gState, (size_t)nc * state_doubles(ld)));
+            CUDA_TRY(r.buf.alloc(a.queue, 1));
+            CUDA_TRY(r.buf.alloc(a.done, nc));
+            CUDA_TRY(cudaMemsetAsync(a.queue, 0, sizeof(int), r.st));
+            CUDA_TRY(cudaMemsetAsync(a.done, 0, sizeof(int) * nc, r.st));
+        }
+        int per_sm = 0, sms = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dram_kernel, DRAM_THREADS, smem));
+        CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, r.device));
+        if (per_sm < 1) return fail(TC_EINVAL, "sampler kernel does not fit on this device");
+        const int grid = std::min(nc, per_sm * sms);           // every CTA resident: slices may wait on each other
         CUDA_TRY(cudaEventRecord(r.e0, r.st));
-        dram_kernel<<<nc, DRAM_THREADS, smem, r.st>>>(a);
+        dram_kernel<<<grid, DRAM_THREADS, smem, r.st>>>(a);
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaEventRecord(r.e1, r.st));
     }
