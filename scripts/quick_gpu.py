@@ -41,5 +41,5 @@ for nsimu, burn, nrep in ((2000, 1000, 1), (2000, 1000, 8)):
           % (cc.size, nsimu, dt, out["kernel_seconds"], cc.size * nsimu / out["kernel_seconds"], cnt[0] / out["kernel_seconds"],
              cnt[0] / (cc.size * nsimu), cnt[1] / (cc.size * nsimu), cnt[2] / (cc.size * nsimu), cnt[3] / (cc.size * nsimu), cnt[4], cnt[5]))
     pc = out["counters"][:, 8:16].sum(axis=0) / (cc.size * nsimu)
-    print("  cycles/step by phase: generate %.0f speculate %.0f resolve %.0f adapt %.0f total %.0f; speculative evals/step %.2f" % (*pc[:4], pc[:4].sum(), pc[7]))
+    print("  cycles/step by phase: generate %.0f speculate %.0f resolve[emit-rej %.0f accept %.0f s2+state %.0f] adapt %.0f total %.0f; speculative evals/step %.2f" % (*pc[:6], pc[:6].sum(), pc[7]))
     print("  mean v %.3f tau %.3f ton %.3f sigma %.3f" % (out["mean"][:, 0].mean(), out["mean"][:, 1].mean(), out["mean"][:, 2].mean(), out["sig"][:, 0].mean()))

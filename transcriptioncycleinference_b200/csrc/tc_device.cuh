@@ -80,6 +80,21 @@ __device__ __noinline__ void normal_pair(const u32x4 &r, double &z0, double &z1)
     z1 = rad * s;
 }
 
+// (z1[2q], z1[2q+1], z2[2q], z2[2q+1]) of one step: the same draws as two normal_pair calls on the RK_Z1 and
+// RK_Z2 counters, with the two dependent chains interleaved in one function body
+__device__ __noinline__ double4 normal_quad(uint64_t seed, uint64_t uid, uint32_t step, uint32_t q)
+{
+    const uint32_t c2 = (uint32_t)uid, c3 = (uint32_t)(uid >> 32) << 8, k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    const u32x4 r1 = philox4x32_10(q, step, c2, c3 | RK_Z1, k0, k1);
+    const u32x4 r2 = philox4x32_10(q, step, c2, c3 | RK_Z2, k0, k1);
+    const double ua1 = u01(r1.x, r1.y), ub1 = u01(r1.z, r1.w), ua2 = u01(r2.x, r2.y), ub2 = u01(r2.z, r2.w);
+    const double rad1 = sqrt(-2.0 * log(ua1)), rad2 = sqrt(-2.0 * log(ua2));
+    double s1, c1, s2, cc2;
+    sincospi(2.0 * ub1, &s1, &c1);
+    sincospi(2.0 * ub2, &s2, &cc2);
+    return make_double4(rad1 * c1, rad1 * s1, rad2 * cc2, rad2 * s2);
+}
+
 // chi-square(dof) = 2*Gamma(dof/2) by Marsaglia-Tsang (dof >= 2); attempt t uses slots 2t, 2t+1.
 __device__ __noinline__ double chi2_draw(uint64_t seed, uint64_t uid, uint32_t step, double dof)
 {

@@ -190,6 +190,14 @@ struct StepRes { double ssn, prin; int acc, fl, nev, noob; };
 // s2chain statistics over ALL rows (TranscriptionCycleMCMC.m:302-303), thread 0, shared memory
 struct S2Stats { double sum, sq_sum, cnt, pad; };      // sum s2, sum sqrt(s2), rows
 
+// Mutable chain state (uniform across the CTA): shared memory, thread 0 writes between barriers.
+struct ChainState {
+    double ss, pri, sigma2, cov_n, wcnt;
+    int k, r_diag, bad0, pad;
+    long long n_ss, n_acc1, n_acc2, n_oob, n_adapt, n_cholfail, n_dr, n_spec, rej, reju;
+    long long pc[8], tprev;
+};
+
 // Immutable per-chain context, built once in shared memory so that the out-of-line phases below
 // (kept out of line to keep the hot loop inside the instruction cache) can share it.
 struct ChainCtx {
@@ -300,22 +308,22 @@ __device__ __noinline__ void generate(const RunArgs &a, const ChainCtx &cx, int 
             }
         }
     } else {
-        const int npairs = (npar + 1) >> 1, per = 2 * npairs + 1;    // work items per step: normal pairs + (u, chi2)
+        const int npairs = (npar + 1) >> 1, per = npairs + 1;    // work items per step: normal pairs (both stages) + (u, chi2)
 #pragma unroll 1
         for (int it = tid; it < nnew * per; it += DRAM_THREADS) {
             const int sidx = it / per, q2 = it - sidx * per, st = g0 + sidx;
             double *dz = cx.slot_d(st), *sc = cx.slot_sc(st);
-            if (q2 == 2 * npairs) {
+            if (q2 == npairs) {
                 const u32x4 ru = draw(a.seed, cx.uid, st, RK_U, 0);
                 sc[0] = u01(ru.x, ru.y);
                 sc[1] = u01(ru.z, ru.w);
                 sc[2] = a.updatesigma ? chi2_draw(a.seed, cx.uid, st, a.N0 + 2.0 * cx.N) : 1.0;
             } else {
-                const int kind = q2 >= npairs ? 1 : 0, q = q2 - kind * npairs;
-                double za, zb;
-                normal_pair(draw(a.seed, cx.uid, st, kind ? RK_Z2 : RK_Z1, q), za, zb);
-                dz[4 * q + kind] = za;
-                if (2 * q + 1 < npar) dz[4 * q + 2 + kind] = zb;
+                // the stage-1 and stage-2 normals of parameters 2q, 2q+1: two independent Philox + Box-Muller
+                // chains in one body so that they overlap
+                double4 z = normal_quad(a.seed, cx.uid, st, q2);
+                *reinterpret_cast<double2 *>(dz + 4 * q2) = make_double2(z.x, z.z);          // (z1, z2) of parameter 2q
+                if (2 * q2 + 1 < npar) *reinterpret_cast<double2 *>(dz + 4 * q2 + 2) = make_double2(z.y, z.w);
             }
         }
     }
@@ -595,6 +603,7 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
     __shared__ S2Stats s_s2;
     __shared__ double s_sc[4];
     __shared__ int s_item, s_done;
+    __shared__ ChainState st;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     // Persistent CTAs pull (time slice, chain) items from a global queue, slice-major, so that any
@@ -689,50 +698,55 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
             for (int i = tid; i < cx.npk; i += DRAM_THREADS) cx.gM2[i] = 0.0;
         }
 
-        // ---- chain state (uniform across the CTA)
-        bool r_diag = true, bad0 = false;
-        double cov_n = 0.0;                                    // rows folded into (cmean, M2) so far
-        double ss = 0.0, pri = 0.0, sigma2 = a.sigma2_0;
-        long long n_ss = 1, n_acc1 = 0, n_acc2 = 0, n_oob = 0, n_adapt = 0, n_cholfail = 0, n_dr = 0, n_spec = 0;
-        long long rej = 0, reju = 0;
-        double wcnt = 0.0;                                     // rows folded into the summaries
-        long long pc[4] = {0, 0, 0, 0};                        // phase cycles (thread 0)
-        int k;                                                 // next step to decide
-        if (seg > 0) {
-            ss = __ldcg(gst + 0); pri = __ldcg(gst + 1); sigma2 = __ldcg(gst + 2); cov_n = __ldcg(gst + 3);
-            wcnt = __ldcg(gst + 4); r_diag = __ldcg(gst + 5) != 0.0;
-            if (tid == 0) { s_s2.sum = __ldcg(gst + 6); s_s2.sq_sum = __ldcg(gst + 7); s_s2.cnt = __ldcg(gst + 9); }
-            const long long *gc = reinterpret_cast<const long long *>(gst + 16);
-            n_ss = __ldcg(gc + 0); n_acc1 = __ldcg(gc + 1); n_acc2 = __ldcg(gc + 2); n_oob = __ldcg(gc + 3);
-            n_adapt = __ldcg(gc + 4); n_cholfail = __ldcg(gc + 5); n_dr = __ldcg(gc + 6); n_spec = __ldcg(gc + 7);
-            rej = __ldcg(gc + 8);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) pc[i] = __ldcg(gc + 9 + i);
-            k = seg * a.seglen;
+        // ---- chain state: lives in shared memory (st), written by thread 0 between barriers, so that
+        //      almost nothing is live in registers across the out-of-line phase calls (register
+        //      spills go to local memory, and with ~220 KB of the SM carved out as shared memory there
+        //      is practically no L1 left to catch them)
+        if (tid == 0) {
+            if (seg == 0) {
+                st.ss = 0.0; st.pri = 0.0; st.sigma2 = a.sigma2_0; st.cov_n = 0.0; st.wcnt = 0.0; st.r_diag = 1; st.bad0 = 0;
+                st.n_ss = 1; st.n_acc1 = 0; st.n_acc2 = 0; st.n_oob = 0; st.n_adapt = 0; st.n_cholfail = 0; st.n_dr = 0; st.n_spec = 0;
+                st.rej = 0; st.reju = 0;
+                for (int i = 0; i < 8; ++i) st.pc[i] = 0;
+                s_s2.sum = 0.0; s_s2.sq_sum = 0.0; s_s2.cnt = 0.0;
+                st.k = 1;
+            } else {
+                st.ss = __ldcg(gst + 0); st.pri = __ldcg(gst + 1); st.sigma2 = __ldcg(gst + 2); st.cov_n = __ldcg(gst + 3);
+                st.wcnt = __ldcg(gst + 4); st.r_diag = __ldcg(gst + 5) != 0.0; st.bad0 = 0;
+                s_s2.sum = __ldcg(gst + 6); s_s2.sq_sum = __ldcg(gst + 7); s_s2.cnt = __ldcg(gst + 9);
+                const long long *gc = reinterpret_cast<const long long *>(gst + 16);
+                st.n_ss = __ldcg(gc + 0); st.n_acc1 = __ldcg(gc + 1); st.n_acc2 = __ldcg(gc + 2); st.n_oob = __ldcg(gc + 3);
+                st.n_adapt = __ldcg(gc + 4); st.n_cholfail = __ldcg(gc + 5); st.n_dr = __ldcg(gc + 6); st.n_spec = __ldcg(gc + 7);
+                st.rej = __ldcg(gc + 8); st.reju = 0;
+                for (int i = 0; i < 8; ++i) st.pc[i] = __ldcg(gc + 9 + i);
+                st.k = seg * a.seglen;
+            }
+            st.tprev = clock64();
         }
         __syncthreads();
-        long long tprev = clock64();
-#define TC_PHASE(i) do { const long long tn__ = clock64(); pc[i] += tn__ - tprev; tprev = tn__; } while (0)
+#define TC_PHASE(i) do { if (tid == 0) { const long long tn__ = clock64(); st.pc[i] += tn__ - st.tprev; st.tprev = tn__; } } while (0)
 
         if (seg == 0) {
             // ---- row 0: x0
-            ss = ss_eval(a.cons, cx.cv, SmemVec{cx.o_x}, w, a.algo, false, nullptr, nullptr);   // every warp, same value
-            double s = 0.0;
+            const double ss0 = ss_eval(a.cons, cx.cv, SmemVec{cx.o_x}, w, a.algo, false, nullptr, nullptr);   // every warp, same value
+            double sp = 0.0;
 #pragma unroll 1
-            for (int i = lane; i < npar; i += 32) { const double e = (cx.x[i] - cx.mu[i]) * cx.pinv[i]; s += e * e; }
-            pri = warp_sum(s);
-            bad0 = !isfinite(ss);
-            if (tid == 0) { s_s2.sum = 0.0; s_s2.sq_sum = 0.0; s_s2.cnt = 0.0; }
+            for (int i = lane; i < npar; i += 32) { const double e = (cx.x[i] - cx.mu[i]) * cx.pinv[i]; sp += e * e; }
+            sp = warp_sum(sp);
+            const bool bad = !isfinite(ss0);
+            if (tid == 0) { st.ss = ss0; st.pri = sp; st.bad0 = bad ? 1 : 0; }
             __syncthreads();
-            if (!bad0) {
-                wcnt = emit_rows(a, cx, 0, 1, cx.x, wcnt);
-                if (warp == 0) emit_s2(a, cx, &s_s2, nullptr, 0, 1, 1, ss, ss, sigma2);
+            if (!bad) {
+                const double wc = emit_rows(a, cx, 0, 1, cx.x, 0.0);
+                if (tid == 0) st.wcnt = wc;
+                if (warp == 0) emit_s2(a, cx, &s_s2, nullptr, 0, 1, 1, ss0, ss0, a.sigma2_0);
             }
             __syncthreads();
-            k = 1;
         }
 
+        int k = st.k;              // next step to decide
         int gen_upto = k;          // increments are ready for steps [k, gen_upto)
+        const bool bad0 = st.bad0 != 0;
 #pragma unroll 1
         while (k < k_end && !bad0) {
             // the batch never crosses an adaptation: the step whose isimu = st+1 is a multiple of adaptint
@@ -741,59 +755,79 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
             if (a.adaptint > 0) lim = min(lim, ((k + a.adaptint) / a.adaptint) * a.adaptint);   // exclusive step bound
             const int nb = lim - k;
 
-            if (gen_upto < lim) { generate(a, cx, gen_upto, lim - gen_upto, r_diag); gen_upto = lim; }
-            if (tid == 0) TC_PHASE(0);
+            if (gen_upto < lim) { generate(a, cx, gen_upto, lim - gen_upto, st.r_diag != 0); gen_upto = lim; }
+            TC_PHASE(0);
 
             // speculation: warp w runs step k+w assuming steps k..k+w-1 rejected; the sigma2 it sees is the
             // draw made at the end of step k+w-1 from the (unchanged) ss
             if (warp < nb) {
-                double s2p = sigma2;
+                const double ss = st.ss;
+                double s2p = st.sigma2;
                 if (warp > 0 && a.updatesigma) s2p = (a.N0 * a.S20 + ss) / cx.slot_sc(k + warp - 1)[2];
-                dram_step_warp(a, cx, k + warp, ss, pri, s2p, w, y1, y2, &s_res[warp]);
+                dram_step_warp(a, cx, k + warp, ss, st.pri, s2p, w, y1, y2, &s_res[warp]);
             }
             __syncthreads();
-            if (tid == 0) TC_PHASE(1);
+            TC_PHASE(1);
 
             // resolve: commit up to and including the first accepting step
             int first = nb;
 #pragma unroll 1
             for (int q = nb - 1; q >= 0; --q) if (s_res[q].acc) first = q;
             const int ncommit = first < nb ? first + 1 : nb;
-#pragma unroll 1
-            for (int q = 0; q < nb; ++q) {
-                if (q < ncommit) { n_ss += s_res[q].nev; n_oob += s_res[q].noob; if (s_res[q].fl & TC_FL_DR) ++n_dr; }
-                n_spec += s_res[q].nev;
-            }
             const int nrej = first < nb ? first : nb;                     // leading rejected steps: rows equal x
-            rej += nrej; reju += nrej;
-            const double ss_old = ss;
-            if (nrej > 0) wcnt = emit_rows(a, cx, k, nrej, cx.x, wcnt);
+            const double ss_old = st.ss;
+            double wc = st.wcnt;
+            if (nrej > 0) wc = emit_rows(a, cx, k, nrej, cx.x, wc);
+            TC_PHASE(2);
             if (first < nb) {
                 // the accepting warp's proposal becomes the state
                 const double *ya = tc_smem + cx.warp_y(first, s_res[first].acc == 2 ? 1 : 0);
                 __syncthreads();
 #pragma unroll 1
                 for (int i = tid; i < npar; i += DRAM_THREADS) cx.x[i] = ya[i];
-                ss = s_res[first].ssn; pri = s_res[first].prin;
-                if (s_res[first].acc == 1) ++n_acc1; else ++n_acc2;
                 __syncthreads();
-                wcnt = emit_rows(a, cx, k + first, 1, cx.x, wcnt);
+                wc = emit_rows(a, cx, k + first, 1, cx.x, wc);
             }
-            if (warp == 0) emit_s2(a, cx, &s_s2, s_res, k, ncommit, first, ss_old, ss, sigma2);
-            if (a.updatesigma) sigma2 = (a.N0 * a.S20 + ss) / cx.slot_sc(k + ncommit - 1)[2];
+            const double ss_new = first < nb ? s_res[first].ssn : ss_old;
+            TC_PHASE(3);
+            if (warp == 0) emit_s2(a, cx, &s_s2, s_res, k, ncommit, first, ss_old, ss_new, st.sigma2);
+            __syncthreads();                                           // everyone has read st / s_res
+            if (tid == 0) {
+                int d_ss = 0, d_oob = 0, d_dr = 0, d_spec = 0;
+#pragma unroll
+                for (int q = 0; q < SPEC; ++q) {
+                    if (q < nb) {
+                        const int nev = s_res[q].nev;
+                        d_spec += nev;
+                        if (q < ncommit) { d_ss += nev; d_oob += s_res[q].noob; d_dr += (s_res[q].fl & TC_FL_DR) ? 1 : 0; }
+                    }
+                }
+                st.n_ss += d_ss; st.n_oob += d_oob; st.n_dr += d_dr; st.n_spec += d_spec;
+                st.rej += nrej; st.reju += nrej;
+                st.wcnt = wc;
+                if (first < nb) {
+                    st.ss = ss_new; st.pri = s_res[first].prin;
+                    if (s_res[first].acc == 1) ++st.n_acc1; else ++st.n_acc2;
+                }
+                if (a.updatesigma) st.sigma2 = (a.N0 * a.S20 + ss_new) / cx.slot_sc(k + ncommit - 1)[2];
+            }
             k += ncommit;
             __syncthreads();
-            if (tid == 0) TC_PHASE(2);
+            TC_PHASE(4);
 
             // adaptation after the step with isimu = k, a multiple of adaptint
             if (a.adaptint > 0 && k % a.adaptint == 0) {
-                const double rate = a.burnin_cumulative ? (double)rej / k : (double)reju / a.adaptint;
-                const int rc = adapt(a, cx, k, cov_n, rate, r_diag, &s_sc[0]);
-                if (a.do_cov) cov_n += a.adaptint;
-                if (rc == 1) { r_diag = false; ++n_adapt; }
-                else if (rc == 2) ++n_cholfail;
-                reju = 0;
-                if (tid == 0) TC_PHASE(3);
+                const double rate = a.burnin_cumulative ? (double)st.rej / k : (double)st.reju / a.adaptint;
+                const int rc = adapt(a, cx, k, st.cov_n, rate, st.r_diag != 0, &s_sc[0]);
+                __syncthreads();
+                if (tid == 0) {
+                    if (a.do_cov) st.cov_n += a.adaptint;
+                    if (rc == 1) { st.r_diag = 0; ++st.n_adapt; }
+                    else if (rc == 2) ++st.n_cholfail;
+                    st.reju = 0;
+                }
+                __syncthreads();
+                TC_PHASE(5);
             }
         }
 
@@ -808,12 +842,12 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
                 gst[32 + 3 * a.ld + i] = cx.rdiag[i];
             }
             if (tid == 0) {
-                gst[0] = ss; gst[1] = pri; gst[2] = sigma2; gst[3] = cov_n; gst[4] = wcnt; gst[5] = r_diag ? 1.0 : 0.0;
+                gst[0] = st.ss; gst[1] = st.pri; gst[2] = st.sigma2; gst[3] = st.cov_n; gst[4] = st.wcnt; gst[5] = st.r_diag ? 1.0 : 0.0;
                 gst[6] = s_s2.sum; gst[7] = s_s2.sq_sum; gst[8] = 0.0; gst[9] = s_s2.cnt;
                 long long *gc = reinterpret_cast<long long *>(gst + 16);
-                gc[0] = n_ss; gc[1] = n_acc1; gc[2] = n_acc2; gc[3] = n_oob; gc[4] = n_adapt; gc[5] = n_cholfail; gc[6] = n_dr;
-                gc[7] = n_spec; gc[8] = rej;
-                for (int i = 0; i < 4; ++i) gc[9 + i] = pc[i];
+                gc[0] = st.n_ss; gc[1] = st.n_acc1; gc[2] = st.n_acc2; gc[3] = st.n_oob; gc[4] = st.n_adapt; gc[5] = st.n_cholfail;
+                gc[6] = st.n_dr; gc[7] = st.n_spec; gc[8] = st.rej;
+                for (int i = 0; i < 7; ++i) gc[9 + i] = st.pc[i];
             }
             __threadfence();
             __syncthreads();
@@ -822,10 +856,13 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
         }
 
         // ---- summaries (TranscriptionCycleMCMC.m:286-303); a chain whose ss(x0) is not finite ends here
+        {
+            const double wcnt = st.wcnt;
 #pragma unroll 1
-        for (int i = tid; i < npar; i += DRAM_THREADS) {
-            if (a.mean) a.mean[(size_t)ch * a.ld + i] = bad0 ? 0.0 : cx.wmean[i];
-            if (a.std) a.std[(size_t)ch * a.ld + i] = (!bad0 && wcnt > 0) ? sqrt(cx.wM2[i] / wcnt) : 0.0;
+            for (int i = tid; i < npar; i += DRAM_THREADS) {
+                if (a.mean) a.mean[(size_t)ch * a.ld + i] = bad0 ? 0.0 : cx.wmean[i];
+                if (a.std) a.std[(size_t)ch * a.ld + i] = (!bad0 && wcnt > 0) ? sqrt(cx.wM2[i] / wcnt) : 0.0;
+            }
         }
         if (tid == 0) {
             if (a.sig) {
@@ -836,12 +873,11 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
             }
             if (a.counters) {
                 long long *c = a.counters + (size_t)ch * TC_NCOUNTERS;
-                c[TC_CNT_SS_EVALS] = n_ss; c[TC_CNT_ACC_STAGE1] = n_acc1; c[TC_CNT_ACC_STAGE2] = n_acc2;
-                c[TC_CNT_OUT_OF_BOUNDS] = n_oob; c[TC_CNT_ADAPTATIONS] = n_adapt;
-                c[TC_CNT_CHOL_FAIL] = n_cholfail; c[TC_CNT_DR_TRIES] = n_dr; c[TC_CNT_STATUS] = bad0 ? 1 : 0;
-                for (int i = 0; i < 4; ++i) c[TC_CNT_CYCLES0 + i] = pc[i];
-                c[TC_CNT_CYCLES0 + 4] = 0; c[TC_CNT_CYCLES0 + 5] = 0; c[TC_CNT_CYCLES0 + 6] = 0;
-                c[TC_CNT_CYCLES0 + 7] = n_spec;
+                c[TC_CNT_SS_EVALS] = st.n_ss; c[TC_CNT_ACC_STAGE1] = st.n_acc1; c[TC_CNT_ACC_STAGE2] = st.n_acc2;
+                c[TC_CNT_OUT_OF_BOUNDS] = st.n_oob; c[TC_CNT_ADAPTATIONS] = st.n_adapt;
+                c[TC_CNT_CHOL_FAIL] = st.n_cholfail; c[TC_CNT_DR_TRIES] = st.n_dr; c[TC_CNT_STATUS] = bad0 ? 1 : 0;
+                for (int i = 0; i < 7; ++i) c[TC_CNT_CYCLES0 + i] = st.pc[i];
+                c[TC_CNT_CYCLES0 + 7] = st.n_spec;
             }
             // a failed chain must not block the (never issued) later slices: mark everything done
             __threadfence();
