@@ -98,8 +98,8 @@ struct RunArgs {
     // scratch (global)
     double *gR, *gM2, *gRows, *gCmean, *gState;
     // time slicing
-    int seglen, nitems;
-    int *queue, *done;
+    int seglen;
+    int *cstate;
 };
 
 // Shared-memory budget of the sampler (doubles), N = max time points over the dataset.
@@ -602,36 +602,63 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
     __shared__ ChainCtx cx;
     __shared__ S2Stats s_s2;
     __shared__ double s_sc[4];
-    __shared__ int s_item, s_done;
+    __shared__ int s_item, s_done, s_min;
     __shared__ ChainState st;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-    // Persistent CTAs pull (time slice, chain) items from a global queue, slice-major, so that any
-    // number of chains shares the resident CTAs evenly (299 chains on 296 CTA slots would otherwise
-    // cost two full waves).  A slice ends on an adaptation boundary, where the ring is empty and the
-    // factor R / covariance already live in HBM; the rest of the chain state is a few vectors.
+    // Persistent CTAs time-slice the chains: a free CTA claims ANY chain that is not running and still
+    // has slices left (a.cstate[c] = next slice, bit 30 = running), runs one slice and releases it.
+    // So any number of chains shares the resident CTAs evenly (299 chains on 296 CTA slots would
+    // otherwise cost two full waves), and nobody ever waits for a particular chain.  A slice ends on
+    // an adaptation boundary, where the ring is empty and the factor R / covariance already live in
+    // HBM; the rest of the chain state is a few vectors.
+    const int LOCK = 1 << 30;
+    const int nseg = (a.nsimu + a.seglen - 1) / a.seglen;
+    int start = (int)(((long long)blockIdx.x * a.nchains) / gridDim.x);
 #pragma unroll 1
     for (;;) {
-        __syncthreads();
-        if (tid == 0) s_item = atomicAdd(a.queue, 1);
-        __syncthreads();
-        const int item = s_item;
-        if (item >= a.nitems) break;
-        const int ch = item % a.nchains, seg = item / a.nchains;
-        const int k_end = min(a.nsimu, (seg + 1) * a.seglen);
-        const bool last_seg = k_end >= a.nsimu;
-        if (seg > 0) {
-            // the previous slice of this chain may still be running on another CTA (it was dequeued
-            // before this one, so it is resident and making progress)
+        // claim a chain: the whole CTA scans the state words in parallel, thread 0 takes the first free one
+#pragma unroll 1
+        for (;;) {
+            __syncthreads();
+            if (tid == 0) s_min = 0x7fffffff;
+            __syncthreads();
+            int pending = 0;
+#pragma unroll 1
+            for (int base = 0; base < a.nchains; base += DRAM_THREADS) {
+                const int i = base + tid;
+                int hit = 0;
+                if (i < a.nchains) {
+                    const int v = *reinterpret_cast<volatile int *>(a.cstate + (start + i) % a.nchains);
+                    if (v & LOCK) pending = 1;
+                    else if (v < nseg) { hit = 1; atomicMin(&s_min, i); }
+                }
+                if (__syncthreads_or(hit)) break;
+            }
+            pending = __syncthreads_or(pending);
+            const int imin = s_min;
+            if (imin == 0x7fffffff) {
+                if (!pending) { if (tid == 0) s_item = -1; break; }     // every chain is finished
+                __nanosleep(2000);
+                continue;
+            }
             if (tid == 0) {
-                int d;
-                while ((d = atomicAdd(a.done + ch, 0)) < seg) __nanosleep(500);
-                s_done = d;
+                const int c = (start + imin) % a.nchains;
+                const int v = *reinterpret_cast<volatile int *>(a.cstate + c);
+                const bool ok = !(v & LOCK) && v < nseg && atomicCAS(a.cstate + c, v, v | LOCK) == v;
+                s_item = ok ? c : -2;
+                s_done = v;
             }
             __syncthreads();
-            __threadfence();
-            if (s_done >= (1 << 30)) continue;          // the chain ended early (ss(x0) not finite)
+            if (s_item != -2) break;
         }
+        __syncthreads();
+        const int ch = s_item, seg = s_done;
+        if (ch < 0) break;                                  // every chain is finished
+        start = (ch + 1) % a.nchains;
+        __threadfence();
+        const int k_end = min(a.nsimu, (seg + 1) * a.seglen);
+        const bool last_seg = k_end >= a.nsimu;
         const int cid = a.chain_cell[ch];
         const int N = a.cells.N[cid];
         const int npar = 7 + N;
@@ -851,7 +878,7 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
             }
             __threadfence();
             __syncthreads();
-            if (tid == 0) atomicExch(a.done + ch, seg + 1);
+            if (tid == 0) atomicExch(a.cstate + ch, seg + 1);      // release: next slice, not running
             continue;
         }
 
@@ -879,9 +906,8 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
                 for (int i = 0; i < 7; ++i) c[TC_CNT_CYCLES0 + i] = st.pc[i];
                 c[TC_CNT_CYCLES0 + 7] = st.n_spec;
             }
-            // a failed chain must not block the (never issued) later slices: mark everything done
             __threadfence();
-            atomicExch(a.done + ch, 1 << 30);
+            atomicExch(a.cstate + ch, nseg);                        // finished (also ends a chain whose ss(x0) failed)
         }
     }
 }
@@ -1382,13 +1408,9 @@ int tc_mcmc_run(const tc_cells *c, const tc_mcmc_opts *o, int nchains, const int
             long long sl = ((long long)o->nsimu + 31) / 32;
             sl = ((sl + unit - 1) / unit) * unit;
             a.seglen = (int)std::max<long long>(sl, unit);
-            const int nseg = (o->nsimu + a.seglen - 1) / a.seglen;
-            a.nitems = nseg * nc;
             CUDA_TRY(r.buf.alloc(a.gState, (size_t)nc * state_doubles(ld)));
-            CUDA_TRY(r.buf.alloc(a.queue, 1));
-            CUDA_TRY(r.buf.alloc(a.done, nc));
-            CUDA_TRY(cudaMemsetAsync(a.queue, 0, sizeof(int), r.st));
-            CUDA_TRY(cudaMemsetAsync(a.done, 0, sizeof(int) * nc, r.st));
+            CUDA_TRY(r.buf.alloc(a.cstate, nc));
+            CUDA_TRY(cudaMemsetAsync(a.cstate, 0, sizeof(int) * nc, r.st));
         }
         int per_sm = 0, sms = 0;
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dram_kernel, DRAM_THREADS, smem));
