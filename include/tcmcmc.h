@@ -100,8 +100,11 @@ typedef struct tc_mcmc_opts {
 enum {
     TC_CNT_SS_EVALS = 0, TC_CNT_ACC_STAGE1 = 1, TC_CNT_ACC_STAGE2 = 2, TC_CNT_OUT_OF_BOUNDS = 3,
     TC_CNT_ADAPTATIONS = 4, TC_CNT_CHOL_FAIL = 5, TC_CNT_DR_TRIES = 6, TC_CNT_STATUS = 7,
-    /* SM cycles thread 0 spent per phase: randomness, proposals, stage-1 ss, delayed rejection,
-       state/sigma2/row write-back, covariance block update, Cholesky (+burn-in scaling), spare */
+    /* SM cycles thread 0 of the chain's CTA spent per phase of the speculative batch loop:
+       +0 generation (randomness + tensor-core increments), +1 speculation (SPEC steps in parallel),
+       +2 rows of rejected steps, +3 accept/copy, +4 per-row scalars + state update, +5 adaptation
+       (covariance block update + Cholesky), +6 spare; +7 = forward-model evaluations executed
+       including the speculative ones that were discarded (TC_CNT_SS_EVALS counts only the committed) */
     TC_CNT_CYCLES0 = 8,
     TC_NCOUNTERS = 16
 };

@@ -19,3 +19,8 @@ Ns = g["N"][cc]
 print("  per-chain cycles/step: mean %.0f max %.0f min %.0f; by N:" % (tot_c.mean(), tot_c.max(), tot_c.min()), {int(n): int(tot_c[Ns == n].mean()) for n in np.unique(Ns)})
 acc = (out["counters"][:, 1] + out["counters"][:, 2]) / nsimu
 print("  acceptance by chain: mean %.3f min %.3f max %.3f; corr(cycles, acc) %.2f" % (acc.mean(), acc.min(), acc.max(), np.corrcoef(tot_c, acc)[0, 1]))
+i = int(np.argmax(tot_c)); j = int(np.argmin(tot_c))
+for tag, q in (("slowest", i), ("fastest", j)):
+    c = out["counters"][q]
+    nbatch_est = None
+    print("  %s chain %d (N=%d, acc %.3f, evals/step %.2f, spec evals/step %.2f): generate %.0f speculate %.0f emit-rej %.0f accept %.0f s2+state %.0f adapt %.0f" % (tag, q, Ns[q], acc[q], c[0] / nsimu, c[15] / nsimu, *(c[8:14] / nsimu)))

@@ -596,8 +596,18 @@ __device__ __noinline__ int adapt(const RunArgs &a, const ChainCtx &cx, int isim
 //   [0..15] scalars | [16..31] counters (as doubles' bit patterns via long long) | x | wmean | wM2 | rdiag
 __host__ __device__ inline int state_doubles(int ld) { return 32 + 4 * ld; }
 
-__global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_constant__ RunArgs a)
+__global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_constant__ RunArgs ga)
 {
+    // The out-of-line phases take the launch arguments by reference: a reference to the kernel parameter
+    // itself would turn every field access into a generic load from parameter memory, so they get a
+    // shared-memory copy instead.
+    __shared__ RunArgs a;
+    {
+        const int *src = reinterpret_cast<const int *>(&ga);
+        int *dst = reinterpret_cast<int *>(&a);
+        for (int i = threadIdx.x; i < (int)(sizeof(RunArgs) / sizeof(int)); i += DRAM_THREADS) dst[i] = src[i];
+    }
+    __syncthreads();
     __shared__ StepRes s_res[SPEC];
     __shared__ ChainCtx cx;
     __shared__ S2Stats s_s2;
@@ -874,7 +884,7 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
                 long long *gc = reinterpret_cast<long long *>(gst + 16);
                 gc[0] = st.n_ss; gc[1] = st.n_acc1; gc[2] = st.n_acc2; gc[3] = st.n_oob; gc[4] = st.n_adapt; gc[5] = st.n_cholfail;
                 gc[6] = st.n_dr; gc[7] = st.n_spec; gc[8] = st.rej;
-                for (int i = 0; i < 7; ++i) gc[9 + i] = st.pc[i];
+                for (int i = 0; i < 8; ++i) gc[9 + i] = st.pc[i];
             }
             __threadfence();
             __syncthreads();
