@@ -133,3 +133,26 @@ def test_chain_layout_and_bounds(gpu_cells, cells_npz):
         assert np.array_equal(out1["chain"][i][0, :npar], th0[i, :npar])
     acc = out["counters"][:, _lib.CNT_ACC_STAGE1] + out["counters"][:, _lib.CNT_ACC_STAGE2]
     assert np.all(acc > 0)
+
+
+def test_time_slices_are_transparent(gpu_cells, cells_npz, orc):
+    """Chains are time-sliced over the persistent CTAs (state parked in HBM between slices).  With
+    nsimu = 3300 a slice is 200 steps = two adaptation intervals, and there are 17 park/resume
+    cycles: the production run must still be the oracle's chain on the device's own Philox streams
+    (regression: the parked phase clocks once overlapped x[0])."""
+    from transcriptioncycleinference_b200 import _lib
+    chain_cell = np.array([0, 250], dtype=np.int32)
+    uid = np.array([0, 250 << 20], dtype=np.uint64)
+    nsimu, burn, seed = 3300, 1000, 20201028
+    inputs = _setup(gpu_cells, chain_cell, 51)
+    opts = _lib.default_opts(nsimu=nsimu, burnintime=burn, n_burn=1, store_chain=1, seed=seed)
+    out = gpu_cells.mcmc_run(opts, chain_cell, *inputs, chain_uid=uid, want_flags=True)
+    for i, c in enumerate(chain_cell):
+        N = int(cells_npz["N"][c]); npar = 7 + N
+        d = _lib.rng_dump(seed, int(uid[i]), npar, 1 + 2 * N, nsimu)
+        st = {k: v[None] for k, v in d.items()}
+        ref = _oracle_chain(orc, cells_npz, int(c), dict(nsimu=nsimu, burnintime=burn),
+                            [x[i:i + 1] for x in inputs], 0, st)
+        assert np.array_equal(out["flags"][i], ref["flags"])
+        np.testing.assert_allclose(out["chain"][i][:, :npar], ref["chain"], rtol=0, atol=1e-7)
+        np.testing.assert_allclose(out["s2chain"][i], ref["s2chain"], rtol=1e-9)

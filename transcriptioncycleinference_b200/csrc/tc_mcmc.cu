@@ -593,8 +593,9 @@ __device__ __noinline__ int adapt(const RunArgs &a, const ChainCtx &cx, int isim
 // with the CPU oracle).  The randomness and the proposal increments z R do not depend on the state,
 // so they are generated once per step, ahead of use, into a ring of SPEC slots.
 // Saved state of a chain between two time slices (doubles): see dram_kernel.
-//   [0..15] scalars | [16..31] counters (as doubles' bit patterns via long long) | x | wmean | wM2 | rdiag
-__host__ __device__ inline int state_doubles(int ld) { return 32 + 4 * ld; }
+//   [0..15] scalars | [16..47] counters (long long) | x | wmean | wM2 | rdiag
+#define ST_VEC0 48         // first vector: 16 scalars + up to 32 counters (17 used: 9 counts + 8 phase clocks)
+__host__ __device__ inline int state_doubles(int ld) { return ST_VEC0 + 4 * ld; }
 
 __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_constant__ RunArgs ga)
 {
@@ -724,10 +725,10 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
                 cx.wM2[i] = 0.0;
                 if (a.do_cov) cx.cmean[i] = 0.0;
             } else {
-                cx.x[i] = __ldcg(gst + 32 + i);
-                cx.wmean[i] = __ldcg(gst + 32 + a.ld + i);
-                cx.wM2[i] = __ldcg(gst + 32 + 2 * a.ld + i);
-                cx.rdiag[i] = __ldcg(gst + 32 + 3 * a.ld + i);
+                cx.x[i] = __ldcg(gst + ST_VEC0 + i);
+                cx.wmean[i] = __ldcg(gst + ST_VEC0 + a.ld + i);
+                cx.wM2[i] = __ldcg(gst + ST_VEC0 + 2 * a.ld + i);
+                cx.rdiag[i] = __ldcg(gst + ST_VEC0 + 3 * a.ld + i);
             }
         }
         if (seg == 0 && a.do_cov) {
@@ -873,10 +874,10 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
             // ---- park the chain: the next slice may run on any CTA
 #pragma unroll 1
             for (int i = tid; i < npar; i += DRAM_THREADS) {
-                gst[32 + i] = cx.x[i];
-                gst[32 + a.ld + i] = cx.wmean[i];
-                gst[32 + 2 * a.ld + i] = cx.wM2[i];
-                gst[32 + 3 * a.ld + i] = cx.rdiag[i];
+                gst[ST_VEC0 + i] = cx.x[i];
+                gst[ST_VEC0 + a.ld + i] = cx.wmean[i];
+                gst[ST_VEC0 + 2 * a.ld + i] = cx.wM2[i];
+                gst[ST_VEC0 + 3 * a.ld + i] = cx.rdiag[i];
             }
             if (tid == 0) {
                 gst[0] = st.ss; gst[1] = st.pri; gst[2] = st.sigma2; gst[3] = st.cov_n; gst[4] = st.wcnt; gst[5] = st.r_diag ? 1.0 : 0.0;
