@@ -192,6 +192,10 @@ int tc_rng_dump(uint64_t seed, uint64_t chain_uid, int npar, double chi2_dof, in
  * roofline denominator is measured, not assumed. */
 int tc_measure_fp64_peak(int device, double *dfma_per_s, double *sm_clock_mhz);
 
+/* Development aid: cycle counts of the sampler's sub-phases for chain 0 (read and reset).  Returns 1
+ * and fills out[0..n) when the library was built with -DTC_SUBPROF, else returns 0 and zero-fills. */
+int tc_debug_subprof(long long *out, int n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -22,6 +22,7 @@ EXPORTS = [
     "tc_version", "tc_last_error", "tc_device_count", "tc_device_info_get", "tc_opts_default",
     "tc_cells_create", "tc_cells_destroy", "tc_cells_t_interp", "tc_ss_batch", "tc_ss_batch_device",
     "tc_forward", "tc_mcmc_run", "tc_last_kernel_seconds", "tc_rng_dump", "tc_measure_fp64_peak",
+    "tc_debug_subprof",
 ]
 
 
@@ -103,6 +104,7 @@ def load():
     L.tc_rng_dump.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.c_double, C.c_int, dp, dp, dp, dp, dp,
                               C.c_int]
     L.tc_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.tc_debug_subprof.argtypes = [vp, C.c_int]
     _lib = L
     return L
 
@@ -164,3 +166,10 @@ def rng_dump(seed, chain_uid, npar, chi2_dof, nsimu, device=0):
     check(load().tc_rng_dump(seed, chain_uid, npar, float(chi2_dof), nsimu, ptr(z1), ptr(u1), ptr(z2),
                              ptr(u2), ptr(c2), device))
     return dict(z1=z1, u1=u1, z2=z2, u2=u2, chi2=c2)
+
+
+def debug_subprof():
+    """Sub-phase cycle counters of chain 0 (zeros unless libtcmcmc was built with -DTC_SUBPROF)."""
+    out = np.zeros(32, dtype=np.int64)
+    load().tc_debug_subprof(ptr(out), 32)
+    return out

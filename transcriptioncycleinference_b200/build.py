@@ -5,7 +5,8 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libtcmcmc.so")
+# TC_LIBTCMCMC / TC_NVCC_EXTRA: development builds only (e.g. a -DTC_SUBPROF profiling variant beside the product library)
+LIB = os.environ.get("TC_LIBTCMCMC") or os.path.join(HERE, "libtcmcmc.so")
 SOURCES = ["tc_mcmc.cu"]
 HEADERS = ["tc_device.cuh", os.path.join("..", "..", "include", "tcmcmc.h")]
 
@@ -34,7 +35,7 @@ def build(force=False, verbose=False):
     """Compile csrc/*.cu -> libtcmcmc.so.  Returns the library path."""
     if not force and not is_stale():
         return LIB
-    cmd = [nvcc_path()] + NVCC_FLAGS + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd = [nvcc_path()] + NVCC_FLAGS + os.environ.get("TC_NVCC_EXTRA", "").split() + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
     env = dict(os.environ)
     # the image exports CC/CXX pointing at a wrapper; let nvcc pick the system host compiler
     res = subprocess.run(cmd + ["-ccbin", "/usr/bin/g++"] if os.path.exists("/usr/bin/g++") else cmd,

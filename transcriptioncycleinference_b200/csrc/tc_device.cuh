@@ -80,34 +80,38 @@ __device__ __noinline__ void normal_pair(const u32x4 &r, double &z0, double &z1)
     z1 = rad * s;
 }
 
-// (z1[2q], z1[2q+1], z2[2q], z2[2q+1]) of one step: the same draws as two normal_pair calls on the RK_Z1 and
-// RK_Z2 counters, with the two dependent chains interleaved in one function body
+// The proposal normals (z1[2q], z1[2q+1], z2[2q], z2[2q+1]) of step `step`, parameters 2q and 2q+1, from ONE
+// Philox block (kind RK_Z1, slot q): words (x, y) -> the stage-1 pair, (z, w) -> the stage-2 pair.
+// Standard-normal VARIATES are a sampling device, not part of the likelihood arithmetic: they are drawn by
+// Box-Muller in single precision (32-bit radius uniform => |z| <= 6.76, 24-bit angle) and widened to FP64;
+// everything downstream (proposal, forward model, SS, acceptance) is FP64.  tc_rng_dump calls this very
+// function, so the parity harness sees bit-identical draws.
 __device__ __noinline__ double4 normal_quad(uint64_t seed, uint64_t uid, uint32_t step, uint32_t q)
 {
-    const uint32_t c2 = (uint32_t)uid, c3 = (uint32_t)(uid >> 32) << 8, k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-    const u32x4 r1 = philox4x32_10(q, step, c2, c3 | RK_Z1, k0, k1);
-    const u32x4 r2 = philox4x32_10(q, step, c2, c3 | RK_Z2, k0, k1);
-    const double ua1 = u01(r1.x, r1.y), ub1 = u01(r1.z, r1.w), ua2 = u01(r2.x, r2.y), ub2 = u01(r2.z, r2.w);
-    const double rad1 = sqrt(-2.0 * log(ua1)), rad2 = sqrt(-2.0 * log(ua2));
-    double s1, c1, s2, cc2;
-    sincospi(2.0 * ub1, &s1, &c1);
-    sincospi(2.0 * ub2, &s2, &cc2);
-    return make_double4(rad1 * c1, rad1 * s1, rad2 * cc2, rad2 * s2);
+    const u32x4 r = philox4x32_10(q, step, (uint32_t)uid, ((uint32_t)(uid >> 32) << 8) | RK_Z1, (uint32_t)seed, (uint32_t)(seed >> 32));
+    const float ua1 = ((float)r.x + 0.5f) * 2.3283064365386963e-10f, ua2 = ((float)r.z + 0.5f) * 2.3283064365386963e-10f;   // (0, 1]
+    const float ub1 = (float)(r.y >> 8) * 1.1920928955078125e-7f, ub2 = (float)(r.w >> 8) * 1.1920928955078125e-7f;       // [0, 2) turns / 2
+    const float rad1 = sqrtf(-2.0f * logf(ua1)), rad2 = sqrtf(-2.0f * logf(ua2));
+    float s1, c1, s2, c2;
+    sincospif(ub1, &s1, &c1);
+    sincospif(ub2, &s2, &c2);
+    return make_double4((double)(rad1 * c1), (double)(rad1 * s1), (double)(rad2 * c2), (double)(rad2 * s2));
 }
 
-// chi-square(dof) = 2*Gamma(dof/2) by Marsaglia-Tsang (dof >= 2); attempt t uses slots 2t, 2t+1.
+// chi-square(dof) = 2*Gamma(dof/2) by Marsaglia-Tsang (dof >= 2); attempt t uses slots 2t (the normal: Box-Muller
+// in single precision like the proposal normals, words x, y) and 2t+1 (the 53-bit uniform).
 __device__ __noinline__ double chi2_draw(uint64_t seed, uint64_t uid, uint32_t step, double dof)
 {
     const double a = 0.5 * dof;
     const double d = a - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
     for (uint32_t t = 0; t < 64; ++t) {
         const u32x4 r0 = draw(seed, uid, step, RK_CHI2, 2 * t);
-        double x, unused;
-        normal_pair(r0, x, unused);
+        const u32x4 r1 = draw(seed, uid, step, RK_CHI2, 2 * t + 1);
+        const float ua = ((float)r0.x + 0.5f) * 2.3283064365386963e-10f, ub = (float)(r0.y >> 8) * 1.1920928955078125e-7f;
+        const double x = (double)(sqrtf(-2.0f * logf(ua)) * cospif(ub));
         double v = 1.0 + c * x;
         if (v <= 0.0) continue;
         v = v * v * v;
-        const u32x4 r1 = draw(seed, uid, step, RK_CHI2, 2 * t + 1);
         const double u = u01(r1.x, r1.y);
         const double x2 = x * x;
         if (u < 1.0 - 0.0331 * x2 * x2) return 2.0 * d * v;
@@ -139,6 +143,10 @@ extern __shared__ __align__(16) double tc_smem[];
 struct SmemVec {          // a vector in shared memory
     int off;
     __device__ __forceinline__ double operator[](int i) const { return tc_smem[off + i]; }
+};
+struct SumVec {           // theta = state + proposal increment, both in shared memory; increments are stored
+    int ox, os;           // interleaved (stage 1, stage 2) per parameter, os already includes the stage
+    __device__ __forceinline__ double operator[](int i) const { return tc_smem[ox + i] + tc_smem[os + 2 * i]; }
 };
 struct GlobVec {          // a vector in global memory
     const double *p;

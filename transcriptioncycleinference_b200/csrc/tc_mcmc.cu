@@ -37,11 +37,22 @@ static int fail(int code, const std::string &msg)
     } while (0)
 
 #define DRAM_THREADS 256   // 8 warps; warp w simulates future step k+w of the chain speculatively
-#define SPEC 8             // steps per speculative batch (= warps per CTA)
+#define SPEC 8             // steps per speculative round (= warps per CTA)
+#define RING 16            // proposal increments are generated ahead of use, up to RING steps per call
 #define SS_WARPS 8
 #define SS_THREADS (32 * SS_WARPS)
 #define COV_RC 8           // rows of the chain block staged per pass of the scatter update
 #define COV_TPT 3          // 4x4 covariance tiles per thread (3*256 >= 595 tiles at npar = 136)
+
+// development aid: cycle counts of sub-phases, chain 0 only (build with -DTC_SUBPROF; see scripts/subprof.py)
+#ifdef TC_SUBPROF
+__device__ long long tc_subprof[32];
+#define SUBP_BEGIN long long sp_prev__ = clock64()
+#define SUBP(i) do { if (threadIdx.x == 0 && cx.ch == 0) { const long long t__ = clock64(); tc_subprof[i] += t__ - sp_prev__; sp_prev__ = t__; } } while (0)
+#else
+#define SUBP_BEGIN
+#define SUBP(i)
+#endif
 
 // packed upper-triangular row-major index of (i, j), j >= i
 __host__ __device__ __forceinline__ int pidx(int n, int i, int j) { return i * n - (i * (i - 1)) / 2 + (j - i); }
@@ -96,81 +107,196 @@ struct RunArgs {
     int *flags;
     double *sschain;
     // scratch (global)
-    double *gR, *gM2, *gRows, *gCmean, *gState;
+    double *gR, *gM2, *gRows, *gWts, *gCmean, *gState;
     // time slicing
     int seglen;
     int *cstate;
 };
 
 // Shared-memory budget of the sampler (doubles), N = max time points over the dataset.
-//   cell constants | 10 per-parameter vectors | SPEC ring slots of interleaved increments (+8 scalars)
-//   | SPEC per-warp areas (forward-model scratch + the warp's two proposals).
-// The per-warp areas are time-shared: during generation they hold the factor R (copied from HBM/L2
-// for the tensor-core product Z R), during adaptation the covariance row chunk and the Cholesky
-// workspace.
+//   cell constants | 10 per-parameter vectors | RING slots of interleaved proposal increments (+8 scalars)
+//   | SPEC per-warp forward-model scratch areas.
+// Ring + per-warp areas are contiguous: during adaptation (when both are idle) they are the workspace of
+// the covariance update and of the Cholesky factorisation.
+__host__ __device__ __forceinline__ int tidx(int nt4, int bi, int bj) { return bi * nt4 - (bi * (bi - 1)) / 2 + (bj - bi); }
+__host__ __device__ inline int chol_ws_doubles(int n)
+{
+    const int nt4 = (n + 3) >> 2, T = nt4 * (nt4 + 1) / 2;
+    return 16 * T + (T + 3) / 4 + 2;                      // tiles + the u16 tile table
+}
+
+__host__ __device__ inline int dram_slot(int N) { return 2 * (7 + N) + 2 + 8; }
 __host__ __device__ inline int dram_wsz(int N)
 {
-    const int npar = 7 + N, npk = npar * (npar + 1) / 2;
-    int w = work_doubles(N) + 2 * npar + 4;
-    const int need = (npk + SPEC - 1) / SPEC + 2;
+    const int npar = 7 + N;
+    int w = (work_doubles(N) + 1) & ~1;
+    const int need = (chol_ws_doubles(npar) - RING * dram_slot(N) + SPEC - 1) / SPEC + 2;
     if (w < need) w = need;
     return (w + 1) & ~1;
 }
-__host__ __device__ inline int dram_slot(int N) { return 2 * (7 + N) + 2 + 8; }
 __host__ __device__ inline int dram_smem_doubles(int N)
 {
-    return cell_doubles(N) + 10 * (7 + N) + SPEC * dram_slot(N) + SPEC * dram_wsz(N) + 16;
+    return cell_doubles(N) + 10 * (7 + N) + 4 + RING * dram_slot(N) + SPEC * dram_wsz(N) + 16;
 }
 
-// In-place upper Cholesky of the packed matrix in Rw (R'R = A) by the whole CTA (two adjacent lanes
-// split the dot product of one element and combine with a shuffle).  Returns false when the matrix
-// is not positive definite.  Left-looking: row j of R from rows k < j.
-__device__ __noinline__ bool chol_packed(int n, double *Rw, double *s_piv)
+// ---- Cholesky of the proposal covariance, in shared memory, by the whole CTA
+// Storage: the upper triangle in 4x4 TILES (tile (bi, bj), bi <= bj, at index bi*nt4 - bi(bi-1)/2 + bj - bi, 16
+// doubles row-major), padded to a multiple of 4 with an identity block, so that every tile operation is
+// eight 16-byte shared-memory accesses with no index arithmetic; `tab[t]` = (bi << 8) | bj of tile t.
+__device__ __forceinline__ void ld_tile(const double *p, double (&t)[16])
 {
-    const int tid = threadIdx.x, nt = blockDim.x;
-    const int e = tid >> 1, h = tid & 1, ne = nt >> 1;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { const double2 v = reinterpret_cast<const double2 *>(p)[e]; t[2 * e] = v.x; t[2 * e + 1] = v.y; }
+}
+__device__ __forceinline__ void st_tile(double *p, const double (&t)[16])
+{
+#pragma unroll
+    for (int e = 0; e < 8; ++e) reinterpret_cast<double2 *>(p)[e] = make_double2(t[2 * e], t[2 * e + 1]);
+}
+
+// In-place upper Cholesky (R'R = A) of the tiled matrix W (n padded to 4*nt4).  Right-looking, panels of two
+// tile rows (8 matrix rows): (1) every lane of warp 0 factors the 8x8 diagonal block redundantly in registers
+// (a chain of 8 dependent rsqrt's, no communication), (2) the panel to its right is solved column by
+// column (one thread per column), (3) the trailing tiles get the rank-8 update in registers.  Returns
+// false when a pivot is not positive.
+__device__ __noinline__ bool chol_tiled(int nt4, double *W, const unsigned short *tab, double *s_dinv, int *s_fail)
+{
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int T = nt4 * (nt4 + 1) / 2;
+    if (tid == 0) *s_fail = 0;
+    __syncthreads();
 #pragma unroll 1
-    for (int j = 0; j < n; ++j) {
-        const int rj = pidx(n, j, j);
-        const int k0 = h ? (j >> 1) : 0, k1 = h ? j : (j >> 1);
-#pragma unroll 1
-        for (int i0 = j; i0 < n; i0 += ne) {
-            const int i = i0 + e;
-            const bool act = i < n;
-            double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-            if (act) {
-                int k = k0, rk = pidx(n, k0, k0);            // start of packed row k
-#pragma unroll 1
-                for (; k + 3 < k1; k += 4) {
-                    const int r1 = rk + n - k, r2 = r1 + n - k - 1, r3 = r2 + n - k - 2;
-                    s0 = fma(Rw[rk + (j - k)], Rw[rk + (i - k)], s0);
-                    s1 = fma(Rw[r1 + (j - k - 1)], Rw[r1 + (i - k - 1)], s1);
-                    s2 = fma(Rw[r2 + (j - k - 2)], Rw[r2 + (i - k - 2)], s2);
-                    s3 = fma(Rw[r3 + (j - k - 3)], Rw[r3 + (i - k - 3)], s3);
-                    rk = r3 + n - k - 3;
-                }
-#pragma unroll 1
-                for (; k < k1; ++k) {
-                    s0 = fma(Rw[rk + (j - k)], Rw[rk + (i - k)], s0);
-                    rk += n - k;
+    for (int b0 = 0; b0 < nt4; b0 += 2) {
+        const bool two = b0 + 1 < nt4;                    // the last panel of an odd nt4 has one tile row
+        double *t00 = W + 16 * tidx(nt4, b0, b0);
+        double *t01 = two ? W + 16 * tidx(nt4, b0, b0 + 1) : nullptr;
+        double *t11 = two ? W + 16 * tidx(nt4, b0 + 1, b0 + 1) : nullptr;
+        if (tid < 32) {
+            double A[8][8];                               // upper triangle of the block, A[r][c], r <= c
+            {
+                double q[16];
+                ld_tile(t00, q);
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int c = r; c < 4; ++c) A[r][c] = q[4 * r + c];
+                if (two) {
+                    ld_tile(t01, q);
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) A[r][4 + c] = q[4 * r + c];
+                    ld_tile(t11, q);
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+#pragma unroll
+                        for (int c = r; c < 4; ++c) A[4 + r][4 + c] = q[4 * r + c];
+                } else {
+#pragma unroll
+                    for (int r = 0; r < 8; ++r)
+#pragma unroll
+                        for (int c = (r < 4 ? 4 : r); c < 8; ++c) A[r][c] = (r == c) ? 1.0 : 0.0;
                 }
             }
-            double s = (s0 + s1) + (s2 + s3);
-            s += __shfl_xor_sync(0xffffffffu, s, 1);
-            if (act && h == 0) {
-                s = Rw[rj + (i - j)] - s;
-                Rw[rj + (i - j)] = s;
-                if (i == j) *s_piv = s;
+            bool bad = false;
+            double dinv[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const double d = A[j][j];
+                if (!(d > 0.0)) bad = true;
+                const double ri = rsqrt(d);
+                dinv[j] = ri;
+                A[j][j] = d * ri;
+#pragma unroll
+                for (int c = j + 1; c < 8; ++c) A[j][c] *= ri;
+#pragma unroll
+                for (int r = j + 1; r < 8; ++r)
+#pragma unroll
+                    for (int c = r; c < 8; ++c) A[r][c] = fma(-A[j][r], A[j][c], A[r][c]);
+            }
+            if (tid == 0) {
+                double q[16];
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) q[4 * r + c] = c >= r ? A[r][c] : 0.0;
+                st_tile(t00, q);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) s_dinv[j] = dinv[j];
+                if (bad) *s_fail = 1;
+            } else if (tid == 1 && two) {
+                double q[16];
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) q[4 * r + c] = A[r][4 + c];
+                st_tile(t01, q);
+            } else if (tid == 2 && two) {
+                double q[16];
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) q[4 * r + c] = c >= r ? A[4 + r][4 + c] : 0.0;
+                st_tile(t11, q);
             }
         }
         __syncthreads();
-        const double piv = *s_piv;
-        if (!(piv > 0.0)) return false;                   // uniform: every thread reads the same value
-        const double rjj = sqrt(piv), inv = 1.0 / rjj;
+        if (*s_fail) return false;                        // uniform
+        const int bnext = b0 + 2;
+        if (bnext >= nt4) break;
+        // (2) panel solve R12 = R11^-T A12: thread = one matrix column of the panel (tile column bj, column c)
+        {
+            double r11[8][8];                             // R11[p][r], p < r (broadcast reads)
+#pragma unroll
+            for (int p_ = 0; p_ < 8; ++p_)
+#pragma unroll
+                for (int r = p_ + 1; r < 8; ++r)
+                    r11[p_][r] = (p_ < 4) ? (r < 4 ? t00[4 * p_ + r] : t01[4 * p_ + (r - 4)]) : t11[4 * (p_ - 4) + (r - 4)];
+            double di[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) di[j] = s_dinv[j];
 #pragma unroll 1
-        for (int i = j + tid; i < n; i += nt) {
-            const double s = Rw[rj + (i - j)];
-            Rw[rj + (i - j)] = (i == j) ? rjj : s * inv;
+            for (int cc = tid; cc < 4 * (nt4 - bnext); cc += nthr) {
+                const int bj = bnext + (cc >> 2), c = cc & 3;
+                double *u0 = W + 16 * tidx(nt4, b0, bj) + c, *u1 = W + 16 * tidx(nt4, b0 + 1, bj) + c;
+                double xv[8];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) { xv[r] = u0[4 * r]; xv[4 + r] = u1[4 * r]; }
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    double sacc = xv[r];
+#pragma unroll
+                    for (int p_ = 0; p_ < r; ++p_) sacc = fma(-r11[p_][r], xv[p_], sacc);
+                    xv[r] = sacc * di[r];
+                }
+#pragma unroll
+                for (int r = 0; r < 4; ++r) { u0[4 * r] = xv[r]; u1[4 * r] = xv[4 + r]; }
+            }
+        }
+        __syncthreads();
+        // (3) trailing update: C(bi,bj) -= R12(:,bi)' R12(:,bj) for bnext <= bi <= bj
+#pragma unroll 1
+        for (int t = tidx(nt4, bnext, bnext) + tid; t < T; t += nthr) {
+            const int bi = tab[t] >> 8, bj = tab[t] & 0xff;
+            double ai[16], aj[16], c[16];
+            ld_tile(W + 16 * t, c);
+            ld_tile(W + 16 * tidx(nt4, b0, bi), ai);
+            ld_tile(W + 16 * tidx(nt4, b0, bj), aj);
+#pragma unroll
+            for (int p_ = 0; p_ < 4; ++p_)
+#pragma unroll
+                for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) c[4 * ii + jj] = fma(-ai[4 * p_ + ii], aj[4 * p_ + jj], c[4 * ii + jj]);
+            ld_tile(W + 16 * tidx(nt4, b0 + 1, bi), ai);
+            ld_tile(W + 16 * tidx(nt4, b0 + 1, bj), aj);
+#pragma unroll
+            for (int p_ = 0; p_ < 4; ++p_)
+#pragma unroll
+                for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) c[4 * ii + jj] = fma(-ai[4 * p_ + ii], aj[4 * p_ + jj], c[4 * ii + jj]);
+            st_tile(W + 16 * t, c);
         }
         __syncthreads();
     }
@@ -190,10 +316,11 @@ struct StepRes { double ssn, prin; int acc, fl, nev, noob; };
 // s2chain statistics over ALL rows (TranscriptionCycleMCMC.m:302-303), thread 0, shared memory
 struct S2Stats { double sum, sq_sum, cnt, pad; };      // sum s2, sum sqrt(s2), rows
 
-// Mutable chain state (uniform across the CTA): shared memory, thread 0 writes between barriers.
+// Mutable chain state (uniform across the CTA) in shared memory.  Written by thread 0 in the commit phase
+// (between the post-speculation barrier and the end-of-round barrier), read by everyone at the top of a round.
 struct ChainState {
     double ss, pri, sigma2, cov_n, wcnt;
-    int k, r_diag, bad0, pad;
+    int r_diag, bad0, run_r0, ndist;
     long long n_ss, n_acc1, n_acc2, n_oob, n_adapt, n_cholfail, n_dr, n_spec, rej, reju;
     long long pc[8], tprev;
 };
@@ -205,56 +332,46 @@ struct ChainCtx {
     unsigned long long uid;
     double adascale, inv_dr;
     SmemCell cv;
-    int o_x, o_U;                                       // offsets (doubles) of x and of the per-warp areas in tc_smem
+    int o_x, o_ring, o_U;                               // offsets (doubles) into tc_smem
     double *ring, *x, *lo, *hi, *mu, *pinv, *wmean, *wM2, *rdiag, *mb, *dm, *U;
-    double *gRb, *gM2, *gRows, *cmean;
-    __device__ __forceinline__ double *slot_d(int step) const { return ring + (size_t)(step % SPEC) * slot_sz; }
-    __device__ __forceinline__ double *slot_sc(int step) const { return ring + (size_t)(step % SPEC) * slot_sz + (slot_sz - 8); }
-    // warp wq's two proposals live behind its forward-model scratch (offset into tc_smem)
-    __device__ __forceinline__ int warp_y(int wq, int which) const
-    {
-        Work tmp;
-        int o = carve_work(o_U + wq * wsz, N, tmp);
-        o += o & 1;
-        return which ? o + npar + (npar & 1) : o;
-    }
+    double *gRb, *gM2, *gRows, *gWts, *cmean;
+    __device__ __forceinline__ int slot_o(int step) const { return o_ring + (step & (RING - 1)) * slot_sz; }
+    __device__ __forceinline__ double *slot_d(int step) const { return ring + (size_t)(step & (RING - 1)) * slot_sz; }
+    __device__ __forceinline__ double *slot_sc(int step) const { return ring + (size_t)(step & (RING - 1)) * slot_sz + (slot_sz - 8); }
 };
 
-// Book-keeping of `cnt` consecutive chain rows r0.. that all equal xs: summaries (Welford, m equal
-// values at once), optional chain storage, covariance block buffer.  Returns the new summary count.
-__device__ __noinline__ double emit_rows(const RunArgs &a, const ChainCtx &cx, int r0, int cnt, const double *xs, double wcnt)
+// The chain rows [r0, r1) all equal the current state x (a run: the accept at row r0, then rejections).
+// Fold the run into the summaries (Welford with multiplicity; rows >= n_burn-1 only), the optional chain
+// storage, and the distinct-row buffer of the current covariance block (row + weight); then, when
+// so >= 0, move the state: x += increment at tc_smem[so + 2 i].  Every thread owns the indices i = tid, tid+256, ..
+// so the whole thing is one pass.  The caller accounts for wcnt / ndist with the same formulas.
+__device__ __noinline__ void flush_run(const RunArgs &a, const ChainCtx &cx, int r0, int r1, double wcnt, int ndist, int so)
 {
     const int tid = threadIdx.x, npar = cx.npar;
-    const int rs = max(r0, cx.first_row), m = r0 + cnt - rs;          // rows that enter the summaries
-    if (m > 0) {
-        const double nn = wcnt + m, f1 = m / nn, f2 = wcnt * m / nn;
+    const int m_c = r1 - r0, rs = max(r0, cx.first_row), m_w = r1 - rs;
+    const bool cov = a.do_cov && m_c > 0;
+    const double nn = wcnt + m_w, f1 = m_w > 0 ? m_w / nn : 0.0, f2 = m_w > 0 ? wcnt * m_w / nn : 0.0;
+    double *grow = cov ? cx.gRows + (size_t)ndist * cx.ld : nullptr;
 #pragma unroll 1
-        for (int i = tid; i < npar; i += DRAM_THREADS) {
-            const double xi = xs[i], d1 = xi - cx.wmean[i];
+    for (int i = tid; i < npar; i += DRAM_THREADS) {
+        const double xo = cx.x[i];
+        if (m_w > 0) {
+            const double d1 = xo - cx.wmean[i];
             cx.wmean[i] = fma(d1, f1, cx.wmean[i]);
             cx.wM2[i] = fma(d1 * d1, f2, cx.wM2[i]);
-        }
-        wcnt = nn;
-        if (a.store_chain && a.chain) {
+            if (a.store_chain && a.chain) {
+                double *dst = a.chain + ((size_t)cx.ch * cx.nstore + (rs - cx.first_row)) * cx.ld + i;
 #pragma unroll 1
-            for (int r = rs; r < r0 + cnt; ++r) {
-                double *dst = a.chain + ((size_t)cx.ch * cx.nstore + (r - cx.first_row)) * cx.ld;
-#pragma unroll 1
-                for (int i = tid; i < npar; i += DRAM_THREADS) dst[i] = xs[i];
+                for (int r = 0; r < m_w; ++r) dst[(size_t)r * cx.ld] = xo;
             }
         }
-    }
-    if (a.do_cov) {
-#pragma unroll 1
-        for (int r = r0; r < r0 + cnt; ++r) {
-            double *dst = cx.gRows + (size_t)(r % a.adaptint) * cx.ld;
-#pragma unroll 1
-            for (int i = tid; i < npar; i += DRAM_THREADS) dst[i] = xs[i];
+        if (cov) {
+            grow[i] = xo;
+            cx.mb[i] = fma((double)m_c, xo, cx.mb[i]);
         }
-#pragma unroll 1
-        for (int i = tid; i < npar; i += DRAM_THREADS) cx.mb[i] = fma((double)cnt, xs[i], cx.mb[i]);
+        if (so >= 0) cx.x[i] = xo + tc_smem[so + 2 * i];
     }
-    return wcnt;
+    if (cov && tid == 0) cx.gWts[ndist] = (double)m_c;
 }
 
 // Per-row scalars of `cnt` committed rows r0.. by the lanes of warp 0 (one row per lane, cnt <= SPEC):
@@ -278,27 +395,30 @@ __device__ __noinline__ void emit_s2(const RunArgs &a, const ChainCtx &cx, S2Sta
     if (lane == 0) { st->sum += s2; st->sq_sum += sq; st->cnt += cnt; }
 }
 
-// Randomness and proposal increments for steps [g0, g0+nnew): Philox normals z1, z2 (interleaved in
-// the ring slot), u1, u2, chi2, the two norms entering q1, then the increments z1 R and z2 R/drscale
-// in place.  With a full factor, ALL ring slots go through one pass over R on the FP64 tensor cores
-// ([8 x npar] x [npar x npar] mma.sync m8n8k4; A rows = ring slots, old slots are not written back).
+// Randomness and proposal increments for steps [g0, g0+nnew), nnew <= GEN_M = 8 (one MMA row group).
+//   1. Philox normals z1, z2 -> scratch Z (the idle per-warp areas; row = step - g0, (z1, z2) interleaved per
+//      parameter); u1, u2, chi2 -> the scalars of the step's ring slot.
+//   2. the two norms entering q1, from z.
+//   3. increments z1 R and z2 R/drscale -> the ring slot.  With a full factor this is ONE pass over R on the
+//      FP64 tensor cores ([8 x npar] x [npar x npar] as mma.sync m8n8k4, A rows = the new steps).  Every
+//      element of R is needed exactly once per call, so the B fragments are loaded straight from HBM/L2,
+//      double-buffered GEN_UNR k-steps ahead of the MMAs, not staged in shared memory.
+#define GEN_M 8
+#define GEN_UNR 8
 __device__ __noinline__ void generate(const RunArgs &a, const ChainCtx &cx, int g0, int nnew, bool r_diag)
 {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, npar = cx.npar;
-    double *Rs = cx.U;
-    if (!r_diag) {
-        // stage R into shared memory (aliasing the per-warp areas) while the randomness is drawn
-        const unsigned sbase = (unsigned)__cvta_generic_to_shared(Rs);
-#pragma unroll 1
-        for (int c = tid; 2 * c < cx.npk; c += DRAM_THREADS)
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + 16u * c), "l"(cx.gRb + 2 * c) : "memory");
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    }
+    const int zs = 2 * cx.npad;                                   // doubles per row of Z
+    double *Z = cx.U;
+    SUBP_BEGIN;
+#ifdef TC_SUBPROF
+    if (tid == 0 && cx.ch == 0) { tc_subprof[26] += 1; tc_subprof[27] += nnew; }
+#endif
     if (a.replay) {
 #pragma unroll 1
         for (int sidx = 0; sidx < nnew; ++sidx) {
             const int st = g0 + sidx;
-            double *dz = cx.slot_d(st), *sc = cx.slot_sc(st);
+            double *dz = Z + (size_t)sidx * zs, *sc = cx.slot_sc(st);
             const size_t g = ((size_t)cx.ch * a.nsimu + st) * cx.ld;
 #pragma unroll 1
             for (int i = tid; i < npar; i += DRAM_THREADS) { dz[2 * i] = a.z1[g + i]; dz[2 * i + 1] = a.z2[g + i]; }
@@ -308,104 +428,119 @@ __device__ __noinline__ void generate(const RunArgs &a, const ChainCtx &cx, int 
             }
         }
     } else {
-        const int npairs = (npar + 1) >> 1, per = npairs + 1;    // work items per step: normal pairs (both stages) + (u, chi2)
+        // lane 0 of warp w: the uniforms and the chi-square of step g0 + w (one long serial draw per warp, all warps
+        // in parallel); then everybody: one work item = the 4 normals of a parameter pair
+        if (lane == 0 && warp < nnew) {
+            const int st = g0 + warp;
+            double *sc = cx.slot_sc(st);
+            const u32x4 ru = draw(a.seed, cx.uid, st, RK_U, 0);
+            sc[0] = u01(ru.x, ru.y);
+            sc[1] = u01(ru.z, ru.w);
+            sc[2] = a.updatesigma ? chi2_draw(a.seed, cx.uid, st, a.N0 + 2.0 * cx.N) : 1.0;
+        }
+        __syncwarp();
+        const int npairs = (npar + 1) >> 1;
 #pragma unroll 1
-        for (int it = tid; it < nnew * per; it += DRAM_THREADS) {
-            const int sidx = it / per, q2 = it - sidx * per, st = g0 + sidx;
-            double *dz = cx.slot_d(st), *sc = cx.slot_sc(st);
-            if (q2 == npairs) {
-                const u32x4 ru = draw(a.seed, cx.uid, st, RK_U, 0);
-                sc[0] = u01(ru.x, ru.y);
-                sc[1] = u01(ru.z, ru.w);
-                sc[2] = a.updatesigma ? chi2_draw(a.seed, cx.uid, st, a.N0 + 2.0 * cx.N) : 1.0;
-            } else {
-                // the stage-1 and stage-2 normals of parameters 2q, 2q+1: two independent Philox + Box-Muller
-                // chains in one body so that they overlap
-                double4 z = normal_quad(a.seed, cx.uid, st, q2);
-                *reinterpret_cast<double2 *>(dz + 4 * q2) = make_double2(z.x, z.z);          // (z1, z2) of parameter 2q
-                if (2 * q2 + 1 < npar) *reinterpret_cast<double2 *>(dz + 4 * q2 + 2) = make_double2(z.y, z.w);
-            }
+        for (int it = tid; it < nnew * npairs; it += DRAM_THREADS) {
+            const int sidx = it / npairs, q2 = it - sidx * npairs;
+            double *dz = Z + (size_t)sidx * zs;
+            const double4 z = normal_quad(a.seed, cx.uid, g0 + sidx, q2);
+            *reinterpret_cast<double2 *>(dz + 4 * q2) = make_double2(z.x, z.z);          // (z1, z2) of parameter 2q
+            if (2 * q2 + 1 < npar) *reinterpret_cast<double2 *>(dz + 4 * q2 + 2) = make_double2(z.y, z.w);
         }
     }
-    if (!r_diag) asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
-    // q1 = -1/2 (|(y1-y2) R^-1|^2 - |(y1-x) R^-1|^2) = -1/2 (|z1 - z2/drscale|^2 - |z1|^2): from z, before the
-    // increments overwrite it
+    SUBP(0);
+    // q1 = -1/2 (|(y1-y2) R^-1|^2 - |(y1-x) R^-1|^2) = -1/2 (|z1 - z2/drscale|^2 - |z1|^2)
     if (warp < nnew) {
-        const double *dz = cx.slot_d(g0 + warp);
+        const double2 *dz = reinterpret_cast<const double2 *>(Z + (size_t)warp * zs);
         double n1 = 0.0, n0 = 0.0;
 #pragma unroll 1
         for (int i = lane; i < npar; i += 32) {
-            const double za = dz[2 * i], d = za - dz[2 * i + 1] * cx.inv_dr;
+            const double2 zz = dz[i];
+            const double d = zz.x - zz.y * cx.inv_dr;
             n1 = fma(d, d, n1);
-            n0 = fma(za, za, n0);
+            n0 = fma(zz.x, zz.x, n0);
         }
         n1 = warp_sum(n1); n0 = warp_sum(n0);
         if (lane == 0) { double *sc = cx.slot_sc(g0 + warp); sc[3] = n1; sc[4] = n0; }
     }
+    SUBP(1);
     if (r_diag) {
-        __syncthreads();
 #pragma unroll 1
         for (int sidx = 0; sidx < nnew; ++sidx) {
-            double *dz = cx.slot_d(g0 + sidx);
+            const double2 *dz = reinterpret_cast<const double2 *>(Z + (size_t)sidx * zs);
+            double2 *out = reinterpret_cast<double2 *>(cx.slot_d(g0 + sidx));
 #pragma unroll 1
             for (int j = tid; j < npar; j += DRAM_THREADS) {
                 const double r = cx.rdiag[j];
-                dz[2 * j] *= r;
-                dz[2 * j + 1] *= r * cx.inv_dr;
+                const double2 zz = dz[j];
+                out[j] = make_double2(zz.x * r, zz.y * (r * cx.inv_dr));
             }
         }
     } else {
-        const int NT = (npar + 7) >> 3;
-        double r1[4][2], r2[4][2];
-        int rt[4];
-        int nres = 0;
-        const int ar = lane >> 2, ak = lane & 3;                 // A[row = slot][k], B[k][col]
-        const double *arow = cx.ring + (size_t)ar * cx.slot_sz;
+        const int NT = (npar + 7) >> 3;                              // column tiles of 8
+        const int ar = lane >> 2, ak = lane & 3;                     // A[row = step][k], B[k][col]
+        const double *arow = Z + (size_t)ar * zs;                    // rows >= nnew hold stale scratch: their results are dropped
+        double *orow = cx.slot_d(g0 + ar);
+        const double *gR = cx.gRb;
+        const double inv_dr = cx.inv_dr;
+        // tiles are dealt to the warps from the longest (last column tile: k-range = all rows) to the shortest
 #pragma unroll 1
-        for (int pp = warp; pp < (NT + 1) / 2 && nres < 3; pp += SPEC) {   // <= 4 tiles per warp: npar <= 256
+        for (int rnd = 0; rnd * SPEC < NT; ++rnd) {
+            const int nt = NT - 1 - (rnd * SPEC + ((rnd & 1) ? SPEC - 1 - warp : warp));          // serpentine: balances the triangle
+            if (nt < 0) continue;
+            const int j = 8 * nt + ar;                               // B column of this lane
+            const int kmax = min(8 * nt + 8, npar);                  // rows i < kmax can reach these columns
+            double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+            const int ks = (kmax + 3) >> 2;                          // k-steps of this tile
+            const bool jok = j < npar;
+            // rotating register pipeline: bb[u] holds R[i][j] for the k-step GEN_UNR ahead of the one being multiplied;
+            // the packed address of (i, j) advances by 4 npar - 4 i - 10 when i grows by 4
+            int il = ak, ic = ak;
+            const double *pl = gR + pidx(npar, ak, ak) + (j - ak);
+            double bb[GEN_UNR];
 #pragma unroll
-            for (int side = 0; side < 2; ++side) {
-                const int nt = side ? NT - 1 - pp : pp;
-                if (side && nt == pp) break;
-                const int n0c = 8 * nt, j = n0c + ar;          // B column of this lane
-                double c10 = 0, c11 = 0, c20 = 0, c21 = 0;
-                const int kmax = min(n0c + 8, npar);             // rows i < kmax can reach these columns
-#pragma unroll 2
-                for (int k0 = 0; k0 < kmax; k0 += 4) {
-                    const int i = k0 + ak;
-                    const double bv = (i <= j && j < npar) ? Rs[pidx(npar, i, j)] : 0.0;
-                    double2 az = make_double2(0.0, 0.0);
-                    if (i < npar) az = *reinterpret_cast<const double2 *>(arow + 2 * i);
-                    dmma_m8n8k4(c10, c11, az.x, bv);
-                    dmma_m8n8k4(c20, c21, az.y, bv);
+            for (int u = 0; u < GEN_UNR; ++u) {
+                bb[u] = (il <= j && jok) ? __ldcg(pl) : 0.0;
+                pl += 4 * npar - 4 * il - 10; il += 4;
+            }
+#pragma unroll 1
+            for (int kk = 0; kk < ks; kk += GEN_UNR) {
+#pragma unroll
+                for (int u = 0; u < GEN_UNR; ++u) {
+                    if (kk + u < ks) {                               // warp-uniform
+                        double2 za = make_double2(0.0, 0.0);
+                        if (ic < npar) za = *reinterpret_cast<const double2 *>(arow + 2 * ic);
+                        dmma_m8n8k4(acc0, acc1, za.x, bb[u]);
+                        dmma_m8n8k4(acc2, acc3, za.y, bb[u]);
+                        ic += 4;
+                        bb[u] = (il <= j && jok) ? __ldcg(pl) : 0.0;
+                        pl += 4 * npar - 4 * il - 10; il += 4;
+                    }
                 }
-                r1[nres][0] = c10; r1[nres][1] = c11; r2[nres][0] = c20; r2[nres][1] = c21; rt[nres] = nt;
-                ++nres;
+            }
+            const int jc = 8 * nt + 2 * ak;
+            if (ar < nnew) {
+                if (jc < npar) { orow[2 * jc] = acc0; orow[2 * jc + 1] = acc2 * inv_dr; }
+                if (jc + 1 < npar) { orow[2 * jc + 2] = acc1; orow[2 * jc + 3] = acc3 * inv_dr; }
             }
         }
-        __syncthreads();                                         // everyone is done reading z
-        const bool is_new = ((ar - g0) % SPEC + SPEC) % SPEC < nnew;   // slot ar holds a new step?
-        double *orow = cx.ring + (size_t)ar * cx.slot_sz;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            if (q < nres && is_new) {
-                const int jc = 8 * rt[q] + 2 * ak;
-                if (jc < npar) { orow[2 * jc] = r1[q][0]; orow[2 * jc + 1] = r2[q][0] * cx.inv_dr; }
-                if (jc + 1 < npar) { orow[2 * jc + 2] = r1[q][1]; orow[2 * jc + 3] = r2[q][1] * cx.inv_dr; }
-            }
-        }
+        SUBP(2);
     }
     __syncthreads();
+    SUBP(3);
 }
 
 // One DRAM step (both proposal stages) by ONE warp for step `st`, from state x with (ss, pri), seeing
-// sigma2 = s2p.  Result in *res.   mcmcstat DRAM: SURVEY.md 3.2.
+// sigma2 = s2p.  The proposals are never materialised: theta = x + ring increment (SumVec), the very
+// expression the commit phase uses to move the state.  Result in *res.   mcmcstat DRAM: SURVEY.md 3.2.
 __device__ __noinline__ void dram_step_warp(const RunArgs &a, const ChainCtx &cx, int st, double ss, double pri, double s2p,
-                                            Work w, int y1, int y2, StepRes *res)
+                                            Work w, StepRes *res)
 {
     const int lane = threadIdx.x & 31, npar = cx.npar;
-    const double2 *dd = reinterpret_cast<const double2 *>(cx.slot_d(st));
+    const int so = cx.slot_o(st);
+    const double2 *dd = reinterpret_cast<const double2 *>(tc_smem + so);
     const double *sc = cx.slot_sc(st);
     double pr1 = 0.0, pr2 = 0.0;
     unsigned oob = 0;
@@ -413,8 +548,6 @@ __device__ __noinline__ void dram_step_warp(const RunArgs &a, const ChainCtx &cx
     for (int j = lane; j < npar; j += 32) {
         const double2 dj = dd[j];
         const double xj = cx.x[j], a1 = xj + dj.x, a2 = xj + dj.y;
-        tc_smem[y1 + j] = a1;
-        tc_smem[y2 + j] = a2;
         const double lo = cx.lo[j], hi = cx.hi[j];
         if (a1 < lo || a1 > hi) oob |= 1u;
         if (a2 < lo || a2 > hi) oob |= 2u;
@@ -424,13 +557,12 @@ __device__ __noinline__ void dram_step_warp(const RunArgs &a, const ChainCtx &cx
     }
     pr1 = warp_sum(pr1); pr2 = warp_sum(pr2);
     oob = __reduce_or_sync(0xffffffffu, oob);
-    __syncwarp();
     int fl = 0, accept = 0, nev = 0, noob = 0;
     double ss1, a12;
     if (oob & 1u) {
         ss1 = INFINITY; pr1 = 0.0; a12 = 0.0; fl |= TC_FL_OOB1; ++noob;
     } else {
-        ss1 = ss_eval(a.cons, cx.cv, SmemVec{y1}, w, a.algo, false, nullptr, nullptr);
+        ss1 = ss_eval(a.cons, cx.cv, SumVec{cx.o_x, so}, w, a.algo, false, nullptr, nullptr);
         ++nev;
         a12 = tc_exp(-0.5 * ((ss1 - ss) / s2p + pr1 - pri));
         if (a12 <= 0.0) accept = 0;
@@ -443,7 +575,7 @@ __device__ __noinline__ void dram_step_warp(const RunArgs &a, const ChainCtx &cx
         if (oob & 2u) {
             fl |= TC_FL_OOB2; ++noob;
         } else {
-            const double ss2 = ss_eval(a.cons, cx.cv, SmemVec{y2}, w, a.algo, false, nullptr, nullptr);
+            const double ss2 = ss_eval(a.cons, cx.cv, SumVec{cx.o_x, so + 1}, w, a.algo, false, nullptr, nullptr);
             ++nev;
             double a32 = tc_exp(-0.5 * ((ss1 - ss2) / s2p + pr1 - pr2));
             a32 = a32 > 1.0 ? 1.0 : a32;
@@ -459,23 +591,30 @@ __device__ __noinline__ void dram_step_warp(const RunArgs &a, const ChainCtx &cx
     if (lane == 0) { res->acc = accept; res->fl = fl; res->nev = nev; res->noob = noob; res->ssn = ssn; res->prin = prin; }
 }
 
-// Adaptation after the step with isimu (a multiple of adaptint): fold the last adaptint rows into the
-// running covariance (Chan's block update, 4x4 register tiles), then either burn-in scaling or
+// Adaptation after the step with isimu (a multiple of adaptint).  The block of the last adaptint chain rows
+// arrives as `ndist` DISTINCT rows with integer weights (a rejected step repeats the previous row): the
+// scatter of the block is sum_d w_d (x_d - mb)(x_d - mb)', folded into the running scatter matrix with
+// Chan's mean-shift term as one more weighted row, in 4x4 register tiles.  Then either burn-in scaling or
 // R = chol(cov + qcovadj I) * adascale.  Returns 0: R unchanged / scaled, 1: new full factor, 2: Cholesky failed.
 __device__ __noinline__ int adapt(const RunArgs &a, const ChainCtx &cx, int isimu, double cov_n, double rate, bool r_diag,
-                                  double *s_piv)
+                                  int ndist, double *s_dinv, int *s_flag)
 {
     const int tid = threadIdx.x, npar = cx.npar, npad = cx.npad, ld = cx.ld, npk = cx.npk;
-    double *chunk = cx.U, *Rs = cx.U;
+    double *chunk = cx.ring;                           // workspace: ring + per-warp areas (idle now)
+    double *sw = cx.ring + COV_RC * npad;                             // sqrt(weight) per row
+    SUBP_BEGIN;
     if (a.do_cov) {
         const int m = a.adaptint;
+        const double fcorr = cov_n * m / (cov_n + m);
+        const int nrows = ndist + (cov_n > 0.0 ? 1 : 0);              // + the mean-shift row
 #pragma unroll 1
         for (int i = tid; i < npar; i += DRAM_THREADS) {
             const double mbi = cx.mb[i] / m;
             cx.mb[i] = mbi;
             cx.dm[i] = mbi - __ldcg(cx.cmean + i);
         }
-        const double fcorr = cov_n * m / (cov_n + m);
+#pragma unroll 1
+        for (int r = tid; r < nrows; r += DRAM_THREADS) sw[r] = r < ndist ? sqrt(__ldcg(cx.gWts + r)) : sqrt(fcorr);
         const int ntile = (npar + 3) >> 2, T = ntile * (ntile + 1) / 2;
 #pragma unroll 1
         for (int base = 0; base < T; base += COV_TPT * DRAM_THREADS) {
@@ -493,14 +632,24 @@ __device__ __noinline__ int adapt(const RunArgs &a, const ChainCtx &cx, int isim
                 for (int e = 0; e < 16; ++e) acc[u][e] = 0.0;
             }
 #pragma unroll 1
-            for (int r0 = 0; r0 < m; r0 += COV_RC) {
-                const int rc = min(COV_RC, m - r0);
+            for (int r0 = 0; r0 < nrows; r0 += COV_RC) {
+                const int rc = min(COV_RC, nrows - r0);
                 __syncthreads();
 #pragma unroll 1
-                for (int r = 0; r < rc; ++r)
-#pragma unroll 1
-                    for (int c = tid; c < npad; c += DRAM_THREADS)
-                        chunk[r * npad + c] = c < npar ? __ldcg(cx.gRows + (size_t)(r0 + r) * ld + c) - cx.mb[c] : 0.0;
+                for (int c = tid; c < npad; c += DRAM_THREADS) {
+                    double v[COV_RC];
+#pragma unroll
+                    for (int r = 0; r < COV_RC; ++r) {                // independent loads in flight
+                        const int rr = r0 + r;
+                        v[r] = (c < npar && rr < ndist) ? __ldcg(cx.gRows + (size_t)rr * ld + c) : 0.0;
+                    }
+                    const double mbc = c < npar ? cx.mb[c] : 0.0, dmc = c < npar ? cx.dm[c] : 0.0;
+#pragma unroll
+                    for (int r = 0; r < COV_RC; ++r) {
+                        const int rr = r0 + r;
+                        if (r < rc) chunk[r * npad + c] = c < npar ? sw[rr] * (rr < ndist ? v[r] - mbc : dmc) : 0.0;
+                    }
+                }
                 __syncthreads();
 #pragma unroll
                 for (int u = 0; u < COV_TPT; ++u) {
@@ -518,6 +667,7 @@ __device__ __noinline__ int adapt(const RunArgs &a, const ChainCtx &cx, int isim
                     }
                 }
             }
+            SUBP(8);
 #pragma unroll
             for (int u = 0; u < COV_TPT; ++u) {
                 if (!on[u]) continue;
@@ -534,8 +684,7 @@ __device__ __noinline__ int adapt(const RunArgs &a, const ChainCtx &cx, int isim
 #pragma unroll
                     for (int jj = 0; jj < 4; ++jj) {
                         const int pp = 4 * bi[u] + ii, qq = 4 * bj[u] + jj;
-                        if (pp <= qq && qq < npar)
-                            cx.gM2[pidx(npar, pp, qq)] = old[4 * ii + jj] + acc[u][4 * ii + jj] + fcorr * cx.dm[pp] * cx.dm[qq];
+                        if (pp <= qq && qq < npar) cx.gM2[pidx(npar, pp, qq)] = old[4 * ii + jj] + acc[u][4 * ii + jj];
                     }
             }
         }
@@ -544,6 +693,7 @@ __device__ __noinline__ int adapt(const RunArgs &a, const ChainCtx &cx, int isim
         for (int i = tid; i < npar; i += DRAM_THREADS) { cx.cmean[i] = __ldcg(cx.cmean + i) + cx.dm[i] * (m / (cov_n + m)); cx.mb[i] = 0.0; }
         cov_n += m;
         __syncthreads();
+        SUBP(9);
     }
     int ret = 0;
     if (isimu < a.burnintime) {
@@ -560,39 +710,63 @@ __device__ __noinline__ int adapt(const RunArgs &a, const ChainCtx &cx, int isim
             }
         }
     } else {
-        // R = chol(cov + qcovadj I) * adascale, factorised in shared memory, kept in HBM/L2
+        // R = chol(cov + qcovadj I) * adascale, factorised in shared memory (tiled layout), kept in HBM/L2
         const double invn = 1.0 / (cov_n - 1.0);
+        const int nt4 = (npar + 3) >> 2, T4 = nt4 * (nt4 + 1) / 2;
+        double *W = cx.ring;
+        unsigned short *tab = reinterpret_cast<unsigned short *>(W + 16 * T4);
 #pragma unroll 1
-        for (int i = tid; i < npk; i += DRAM_THREADS) Rs[i] = __ldcg(cx.gM2 + i) * invn;
+        for (int t = tid; t < T4; t += DRAM_THREADS) {
+            int rem = t, b = 0;
+            while (rem >= nt4 - b) { rem -= nt4 - b; ++b; }
+            tab[t] = (unsigned short)((b << 8) | (b + rem));
+        }
         __syncthreads();
-#pragma unroll 1
-        for (int i = tid; i < npar; i += DRAM_THREADS) Rs[pidx(npar, i, i)] += a.qcovadj;
+#pragma unroll 4
+        for (int e = tid; e < 16 * T4; e += DRAM_THREADS) {
+            const int t = e >> 4, r = (e >> 2) & 3, c = e & 3;
+            const int row = 4 * (tab[t] >> 8) + r, col = 4 * (tab[t] & 0xff) + c;
+            double v = (row == col) ? 1.0 : 0.0;                     // identity padding; lower parts of diagonal tiles are never read
+            if (row <= col && col < npar) v = __ldcg(cx.gM2 + pidx(npar, row, col)) * invn + (row == col ? a.qcovadj : 0.0);
+            W[e] = v;
+        }
         __syncthreads();
-        const bool ok = chol_packed(npar, Rs, s_piv);
+        SUBP(10);
+        const bool ok = chol_tiled(nt4, W, tab, s_dinv, s_flag);
         __syncthreads();
+        SUBP(11);
         if (ok) {
-#pragma unroll 1
-            for (int i = tid; i < npk; i += DRAM_THREADS) cx.gRb[i] = Rs[i] * cx.adascale;
+#pragma unroll 4
+            for (int e = tid; e < 16 * T4; e += DRAM_THREADS) {
+                const int t = e >> 4, r = (e >> 2) & 3, c = e & 3;
+                const int row = 4 * (tab[t] >> 8) + r, col = 4 * (tab[t] & 0xff) + c;
+                if (row <= col && col < npar) cx.gRb[pidx(npar, row, col)] = W[e] * cx.adascale;
+            }
             ret = 1;
         } else {
             ret = 2;                                                // R unchanged
         }
     }
     __syncthreads();
+    SUBP(12);
     return ret;
 }
 
-// The device-resident DRAM sampler: one CTA per chain, SPEC future steps per batch.
+// The device-resident DRAM sampler: one CTA per chain slice, SPEC future steps per round.
 //
 // DRAM is sequential, but a step that rejects leaves the state untouched, and at the acceptance
-// rates of this model (8-30 %) most do.  So the CTA simulates the next SPEC steps AT ONCE, warp w
+// rates of this model (3-30 %) most do.  So the CTA simulates the next SPEC steps AT ONCE, warp w
 // running step k+w in full (both proposal stages, forward model, accept/reject) under the
-// hypothesis "nothing before me accepted"; the batch is then cut after the first step that did
+// hypothesis "nothing before me accepted"; the round is then cut after the first step that did
 // accept, that prefix is committed, and the later warps' work is discarded.  The chain produced is
 // exactly the sequential one (same Philox draws per step; the replay tests compare it flag by flag
 // with the CPU oracle).  The randomness and the proposal increments z R do not depend on the state,
-// so they are generated once per step, ahead of use, into a ring of SPEC slots.
-// Saved state of a chain between two time slices (doubles): see dram_kernel.
+// so they are generated ahead of use, up to RING steps per call, into a ring of RING slots.
+// Book-keeping works on RUNS (an accepted state and the rejections that follow it): a rejected step
+// only lengthens the current run; summaries, chain storage and the covariance block see a run once,
+// with its length as weight.
+//
+// Saved state of a chain between two time slices (doubles):
 //   [0..15] scalars | [16..47] counters (long long) | x | wmean | wM2 | rdiag
 #define ST_VEC0 48         // first vector: 16 scalars + up to 32 counters (17 used: 9 counts + 8 phase clocks)
 __host__ __device__ inline int state_doubles(int ld) { return ST_VEC0 + 4 * ld; }
@@ -612,27 +786,29 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
     __shared__ StepRes s_res[SPEC];
     __shared__ ChainCtx cx;
     __shared__ S2Stats s_s2;
-    __shared__ double s_sc[4];
-    __shared__ int s_item, s_done, s_min;
+    __shared__ double s_dinv[8];
+    __shared__ int s_flag;
+    __shared__ int s_item, s_done;
+    __shared__ unsigned s_min;
     __shared__ ChainState st;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-    // Persistent CTAs time-slice the chains: a free CTA claims ANY chain that is not running and still
-    // has slices left (a.cstate[c] = next slice, bit 30 = running), runs one slice and releases it.
-    // So any number of chains shares the resident CTAs evenly (299 chains on 296 CTA slots would
-    // otherwise cost two full waves), and nobody ever waits for a particular chain.  A slice ends on
-    // an adaptation boundary, where the ring is empty and the factor R / covariance already live in
-    // HBM; the rest of the chain state is a few vectors.
+    // Persistent CTAs time-slice the chains: a free CTA claims a chain that is not running and still
+    // has slices left (a.cstate[c] = next slice, bit 30 = running) — the one that is furthest behind,
+    // so that all chains finish together — runs one slice and releases it.  So any number of chains
+    // shares the resident CTAs evenly (299 chains on 296 CTA slots would otherwise cost two full
+    // waves).  A slice ends on an adaptation boundary, where the ring is empty, the current run is
+    // closed and the factor R / covariance already live in HBM; the rest of the chain state is a few vectors.
     const int LOCK = 1 << 30;
     const int nseg = (a.nsimu + a.seglen - 1) / a.seglen;
     int start = (int)(((long long)blockIdx.x * a.nchains) / gridDim.x);
 #pragma unroll 1
     for (;;) {
-        // claim a chain: the whole CTA scans the state words in parallel, thread 0 takes the first free one
+        // claim a chain: the whole CTA scans the state words in parallel; key = (slices done, distance from `start`)
 #pragma unroll 1
         for (;;) {
             __syncthreads();
-            if (tid == 0) s_min = 0x7fffffff;
+            if (tid == 0) s_min = 0xffffffffu;
             __syncthreads();
             int pending = 0;
 #pragma unroll 1
@@ -642,19 +818,19 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
                 if (i < a.nchains) {
                     const int v = *reinterpret_cast<volatile int *>(a.cstate + (start + i) % a.nchains);
                     if (v & LOCK) pending = 1;
-                    else if (v < nseg) { hit = 1; atomicMin(&s_min, i); }
+                    else if (v < nseg) { hit = 1; atomicMin(&s_min, ((unsigned)v << 24) | (unsigned)min(i, 0xffffff)); }
                 }
-                if (__syncthreads_or(hit)) break;
+                if (__syncthreads_or(hit) && nseg == 1) break;           // unsliced: any free chain will do
             }
             pending = __syncthreads_or(pending);
-            const int imin = s_min;
-            if (imin == 0x7fffffff) {
+            const unsigned kmin = s_min;
+            if (kmin == 0xffffffffu) {
                 if (!pending) { if (tid == 0) s_item = -1; break; }     // every chain is finished
                 __nanosleep(2000);
                 continue;
             }
             if (tid == 0) {
-                const int c = (start + imin) % a.nchains;
+                const int c = (start + (int)(kmin & 0xffffffu)) % a.nchains;
                 const int v = *reinterpret_cast<volatile int *>(a.cstate + c);
                 const bool ok = !(v & LOCK) && v < nseg && atomicCAS(a.cstate + c, v, v | LOCK) == v;
                 s_item = ok ? c : -2;
@@ -688,27 +864,28 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
                 cx.adascale = a.adascale > 0.0 ? a.adascale : 2.4 / sqrt((double)npar);
                 cx.inv_dr = 1.0 / a.drscale;
                 cx.cv = cv; cx.cv.d = a.cells.dmean[cid];
-                cx.ring = tc_smem + o; o += SPEC * dram_slot(N);
                 cx.o_x = o;
                 cx.x = tc_smem + o; o += npar;     cx.lo = tc_smem + o; o += npar;    cx.hi = tc_smem + o; o += npar;
                 cx.mu = tc_smem + o; o += npar;    cx.pinv = tc_smem + o; o += npar;  cx.wmean = tc_smem + o; o += npar;
                 cx.wM2 = tc_smem + o; o += npar;   cx.rdiag = tc_smem + o; o += npar; cx.mb = tc_smem + o; o += npar;
                 cx.dm = tc_smem + o; o += npar;
                 o += o & 1;
+                cx.o_ring = o;
+                cx.ring = tc_smem + o; o += RING * dram_slot(N);
                 cx.o_U = o;
                 cx.U = tc_smem + o;
                 cx.gRb = a.gR + (size_t)ch * a.ldR;                 // the factor R lives in HBM/L2 (packed upper)
                 cx.gM2 = a.gM2 ? a.gM2 + (size_t)ch * a.ldR : nullptr;
                 cx.gRows = a.gRows ? a.gRows + (size_t)ch * (size_t)a.adaptint * a.ld : nullptr;
+                cx.gWts = a.gWts ? a.gWts + (size_t)ch * (size_t)a.adaptint : nullptr;
                 cx.cmean = a.gCmean ? a.gCmean + (size_t)ch * a.ld : nullptr;
             }
             load_cell(a.cells, cid, false, cv);
         }
         __syncthreads();
-        // this warp's private area: forward-model scratch + its two proposals
+        // this warp's private forward-model scratch
         Work w;
         carve_work(cx.o_U + warp * cx.wsz, N, w);
-        const int y1 = cx.warp_y(warp, 0), y2 = cx.warp_y(warp, 1);
 #pragma unroll 1
         for (int i = tid; i < npar; i += DRAM_THREADS) {
             const size_t g = (size_t)ch * a.ld + i;
@@ -731,15 +908,16 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
                 cx.rdiag[i] = __ldcg(gst + ST_VEC0 + 3 * a.ld + i);
             }
         }
-        if (seg == 0 && a.do_cov) {
+        if (seg == 0) {
+            if (a.do_cov) {
 #pragma unroll 1
-            for (int i = tid; i < cx.npk; i += DRAM_THREADS) cx.gM2[i] = 0.0;
+                for (int i = tid; i < cx.npk; i += DRAM_THREADS) cx.gM2[i] = 0.0;
+            }
+            // ring slot 0 = zero increments: row 0 evaluates ss(x0) through the same theta view as every step
+#pragma unroll 1
+            for (int i = tid; i < cx.slot_sz; i += DRAM_THREADS) cx.ring[i] = 0.0;
         }
 
-        // ---- chain state: lives in shared memory (st), written by thread 0 between barriers, so that
-        //      almost nothing is live in registers across the out-of-line phase calls (register
-        //      spills go to local memory, and with ~220 KB of the SM carved out as shared memory there
-        //      is practically no L1 left to catch them)
         if (tid == 0) {
             if (seg == 0) {
                 st.ss = 0.0; st.pri = 0.0; st.sigma2 = a.sigma2_0; st.cov_n = 0.0; st.wcnt = 0.0; st.r_diag = 1; st.bad0 = 0;
@@ -747,7 +925,7 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
                 st.rej = 0; st.reju = 0;
                 for (int i = 0; i < 8; ++i) st.pc[i] = 0;
                 s_s2.sum = 0.0; s_s2.sq_sum = 0.0; s_s2.cnt = 0.0;
-                st.k = 1;
+                st.run_r0 = 0;
             } else {
                 st.ss = __ldcg(gst + 0); st.pri = __ldcg(gst + 1); st.sigma2 = __ldcg(gst + 2); st.cov_n = __ldcg(gst + 3);
                 st.wcnt = __ldcg(gst + 4); st.r_diag = __ldcg(gst + 5) != 0.0; st.bad0 = 0;
@@ -757,109 +935,120 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
                 st.n_adapt = __ldcg(gc + 4); st.n_cholfail = __ldcg(gc + 5); st.n_dr = __ldcg(gc + 6); st.n_spec = __ldcg(gc + 7);
                 st.rej = __ldcg(gc + 8); st.reju = 0;
                 for (int i = 0; i < 8; ++i) st.pc[i] = __ldcg(gc + 9 + i);
-                st.k = seg * a.seglen;
+                st.run_r0 = seg * a.seglen;
             }
+            st.ndist = 0;
             st.tprev = clock64();
         }
         __syncthreads();
 #define TC_PHASE(i) do { if (tid == 0) { const long long tn__ = clock64(); st.pc[i] += tn__ - st.tprev; st.tprev = tn__; } } while (0)
 
         if (seg == 0) {
-            // ---- row 0: x0
-            const double ss0 = ss_eval(a.cons, cx.cv, SmemVec{cx.o_x}, w, a.algo, false, nullptr, nullptr);   // every warp, same value
+            // ---- row 0: x0 (opens the first run)
+            const double ss0 = ss_eval(a.cons, cx.cv, SumVec{cx.o_x, cx.o_ring}, w, a.algo, false, nullptr, nullptr);   // every warp, same value
             double sp = 0.0;
 #pragma unroll 1
             for (int i = lane; i < npar; i += 32) { const double e = (cx.x[i] - cx.mu[i]) * cx.pinv[i]; sp += e * e; }
             sp = warp_sum(sp);
             const bool bad = !isfinite(ss0);
             if (tid == 0) { st.ss = ss0; st.pri = sp; st.bad0 = bad ? 1 : 0; }
-            __syncthreads();
-            if (!bad) {
-                const double wc = emit_rows(a, cx, 0, 1, cx.x, 0.0);
-                if (tid == 0) st.wcnt = wc;
-                if (warp == 0) emit_s2(a, cx, &s_s2, nullptr, 0, 1, 1, ss0, ss0, a.sigma2_0);
-            }
+            if (!bad && warp == 0) emit_s2(a, cx, &s_s2, nullptr, 0, 1, 1, ss0, ss0, a.sigma2_0);
             __syncthreads();
         }
 
-        int k = st.k;              // next step to decide
-        int gen_upto = k;          // increments are ready for steps [k, gen_upto)
+        int k = seg == 0 ? 1 : seg * a.seglen;      // next step to decide
+        int gen_upto = k;                           // increments are ready for steps [k, gen_upto)
         const bool bad0 = st.bad0 != 0;
 #pragma unroll 1
         while (k < k_end && !bad0) {
-            // the batch never crosses an adaptation: the step whose isimu = st+1 is a multiple of adaptint
+            // the round never crosses an adaptation: the step whose isimu = st+1 is a multiple of adaptint
             // is the last one that may use the current R
-            int lim = min(k + SPEC, k_end);
-            if (a.adaptint > 0) lim = min(lim, ((k + a.adaptint) / a.adaptint) * a.adaptint);   // exclusive step bound
+            int bound = k_end;
+            if (a.adaptint > 0) bound = min(bound, ((k + a.adaptint) / a.adaptint) * a.adaptint);   // exclusive step bound
+            const int lim = min(k + SPEC, bound);
             const int nb = lim - k;
+            // chain state of this round (thread 0 rewrites st only after the post-speculation barrier)
+            const double ss = st.ss, pri = st.pri, sig2 = st.sigma2, wcnt = st.wcnt;
+            const int run_r0 = st.run_r0, ndist = st.ndist;
 
-            if (gen_upto < lim) { generate(a, cx, gen_upto, lim - gen_upto, st.r_diag != 0); gen_upto = lim; }
+            if (gen_upto < lim) {
+                // fewer than a round's worth of steps ready => at least GEN_M ring slots are free
+                const int glim = min(gen_upto + GEN_M, bound);
+                generate(a, cx, gen_upto, glim - gen_upto, st.r_diag != 0);
+                gen_upto = glim;
+            }
             TC_PHASE(0);
 
             // speculation: warp w runs step k+w assuming steps k..k+w-1 rejected; the sigma2 it sees is the
             // draw made at the end of step k+w-1 from the (unchanged) ss
             if (warp < nb) {
-                const double ss = st.ss;
-                double s2p = st.sigma2;
+                double s2p = sig2;
                 if (warp > 0 && a.updatesigma) s2p = (a.N0 * a.S20 + ss) / cx.slot_sc(k + warp - 1)[2];
-                dram_step_warp(a, cx, k + warp, ss, st.pri, s2p, w, y1, y2, &s_res[warp]);
+                dram_step_warp(a, cx, k + warp, ss, pri, s2p, w, &s_res[warp]);
             }
             __syncthreads();
             TC_PHASE(1);
 
-            // resolve: commit up to and including the first accepting step
+            // commit up to and including the first accepting step
             int first = nb;
 #pragma unroll 1
             for (int q = nb - 1; q >= 0; --q) if (s_res[q].acc) first = q;
-            const int ncommit = first < nb ? first + 1 : nb;
-            const int nrej = first < nb ? first : nb;                     // leading rejected steps: rows equal x
-            const double ss_old = st.ss;
-            double wc = st.wcnt;
-            if (nrej > 0) wc = emit_rows(a, cx, k, nrej, cx.x, wc);
-            TC_PHASE(2);
-            if (first < nb) {
-                // the accepting warp's proposal becomes the state
-                const double *ya = tc_smem + cx.warp_y(first, s_res[first].acc == 2 ? 1 : 0);
-                __syncthreads();
-#pragma unroll 1
-                for (int i = tid; i < npar; i += DRAM_THREADS) cx.x[i] = ya[i];
-                __syncthreads();
-                wc = emit_rows(a, cx, k + first, 1, cx.x, wc);
+            const bool accd = first < nb;
+            const int ncommit = accd ? first + 1 : nb;
+            const int r_acc = k + first;                                    // row of the accept
+            if (accd) {
+                // close the run of the old state at row r_acc and move x by the accepting warp's increment
+                const int so = cx.slot_o(r_acc) + (s_res[first].acc == 2 ? 1 : 0);
+                flush_run(a, cx, run_r0, r_acc, wcnt, ndist, so);
             }
-            const double ss_new = first < nb ? s_res[first].ssn : ss_old;
-            TC_PHASE(3);
-            if (warp == 0) emit_s2(a, cx, &s_s2, s_res, k, ncommit, first, ss_old, ss_new, st.sigma2);
-            __syncthreads();                                           // everyone has read st / s_res
-            if (tid == 0) {
-                int d_ss = 0, d_oob = 0, d_dr = 0, d_spec = 0;
+            if (warp == 0) {
+                const double ss_new = accd ? s_res[first].ssn : ss;
+                emit_s2(a, cx, &s_s2, s_res, k, ncommit, first, ss, ss_new, sig2);
+                if (lane == 0) {
+                    int d_ss = 0, d_oob = 0, d_dr = 0, d_spec = 0;
 #pragma unroll
-                for (int q = 0; q < SPEC; ++q) {
-                    if (q < nb) {
-                        const int nev = s_res[q].nev;
-                        d_spec += nev;
-                        if (q < ncommit) { d_ss += nev; d_oob += s_res[q].noob; d_dr += (s_res[q].fl & TC_FL_DR) ? 1 : 0; }
+                    for (int q = 0; q < SPEC; ++q) {
+                        if (q < nb) {
+                            const int nev = s_res[q].nev;
+                            d_spec += nev;
+                            if (q < ncommit) { d_ss += nev; d_oob += s_res[q].noob; d_dr += (s_res[q].fl & TC_FL_DR) ? 1 : 0; }
+                        }
                     }
+                    const int nrej = accd ? first : nb;
+                    st.n_ss += d_ss; st.n_oob += d_oob; st.n_dr += d_dr; st.n_spec += d_spec;
+                    st.rej += nrej; st.reju += nrej;
+                    if (accd) {
+                        st.ss = ss_new; st.pri = s_res[first].prin;
+                        if (s_res[first].acc == 1) ++st.n_acc1; else ++st.n_acc2;
+                        st.wcnt = wcnt + max(0, r_acc - max(run_r0, cx.first_row));
+                        if (a.do_cov && r_acc > run_r0) st.ndist = ndist + 1;
+                        st.run_r0 = r_acc;
+                    }
+                    if (a.updatesigma) st.sigma2 = (a.N0 * a.S20 + ss_new) / cx.slot_sc(k + ncommit - 1)[2];
                 }
-                st.n_ss += d_ss; st.n_oob += d_oob; st.n_dr += d_dr; st.n_spec += d_spec;
-                st.rej += nrej; st.reju += nrej;
-                st.wcnt = wc;
-                if (first < nb) {
-                    st.ss = ss_new; st.pri = s_res[first].prin;
-                    if (s_res[first].acc == 1) ++st.n_acc1; else ++st.n_acc2;
-                }
-                if (a.updatesigma) st.sigma2 = (a.N0 * a.S20 + ss_new) / cx.slot_sc(k + ncommit - 1)[2];
             }
             k += ncommit;
             __syncthreads();
-            TC_PHASE(4);
+#ifdef TC_SUBPROF
+            if (tid == 0 && cx.ch == 0) { tc_subprof[24] += 1; tc_subprof[25] += ncommit; }
+#endif
+            TC_PHASE(2);
 
             // adaptation after the step with isimu = k, a multiple of adaptint
             if (a.adaptint > 0 && k % a.adaptint == 0) {
+                const int rr0 = st.run_r0, nd0 = st.ndist;
+                const double wc0 = st.wcnt;
+                flush_run(a, cx, rr0, k, wc0, nd0, -1);                     // close the run at the block boundary
+                const int nd = nd0 + ((a.do_cov && k > rr0) ? 1 : 0);
                 const double rate = a.burnin_cumulative ? (double)st.rej / k : (double)st.reju / a.adaptint;
-                const int rc = adapt(a, cx, k, st.cov_n, rate, st.r_diag != 0, &s_sc[0]);
+                const double cov_n = st.cov_n;
+                const bool rdg = st.r_diag != 0;
                 __syncthreads();
+                const int rc = adapt(a, cx, k, cov_n, rate, rdg, nd, s_dinv, &s_flag);
                 if (tid == 0) {
-                    if (a.do_cov) st.cov_n += a.adaptint;
+                    st.wcnt = wc0 + max(0, k - max(rr0, cx.first_row));
+                    st.run_r0 = k; st.ndist = 0;
+                    if (a.do_cov) st.cov_n = cov_n + a.adaptint;
                     if (rc == 1) { st.r_diag = 0; ++st.n_adapt; }
                     else if (rc == 2) ++st.n_cholfail;
                     st.reju = 0;
@@ -870,6 +1059,15 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
         }
 
         __syncthreads();
+        if (!bad0 && st.run_r0 < k) {
+            // close the last run (the fit or the slice does not end on an adaptation boundary)
+            const int rr0 = st.run_r0;
+            const double wc0 = st.wcnt;
+            flush_run(a, cx, rr0, k, wc0, st.ndist, -1);
+            __syncthreads();
+            if (tid == 0) { st.wcnt = wc0 + max(0, k - max(rr0, cx.first_row)); st.run_r0 = k; }
+            __syncthreads();
+        }
         if (!last_seg && !bad0) {
             // ---- park the chain: the next slice may run on any CTA
 #pragma unroll 1
@@ -929,13 +1127,10 @@ __global__ void rng_dump_kernel(unsigned long long seed, unsigned long long uid,
 {
     for (int k = blockIdx.x; k < nsimu; k += gridDim.x) {
         for (int q = threadIdx.x; 2 * q < npar; q += blockDim.x) {
-            double za, zb;
-            normal_pair(draw(seed, uid, k, RK_Z1, q), za, zb);
-            z1[(size_t)k * npar + 2 * q] = za;
-            if (2 * q + 1 < npar) z1[(size_t)k * npar + 2 * q + 1] = zb;
-            normal_pair(draw(seed, uid, k, RK_Z2, q), za, zb);
-            z2[(size_t)k * npar + 2 * q] = za;
-            if (2 * q + 1 < npar) z2[(size_t)k * npar + 2 * q + 1] = zb;
+            const double4 z = normal_quad(seed, uid, k, q);
+            z1[(size_t)k * npar + 2 * q] = z.x;
+            z2[(size_t)k * npar + 2 * q] = z.z;
+            if (2 * q + 1 < npar) { z1[(size_t)k * npar + 2 * q + 1] = z.y; z2[(size_t)k * npar + 2 * q + 1] = z.w; }
         }
         if (threadIdx.x == 0) {
             const u32x4 ru = draw(seed, uid, k, RK_U, 0);
@@ -1311,6 +1506,7 @@ int tc_mcmc_run(const tc_cells *c, const tc_mcmc_opts *o, int nchains, const int
     if (o->ntry < 1 || o->ntry > 2) return fail(TC_EINVAL, "ntry must be 1 or 2");
     if (!(o->drscale > 0)) return fail(TC_EINVAL, "drscale must be > 0");
     if (o->algo != TC_ALGO_PAIRS && o->algo != TC_ALGO_TOEPLITZ) return fail(TC_EINVAL, "unknown algo");
+    if (o->adaptint < 0 || o->adaptint > 2048) return fail(TC_EINVAL, "adaptint must be in [0, 2048]");
     if (o->replay && (!rp || !rp->z1 || !rp->u1 || !rp->z2 || !rp->u2 || !rp->chi2)) return fail(TC_EINVAL, "replay streams missing");
     if (o->store_chain && (!chain || !s2chain)) return fail(TC_EINVAL, "store_chain set but chain/s2chain is NULL");
     for (int i = 0; i < nchains; ++i)
@@ -1403,6 +1599,7 @@ int tc_mcmc_run(const tc_cells *c, const tc_mcmc_opts *o, int nchains, const int
         if (do_cov) {
             CUDA_TRY(r.buf.alloc(a.gM2, (size_t)nc * ldR));
             CUDA_TRY(r.buf.alloc(a.gRows, (size_t)nc * o->adaptint * ld));
+            CUDA_TRY(r.buf.alloc(a.gWts, (size_t)nc * o->adaptint));
             CUDA_TRY(r.buf.alloc(a.gCmean, (size_t)nc * ld));
         }
         a.wsz = dram_wsz(Nmax);
@@ -1417,6 +1614,7 @@ int tc_mcmc_run(const tc_cells *c, const tc_mcmc_opts *o, int nchains, const int
         {
             const int unit = o->adaptint > 0 ? o->adaptint : 1;
             long long sl = ((long long)o->nsimu + 31) / 32;
+            if (nc >= 4 * 296) sl = o->nsimu;                 // many chains per CTA slot: imbalance averages out, no slicing
             sl = ((sl + unit - 1) / unit) * unit;
             a.seglen = (int)std::max<long long>(sl, unit);
             CUDA_TRY(r.buf.alloc(a.gState, (size_t)nc * state_doubles(ld)));
@@ -1482,6 +1680,21 @@ int tc_rng_dump(uint64_t seed, uint64_t chain_uid, int npar, double chi2_dof, in
     CUDA_TRY(cudaMemcpy(u2, du2, (size_t)nsimu * 8, cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(chi2, dc2, (size_t)nsimu * 8, cudaMemcpyDeviceToHost));
     return TC_OK;
+}
+
+int tc_debug_subprof(long long *out, int n)
+{
+#ifdef TC_SUBPROF
+    long long h[32];
+    CUDA_TRY(cudaMemcpyFromSymbol(h, tc_subprof, sizeof(h)));
+    for (int i = 0; i < n && i < 32; ++i) out[i] = h[i];
+    std::memset(h, 0, sizeof(h));
+    CUDA_TRY(cudaMemcpyToSymbol(tc_subprof, h, sizeof(h)));
+    return 1;
+#else
+    for (int i = 0; i < n; ++i) out[i] = 0;
+    return 0;
+#endif
 }
 
 int tc_measure_fp64_peak(int device, double *dfma_per_s, double *sm_clock_mhz)
