@@ -132,6 +132,8 @@ __host__ __device__ inline int dram_wsz(int N)
     int w = (work_doubles(N) + 1) & ~1;
     const int need = (chol_ws_doubles(npar) - RING * dram_slot(N) + SPEC - 1) / SPEC + 2;
     if (w < need) w = need;
+    const int need2 = 2 * ((npar + 3) & ~3) + 16 * 32;        // generate(): a row of Z + the warp's B staging (16 k-steps x 32 lanes)
+    if (w < need2) w = need2;
     return (w + 1) & ~1;
 }
 __host__ __device__ inline int dram_smem_doubles(int N)
@@ -311,8 +313,10 @@ __device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, do
                  : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
-// per-step result record of the speculative batch (shared memory)
-struct StepRes { double ssn, prin; int acc, fl, nev, noob; };
+// per-candidate-step record of a round: out-of-bounds bits and prior sums of the two proposals (shared memory)
+struct Cand { double pr1, pr2; int oob, pad; };
+// outcome of one step under the hypothesis "every earlier step of the round rejected" (registers of lane = step)
+struct StepOut { double ssn, prin; int acc, fl, nev, noob; };
 // s2chain statistics over ALL rows (TranscriptionCycleMCMC.m:302-303), thread 0, shared memory
 struct S2Stats { double sum, sq_sum, cnt, pad; };      // sum s2, sum sqrt(s2), rows
 
@@ -377,7 +381,7 @@ __device__ __noinline__ void flush_run(const RunArgs &a, const ChainCtx &cx, int
 // Per-row scalars of `cnt` committed rows r0.. by the lanes of warp 0 (one row per lane, cnt <= SPEC):
 // sigma2 of the row, s2chain statistics (sum s2, sum sqrt(s2)) and the optional per-step outputs.
 // Rows before `first` keep (ss_old); row `first` (if < cnt) carries the accepted (ss_new).
-__device__ __noinline__ void emit_s2(const RunArgs &a, const ChainCtx &cx, S2Stats *st, const StepRes *res, int r0, int cnt,
+__device__ __noinline__ void emit_s2(const RunArgs &a, const ChainCtx &cx, S2Stats *st, int fl, int r0, int cnt,
                                      int first, double ss_old, double ss_new, double sigma2_fixed)
 {
     const int lane = threadIdx.x & 31;
@@ -388,7 +392,7 @@ __device__ __noinline__ void emit_s2(const RunArgs &a, const ChainCtx &cx, S2Sta
         s2 = (a.updatesigma && r > 0) ? (a.N0 * a.S20 + ssr) / cx.slot_sc(r)[2] : sigma2_fixed;
         sq = sqrt(s2);
         if (a.store_chain && a.s2chain) a.s2chain[(size_t)cx.ch * a.nsimu + r] = s2;
-        if (a.flags) a.flags[(size_t)cx.ch * a.nsimu + r] = res ? res[lane].fl : 0;
+        if (a.flags) a.flags[(size_t)cx.ch * a.nsimu + r] = fl;
         if (a.sschain) a.sschain[(size_t)cx.ch * a.nsimu + r] = ssr;
     }
     s2 = warp_sum(s2); sq = warp_sum(sq);
@@ -404,7 +408,10 @@ __device__ __noinline__ void emit_s2(const RunArgs &a, const ChainCtx &cx, S2Sta
 //      element of R is needed exactly once per call, so the B fragments are loaded straight from HBM/L2,
 //      double-buffered GEN_UNR k-steps ahead of the MMAs, not staged in shared memory.
 #define GEN_M 8
-#define GEN_UNR 8
+#define GEN_UNR 16
+#ifndef TC_NOLOAD
+#define TC_NOLOAD 0
+#endif
 __device__ __noinline__ void generate(const RunArgs &a, const ChainCtx &cx, int g0, int nnew, bool r_diag)
 {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, npar = cx.npar;
@@ -428,10 +435,11 @@ __device__ __noinline__ void generate(const RunArgs &a, const ChainCtx &cx, int 
             }
         }
     } else {
-        // lane 0 of warp w: the uniforms and the chi-square of step g0 + w (one long serial draw per warp, all warps
-        // in parallel); then everybody: one work item = the 4 normals of a parameter pair
-        if (lane == 0 && warp < nnew) {
-            const int st = g0 + warp;
+        // lanes 0..nnew-1 of warp 0: the uniforms and the chi-square of step g0 + lane (a long serial draw, one step
+        // per lane); everybody: one work item = the 4 normals of a parameter pair.  The items are dealt from warp 1
+        // on, so that the odd extra item round lands on warp 7, not on warp 0.
+        if (warp == 0 && lane < nnew) {
+            const int st = g0 + lane;
             double *sc = cx.slot_sc(st);
             const u32x4 ru = draw(a.seed, cx.uid, st, RK_U, 0);
             sc[0] = u01(ru.x, ru.y);
@@ -441,7 +449,7 @@ __device__ __noinline__ void generate(const RunArgs &a, const ChainCtx &cx, int 
         __syncwarp();
         const int npairs = (npar + 1) >> 1;
 #pragma unroll 1
-        for (int it = tid; it < nnew * npairs; it += DRAM_THREADS) {
+        for (int it = (tid + 32) & (DRAM_THREADS - 1); it < nnew * npairs; it += DRAM_THREADS) {
             const int sidx = it / npairs, q2 = it - sidx * npairs;
             double *dz = Z + (size_t)sidx * zs;
             const double4 z = normal_quad(a.seed, cx.uid, g0 + sidx, q2);
@@ -485,45 +493,71 @@ __device__ __noinline__ void generate(const RunArgs &a, const ChainCtx &cx, int 
         double *orow = cx.slot_d(g0 + ar);
         const double *gR = cx.gRb;
         const double inv_dr = cx.inv_dr;
-        // tiles are dealt to the warps from the longest (last column tile: k-range = all rows) to the shortest
+        // Column tiles are dealt to the warps in serpentine order (longest k-range first: balances the triangle).
+        // tile of round r: NT-1 - (8 r + (r odd ? 7-w : w)).  Per tile, a rotating register file keeps the B
+        // fragments GEN_UNR k-steps ahead of the MMAs; the packed address of (i, j) advances by
+        // 4 npar - 4 i - 10 when i grows by 4.
+        const int oa = cx.o_U + ar * zs;                              // A row of this lane (offset into tc_smem)
+        const int oo = cx.slot_o(g0 + ar);                            // output slot of this lane's row
+        const bool rowok = ar < nnew;
+        const int pbase = pidx(npar, ak, ak) - ak;                    // packed index of (ak, j) is pbase + j
+        const int ostg = cx.o_U + GEN_M * zs + warp * (16 * 32) + lane;   // staging slot s of this lane: ostg + 32 s
+        const unsigned sstg = (unsigned)__cvta_generic_to_shared(tc_smem + ostg);
 #pragma unroll 1
         for (int rnd = 0; rnd * SPEC < NT; ++rnd) {
-            const int nt = NT - 1 - (rnd * SPEC + ((rnd & 1) ? SPEC - 1 - warp : warp));          // serpentine: balances the triangle
+            const int nt = NT - 1 - (rnd * SPEC + ((rnd & 1) ? SPEC - 1 - warp : warp));
             if (nt < 0) continue;
-            const int j = 8 * nt + ar;                               // B column of this lane
-            const int kmax = min(8 * nt + 8, npar);                  // rows i < kmax can reach these columns
-            double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
-            const int ks = (kmax + 3) >> 2;                          // k-steps of this tile
-            const bool jok = j < npar;
-            // rotating register pipeline: bb[u] holds R[i][j] for the k-step GEN_UNR ahead of the one being multiplied;
-            // the packed address of (i, j) advances by 4 npar - 4 i - 10 when i grows by 4
-            int il = ak, ic = ak;
-            const double *pl = gR + pidx(npar, ak, ak) + (j - ak);
-            double bb[GEN_UNR];
+            const int ks = (min(8 * nt + 8, npar) + 3) >> 2;         // k-steps of this tile
+            const int j = (8 * nt + ar < npar) ? 8 * nt + ar : -1;   // B column of this lane (-1: nothing to load)
+            // four interleaved accumulator sets (k-steps u mod 4): 8 independent MMA chains hide the MMA latency
+            double acc[4][4];
 #pragma unroll
-            for (int u = 0; u < GEN_UNR; ++u) {
-                bb[u] = (il <= j && jok) ? __ldcg(pl) : 0.0;
-                pl += 4 * npar - 4 * il - 10; il += 4;
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) acc[q][e] = 0.0;
+            int il = ak, dpl = 4 * npar - 4 * ak - 10, ic = ak;
+            const double *pl = gR + pbase + j;
+            // B fragments: 8-byte cp.async into this lane's private staging slots, two groups of 8 k-steps in flight
+            // (commit / wait_group order the arrivals; a register pipeline would have to share the warp's 6 scoreboards)
+#define GEN_ISSUE(slot)                                                                                     \
+    {                                                                                                       \
+        if (il <= j && !TC_NOLOAD) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sstg + 256u * (unsigned)(slot)), "l"(pl) : "memory"); \
+        else tc_smem[ostg + 32 * (slot)] = 0.0;                                                             \
+        pl += dpl; dpl -= 16; il += 4;                                                                      \
+    }
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) if (8 * g + u < ks) GEN_ISSUE(8 * g + u)
+                asm volatile("cp.async.commit_group;" ::: "memory");
             }
 #pragma unroll 1
-            for (int kk = 0; kk < ks; kk += GEN_UNR) {
+            for (int kk = 0; kk < ks; kk += 8) {
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
+                const int base = kk & 15;
 #pragma unroll
-                for (int u = 0; u < GEN_UNR; ++u) {
+                for (int u = 0; u < 8; ++u) {
                     if (kk + u < ks) {                               // warp-uniform
+                        const double bv = tc_smem[ostg + 32 * (base + u)];
                         double2 za = make_double2(0.0, 0.0);
-                        if (ic < npar) za = *reinterpret_cast<const double2 *>(arow + 2 * ic);
-                        dmma_m8n8k4(acc0, acc1, za.x, bb[u]);
-                        dmma_m8n8k4(acc2, acc3, za.y, bb[u]);
+                        if (ic < npar) za = *reinterpret_cast<const double2 *>(tc_smem + oa + 2 * ic);
+                        dmma_m8n8k4(acc[u & 3][0], acc[u & 3][1], za.x, bv);
+                        dmma_m8n8k4(acc[u & 3][2], acc[u & 3][3], za.y, bv);
                         ic += 4;
-                        bb[u] = (il <= j && jok) ? __ldcg(pl) : 0.0;
-                        pl += 4 * npar - 4 * il - 10; il += 4;
                     }
                 }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) if (kk + 16 + u < ks) GEN_ISSUE(base + u)
+                asm volatile("cp.async.commit_group;" ::: "memory");
             }
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+#undef GEN_ISSUE
+            const double acc0 = (acc[0][0] + acc[1][0]) + (acc[2][0] + acc[3][0]), acc1 = (acc[0][1] + acc[1][1]) + (acc[2][1] + acc[3][1]);
+            const double acc2 = (acc[0][2] + acc[1][2]) + (acc[2][2] + acc[3][2]), acc3 = (acc[0][3] + acc[1][3]) + (acc[2][3] + acc[3][3]);
             const int jc = 8 * nt + 2 * ak;
-            if (ar < nnew) {
-                if (jc < npar) { orow[2 * jc] = acc0; orow[2 * jc + 1] = acc2 * inv_dr; }
-                if (jc + 1 < npar) { orow[2 * jc + 2] = acc1; orow[2 * jc + 3] = acc3 * inv_dr; }
+            if (rowok) {
+                if (jc < npar) *reinterpret_cast<double2 *>(tc_smem + oo + 2 * jc) = make_double2(acc0, acc2 * inv_dr);
+                if (jc + 1 < npar) *reinterpret_cast<double2 *>(tc_smem + oo + 2 * jc + 2) = make_double2(acc1, acc3 * inv_dr);
             }
         }
         SUBP(2);
@@ -532,37 +566,52 @@ __device__ __noinline__ void generate(const RunArgs &a, const ChainCtx &cx, int 
     SUBP(3);
 }
 
-// One DRAM step (both proposal stages) by ONE warp for step `st`, from state x with (ss, pri), seeing
-// sigma2 = s2p.  The proposals are never materialised: theta = x + ring increment (SumVec), the very
-// expression the commit phase uses to move the state.  Result in *res.   mcmcstat DRAM: SURVEY.md 3.2.
-__device__ __noinline__ void dram_step_warp(const RunArgs &a, const ChainCtx &cx, int st, double ss, double pri, double s2p,
-                                            Work w, StepRes *res)
+__device__ __forceinline__ void warp_sum2(double &p, double &q)
 {
-    const int lane = threadIdx.x & 31, npar = cx.npar;
-    const int so = cx.slot_o(st);
-    const double2 *dd = reinterpret_cast<const double2 *>(tc_smem + so);
-    const double *sc = cx.slot_sc(st);
-    double pr1 = 0.0, pr2 = 0.0;
-    unsigned oob = 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { p += __shfl_xor_sync(0xffffffffu, p, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+}
+
+// Round phase A: bounds and prior of both proposals of the candidate steps k .. k+C-1 (warp w: candidates w, w+8).
+// The proposals are never materialised: theta = x + ring increment, the very expression the forward model
+// (SumVec) and the commit phase use.                    bounds/prior: TranscriptionCycleMCMC.m:235-255
+__device__ __noinline__ void cand_bounds(const ChainCtx &cx, int k, int C, Cand *cand)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, npar = cx.npar;
 #pragma unroll 1
-    for (int j = lane; j < npar; j += 32) {
-        const double2 dj = dd[j];
-        const double xj = cx.x[j], a1 = xj + dj.x, a2 = xj + dj.y;
-        const double lo = cx.lo[j], hi = cx.hi[j];
-        if (a1 < lo || a1 > hi) oob |= 1u;
-        if (a2 < lo || a2 > hi) oob |= 2u;
-        const double e1 = (a1 - cx.mu[j]) * cx.pinv[j], e2 = (a2 - cx.mu[j]) * cx.pinv[j];
-        pr1 = fma(e1, e1, pr1);
-        pr2 = fma(e2, e2, pr2);
+    for (int c = warp; c < C; c += SPEC) {
+        const double2 *dd = reinterpret_cast<const double2 *>(tc_smem + cx.slot_o(k + c));
+        double pr1 = 0.0, pr2 = 0.0;
+        unsigned oob = 0;
+#pragma unroll 1
+        for (int j = lane; j < npar; j += 32) {
+            const double2 dj = dd[j];
+            const double xj = cx.x[j], a1 = xj + dj.x, a2 = xj + dj.y;
+            const double lo = cx.lo[j], hi = cx.hi[j];
+            if (a1 < lo || a1 > hi) oob |= 1u;
+            if (a2 < lo || a2 > hi) oob |= 2u;
+            const double e1 = (a1 - cx.mu[j]) * cx.pinv[j], e2 = (a2 - cx.mu[j]) * cx.pinv[j];
+            pr1 = fma(e1, e1, pr1);
+            pr2 = fma(e2, e2, pr2);
+        }
+        warp_sum2(pr1, pr2);
+        oob = __reduce_or_sync(0xffffffffu, oob);
+        if (lane == 0) { cand[c].pr1 = pr1; cand[c].pr2 = pr2; cand[c].oob = (int)oob; }
     }
-    pr1 = warp_sum(pr1); pr2 = warp_sum(pr2);
-    oob = __reduce_or_sync(0xffffffffu, oob);
+}
+
+// Round phase D: the accept/reject arithmetic of ONE step (one lane), given the SS of its proposals, from state
+// (ss, pri) seeing sigma2 = s2p.                                             mcmcstat DRAM: SURVEY.md 3.2
+__device__ __noinline__ StepOut resolve_step(const RunArgs &a, const double *sc, int oob, double pr1, double pr2, double ss1v,
+                                             double ss2v, double ss, double pri, double s2p)
+{
+    StepOut r;
     int fl = 0, accept = 0, nev = 0, noob = 0;
     double ss1, a12;
-    if (oob & 1u) {
+    if (oob & 1) {
         ss1 = INFINITY; pr1 = 0.0; a12 = 0.0; fl |= TC_FL_OOB1; ++noob;
     } else {
-        ss1 = ss_eval(a.cons, cx.cv, SumVec{cx.o_x, so}, w, a.algo, false, nullptr, nullptr);
+        ss1 = ss1v;
         ++nev;
         a12 = tc_exp(-0.5 * ((ss1 - ss) / s2p + pr1 - pri));
         if (a12 <= 0.0) accept = 0;
@@ -572,10 +621,10 @@ __device__ __noinline__ void dram_step_warp(const RunArgs &a, const ChainCtx &cx
     double ssn = ss1, prin = pr1;
     if (!accept && a.ntry >= 2) {                                // delayed rejection with R/drscale
         fl |= TC_FL_DR;
-        if (oob & 2u) {
+        if (oob & 2) {
             fl |= TC_FL_OOB2; ++noob;
         } else {
-            const double ss2 = ss_eval(a.cons, cx.cv, SumVec{cx.o_x, so + 1}, w, a.algo, false, nullptr, nullptr);
+            const double ss2 = ss2v;
             ++nev;
             double a32 = tc_exp(-0.5 * ((ss1 - ss2) / s2p + pr1 - pr2));
             a32 = a32 > 1.0 ? 1.0 : a32;
@@ -588,7 +637,8 @@ __device__ __noinline__ void dram_step_warp(const RunArgs &a, const ChainCtx &cx
         }
     }
     if (accept) fl |= TC_FL_ACCEPT;
-    if (lane == 0) { res->acc = accept; res->fl = fl; res->nev = nev; res->noob = noob; res->ssn = ssn; res->prin = prin; }
+    r.acc = accept; r.fl = fl; r.nev = nev; r.noob = noob; r.ssn = ssn; r.prin = prin;
+    return r;
 }
 
 // Adaptation after the step with isimu (a multiple of adaptint).  The block of the last adaptint chain rows
@@ -783,7 +833,8 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
         for (int i = threadIdx.x; i < (int)(sizeof(RunArgs) / sizeof(int)); i += DRAM_THREADS) dst[i] = src[i];
     }
     __syncthreads();
-    __shared__ StepRes s_res[SPEC];
+    __shared__ Cand s_cand[RING];
+    __shared__ double s_ssv[2 * RING];
     __shared__ ChainCtx cx;
     __shared__ S2Stats s_s2;
     __shared__ double s_dinv[8];
@@ -826,7 +877,7 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
             const unsigned kmin = s_min;
             if (kmin == 0xffffffffu) {
                 if (!pending) { if (tid == 0) s_item = -1; break; }     // every chain is finished
-                __nanosleep(2000);
+                __nanosleep(20000);
                 continue;
             }
             if (tid == 0) {
@@ -952,7 +1003,7 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
             sp = warp_sum(sp);
             const bool bad = !isfinite(ss0);
             if (tid == 0) { st.ss = ss0; st.pri = sp; st.bad0 = bad ? 1 : 0; }
-            if (!bad && warp == 0) emit_s2(a, cx, &s_s2, nullptr, 0, 1, 1, ss0, ss0, a.sigma2_0);
+            if (!bad && warp == 0) emit_s2(a, cx, &s_s2, 0, 0, 1, 1, ss0, ss0, a.sigma2_0);
             __syncthreads();
         }
 
@@ -965,61 +1016,85 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
             // is the last one that may use the current R
             int bound = k_end;
             if (a.adaptint > 0) bound = min(bound, ((k + a.adaptint) / a.adaptint) * a.adaptint);   // exclusive step bound
-            const int lim = min(k + SPEC, bound);
-            const int nb = lim - k;
-            // chain state of this round (thread 0 rewrites st only after the post-speculation barrier)
+            // chain state of this round (thread 0 rewrites st only in the commit phase, after two barriers)
             const double ss = st.ss, pri = st.pri, sig2 = st.sigma2, wcnt = st.wcnt;
             const int run_r0 = st.run_r0, ndist = st.ndist;
 
-            if (gen_upto < lim) {
-                // fewer than a round's worth of steps ready => at least GEN_M ring slots are free
+            if (gen_upto < bound && gen_upto - k < SPEC) {
+                // fewer than SPEC steps ready => at least GEN_M of the RING slots are free
                 const int glim = min(gen_upto + GEN_M, bound);
                 generate(a, cx, gen_upto, glim - gen_upto, st.r_diag != 0);
                 gen_upto = glim;
             }
             TC_PHASE(0);
 
-            // speculation: warp w runs step k+w assuming steps k..k+w-1 rejected; the sigma2 it sees is the
-            // draw made at the end of step k+w-1 from the (unchanged) ss
-            if (warp < nb) {
-                double s2p = sig2;
-                if (warp > 0 && a.updatesigma) s2p = (a.N0 * a.S20 + ss) / cx.slot_sc(k + warp - 1)[2];
-                dram_step_warp(a, cx, k + warp, ss, pri, s2p, w, &s_res[warp]);
+            // ---- one round = SPEC forward-model evaluations, one per warp, over as many future steps as they cover.
+            // A. bounds + prior of both proposals of every ready step (an out-of-bounds proposal needs no evaluation)
+            const int C = gen_upto - k;                                     // candidates: 1 .. RING-1
+            cand_bounds(cx, k, C, s_cand);
+            __syncthreads();
+            // B. task list, in step order: stage 1 (if in bounds), stage 2 (if in bounds; needed unless stage 1 accepts,
+            //    which is rare); the round covers the longest prefix of steps whose tasks fit in SPEC warps.  Every warp
+            //    derives the same list (lane = candidate step).
+            int c_oob = 3, c_nt = 2 * SPEC;
+            if (lane < C) {
+                c_oob = s_cand[lane].oob;
+                c_nt = ((c_oob & 1) ? 0 : 1) + ((a.ntry >= 2 && !(c_oob & 2)) ? 1 : 0);
+            }
+            int inc = c_nt;
+#pragma unroll
+            for (int o = 1; o < RING; o <<= 1) { const int up = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += up; }
+            const int exc = inc - c_nt;
+            const bool covered = lane < C && inc <= SPEC;
+            const int nsteps = __popc(__ballot_sync(0xffffffffu, covered));  // >= 1: a step has at most 2 tasks
+            const unsigned tmask = __ballot_sync(0xffffffffu, covered && exc <= warp && warp < inc);
+            // C. this warp's evaluation
+            if (tmask) {
+                const int mc = __ffs(tmask) - 1;
+                const int e0 = __shfl_sync(0xffffffffu, exc, mc), ob = __shfl_sync(0xffffffffu, c_oob, mc);
+                const int stage = (warp == e0 && !(ob & 1)) ? 0 : 1;
+                const double v = ss_eval(a.cons, cx.cv, SumVec{cx.o_x, cx.slot_o(k + mc) + stage}, w, a.algo, false, nullptr, nullptr);
+                if (lane == 0) s_ssv[2 * mc + stage] = v;
             }
             __syncthreads();
             TC_PHASE(1);
-
-            // commit up to and including the first accepting step
-            int first = nb;
-#pragma unroll 1
-            for (int q = nb - 1; q >= 0; --q) if (s_res[q].acc) first = q;
-            const bool accd = first < nb;
-            const int ncommit = accd ? first + 1 : nb;
+            // D. accept/reject of every covered step under the hypothesis "the steps before it rejected" (lane = step; the
+            //    sigma2 a step sees is the draw made at the end of the previous step from the unchanged ss).  Every warp
+            //    computes the same outcomes, so no barrier is needed before the commit.
+            StepOut so_;
+            so_.acc = 0; so_.fl = 0; so_.nev = 0; so_.noob = 0; so_.ssn = 0.0; so_.prin = 0.0;
+            if (lane < nsteps) {
+                double s2p = sig2;
+                if (lane > 0 && a.updatesigma) s2p = (a.N0 * a.S20 + ss) / cx.slot_sc(k + lane - 1)[2];
+                so_ = resolve_step(a, cx.slot_sc(k + lane), c_oob, s_cand[lane].pr1, s_cand[lane].pr2, s_ssv[2 * lane], s_ssv[2 * lane + 1],
+                                   ss, pri, s2p);
+            }
+            const unsigned amask = __ballot_sync(0xffffffffu, lane < nsteps && so_.acc != 0);
+            const bool accd = amask != 0;
+            const int first = accd ? __ffs(amask) - 1 : nsteps;
+            const int ncommit = accd ? first + 1 : nsteps;
             const int r_acc = k + first;                                    // row of the accept
+            const int src = accd ? first : 0;
+            const int acc_t = __shfl_sync(0xffffffffu, so_.acc, src);
+            const double ssn_a = __shfl_sync(0xffffffffu, so_.ssn, src), prin_a = __shfl_sync(0xffffffffu, so_.prin, src);
             if (accd) {
-                // close the run of the old state at row r_acc and move x by the accepting warp's increment
-                const int so = cx.slot_o(r_acc) + (s_res[first].acc == 2 ? 1 : 0);
-                flush_run(a, cx, run_r0, r_acc, wcnt, ndist, so);
+                // close the run of the old state at row r_acc and move x by the accepted increment
+                flush_run(a, cx, run_r0, r_acc, wcnt, ndist, cx.slot_o(r_acc) + (acc_t == 2 ? 1 : 0));
             }
             if (warp == 0) {
-                const double ss_new = accd ? s_res[first].ssn : ss;
-                emit_s2(a, cx, &s_s2, s_res, k, ncommit, first, ss, ss_new, sig2);
+                const double ss_new = accd ? ssn_a : ss;
+                emit_s2(a, cx, &s_s2, so_.fl, k, ncommit, first, ss, ss_new, sig2);
+                const int d_ss = __reduce_add_sync(0xffffffffu, lane < ncommit ? so_.nev : 0);
+                const int d_oob = __reduce_add_sync(0xffffffffu, lane < ncommit ? so_.noob : 0);
+                const int d_dr = __reduce_add_sync(0xffffffffu, (lane < ncommit && (so_.fl & TC_FL_DR)) ? 1 : 0);
+                const int d_spec = __shfl_sync(0xffffffffu, inc, nsteps - 1);       // evaluations of this round
                 if (lane == 0) {
-                    int d_ss = 0, d_oob = 0, d_dr = 0, d_spec = 0;
-#pragma unroll
-                    for (int q = 0; q < SPEC; ++q) {
-                        if (q < nb) {
-                            const int nev = s_res[q].nev;
-                            d_spec += nev;
-                            if (q < ncommit) { d_ss += nev; d_oob += s_res[q].noob; d_dr += (s_res[q].fl & TC_FL_DR) ? 1 : 0; }
-                        }
-                    }
-                    const int nrej = accd ? first : nb;
+                    const int nrej = accd ? first : nsteps;
                     st.n_ss += d_ss; st.n_oob += d_oob; st.n_dr += d_dr; st.n_spec += d_spec;
                     st.rej += nrej; st.reju += nrej;
                     if (accd) {
-                        st.ss = ss_new; st.pri = s_res[first].prin;
-                        if (s_res[first].acc == 1) ++st.n_acc1; else ++st.n_acc2;
+                        st.ss = ss_new; st.pri = prin_a;
+                        if (acc_t == 1) ++st.n_acc1; else ++st.n_acc2;
                         st.wcnt = wcnt + max(0, r_acc - max(run_r0, cx.first_row));
                         if (a.do_cov && r_acc > run_r0) st.ndist = ndist + 1;
                         st.run_r0 = r_acc;
