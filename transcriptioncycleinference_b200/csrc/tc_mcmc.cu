@@ -408,7 +408,6 @@ __device__ __noinline__ void emit_s2(const RunArgs &a, const ChainCtx &cx, S2Sta
 //      element of R is needed exactly once per call, so the B fragments are loaded straight from HBM/L2,
 //      double-buffered GEN_UNR k-steps ahead of the MMAs, not staged in shared memory.
 #define GEN_M 8
-#define GEN_UNR 16
 #ifndef TC_NOLOAD
 #define TC_NOLOAD 0
 #endif
@@ -489,41 +488,40 @@ __device__ __noinline__ void generate(const RunArgs &a, const ChainCtx &cx, int 
     } else {
         const int NT = (npar + 7) >> 3;                              // column tiles of 8
         const int ar = lane >> 2, ak = lane & 3;                     // A[row = step][k], B[k][col]
-        const double *arow = Z + (size_t)ar * zs;                    // rows >= nnew hold stale scratch: their results are dropped
-        double *orow = cx.slot_d(g0 + ar);
         const double *gR = cx.gRb;
         const double inv_dr = cx.inv_dr;
-        // Column tiles are dealt to the warps in serpentine order (longest k-range first: balances the triangle).
-        // tile of round r: NT-1 - (8 r + (r odd ? 7-w : w)).  Per tile, a rotating register file keeps the B
-        // fragments GEN_UNR k-steps ahead of the MMAs; the packed address of (i, j) advances by
-        // 4 npar - 4 i - 10 when i grows by 4.
-        const int oa = cx.o_U + ar * zs;                              // A row of this lane (offset into tc_smem)
+        // Column tiles are dealt to the warps in serpentine order (longest k-range first: balances the triangle):
+        // tile of round r = NT-1 - (8 r + (r odd ? 7-w : w)).
+        const int oa = cx.o_U + ar * zs;                              // A row of this lane (offset into tc_smem); rows >= nnew hold
+                                                                      // stale scratch: their results are dropped
         const int oo = cx.slot_o(g0 + ar);                            // output slot of this lane's row
         const bool rowok = ar < nnew;
-        const int pbase = pidx(npar, ak, ak) - ak;                    // packed index of (ak, j) is pbase + j
+        const int nt4 = (npar + 3) >> 2;
+        const int inner = 4 * ak + (ar & 3);                          // position of (row 4kk+ak, column 8nt+ar) inside its 4x4 tile
         const int ostg = cx.o_U + GEN_M * zs + warp * (16 * 32) + lane;   // staging slot s of this lane: ostg + 32 s
         const unsigned sstg = (unsigned)__cvta_generic_to_shared(tc_smem + ostg);
 #pragma unroll 1
         for (int rnd = 0; rnd * SPEC < NT; ++rnd) {
             const int nt = NT - 1 - (rnd * SPEC + ((rnd & 1) ? SPEC - 1 - warp : warp));
             if (nt < 0) continue;
-            const int ks = (min(8 * nt + 8, npar) + 3) >> 2;         // k-steps of this tile
-            const int j = (8 * nt + ar < npar) ? 8 * nt + ar : -1;   // B column of this lane (-1: nothing to load)
+            const int ks = (min(8 * nt + 8, npar) + 3) >> 2;         // k-steps (= tile rows) of this column tile
+            const int bj = (8 * nt + ar < npar) ? 2 * nt + (ar >> 2) : -1;   // 4x4 tile column of this lane (-1: nothing to load)
             // four interleaved accumulator sets (k-steps u mod 4): 8 independent MMA chains hide the MMA latency
             double acc[4][4];
 #pragma unroll
             for (int q = 0; q < 4; ++q)
 #pragma unroll
                 for (int e = 0; e < 4; ++e) acc[q][e] = 0.0;
-            int il = ak, dpl = 4 * npar - 4 * ak - 10, ic = ak;
-            const double *pl = gR + pbase + j;
+            // R is stored in 4x4 tiles (see chol_tiled): tile (kk, bj) sits 16 (nt4 - kk - 1) doubles after tile (kk-1, bj)
+            int il = 0, dpl = 16 * (nt4 - 1), ic = ak;
+            const double *pl = gR + 16 * bj + inner;
             // B fragments: 8-byte cp.async into this lane's private staging slots, two groups of 8 k-steps in flight
             // (commit / wait_group order the arrivals; a register pipeline would have to share the warp's 6 scoreboards)
 #define GEN_ISSUE(slot)                                                                                     \
     {                                                                                                       \
-        if (il <= j && !TC_NOLOAD) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sstg + 256u * (unsigned)(slot)), "l"(pl) : "memory"); \
+        if (il <= bj && !TC_NOLOAD) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sstg + 256u * (unsigned)(slot)), "l"(pl) : "memory"); \
         else tc_smem[ostg + 32 * (slot)] = 0.0;                                                             \
-        pl += dpl; dpl -= 16; il += 4;                                                                      \
+        pl += dpl; dpl -= 16; il += 1;                                                                      \
     }
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
@@ -649,7 +647,7 @@ __device__ __noinline__ StepOut resolve_step(const RunArgs &a, const double *sc,
 __device__ __noinline__ int adapt(const RunArgs &a, const ChainCtx &cx, int isimu, double cov_n, double rate, bool r_diag,
                                   int ndist, double *s_dinv, int *s_flag)
 {
-    const int tid = threadIdx.x, npar = cx.npar, npad = cx.npad, ld = cx.ld, npk = cx.npk;
+    const int tid = threadIdx.x, npar = cx.npar, npad = cx.npad, ld = cx.ld;
     double *chunk = cx.ring;                           // workspace: ring + per-warp areas (idle now)
     double *sw = cx.ring + COV_RC * npad;                             // sqrt(weight) per row
     SUBP_BEGIN;
@@ -718,24 +716,16 @@ __device__ __noinline__ int adapt(const RunArgs &a, const ChainCtx &cx, int isim
                 }
             }
             SUBP(8);
+            // the scatter matrix lives in HBM/L2 in the same 4x4-tile layout: tile tix is 16 contiguous doubles
 #pragma unroll
             for (int u = 0; u < COV_TPT; ++u) {
                 if (!on[u]) continue;
-                double old[16];
+                double2 *g = reinterpret_cast<double2 *>(cx.gM2 + 16 * (size_t)(base + u * DRAM_THREADS + tid));
+                double2 old[8];
 #pragma unroll
-                for (int ii = 0; ii < 4; ++ii)
+                for (int e = 0; e < 8; ++e) old[e] = __ldcg(g + e);
 #pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) {
-                        const int pp = 4 * bi[u] + ii, qq = 4 * bj[u] + jj;
-                        old[4 * ii + jj] = (pp <= qq && qq < npar) ? __ldcg(cx.gM2 + pidx(npar, pp, qq)) : 0.0;
-                    }
-#pragma unroll
-                for (int ii = 0; ii < 4; ++ii)
-#pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) {
-                        const int pp = 4 * bi[u] + ii, qq = 4 * bj[u] + jj;
-                        if (pp <= qq && qq < npar) cx.gM2[pidx(npar, pp, qq)] = old[4 * ii + jj] + acc[u][4 * ii + jj];
-                    }
+                for (int e = 0; e < 8; ++e) g[e] = make_double2(old[e].x + acc[u][2 * e], old[e].y + acc[u][2 * e + 1]);
             }
         }
         __syncthreads();
@@ -756,7 +746,7 @@ __device__ __noinline__ int adapt(const RunArgs &a, const ChainCtx &cx, int isim
                 for (int i = tid; i < npar; i += DRAM_THREADS) cx.rdiag[i] *= f;
             } else {
 #pragma unroll 1
-                for (int i = tid; i < npk; i += DRAM_THREADS) cx.gRb[i] = __ldcg(cx.gRb + i) * f;
+                for (int i = tid; i < 16 * (((npar + 3) >> 2) * (((npar + 3) >> 2) + 1) / 2); i += DRAM_THREADS) cx.gRb[i] = __ldcg(cx.gRb + i) * f;
             }
         }
     } else {
@@ -771,14 +761,18 @@ __device__ __noinline__ int adapt(const RunArgs &a, const ChainCtx &cx, int isim
             while (rem >= nt4 - b) { rem -= nt4 - b; ++b; }
             tab[t] = (unsigned short)((b << 8) | (b + rem));
         }
+        {
+            const double2 *src = reinterpret_cast<const double2 *>(cx.gM2);
+            double2 *dst = reinterpret_cast<double2 *>(W);
+#pragma unroll 8
+            for (int e = tid; e < 8 * T4; e += DRAM_THREADS) { const double2 v = __ldcg(src + e); dst[e] = make_double2(v.x * invn, v.y * invn); }
+        }
         __syncthreads();
-#pragma unroll 4
-        for (int e = tid; e < 16 * T4; e += DRAM_THREADS) {
-            const int t = e >> 4, r = (e >> 2) & 3, c = e & 3;
-            const int row = 4 * (tab[t] >> 8) + r, col = 4 * (tab[t] & 0xff) + c;
-            double v = (row == col) ? 1.0 : 0.0;                     // identity padding; lower parts of diagonal tiles are never read
-            if (row <= col && col < npar) v = __ldcg(cx.gM2 + pidx(npar, row, col)) * invn + (row == col ? a.qcovadj : 0.0);
-            W[e] = v;
+        // + qcovadj I; identity on the padding rows (the rest of the padding is zero: it only ever accumulated zeros)
+#pragma unroll 1
+        for (int i = tid; i < 4 * nt4; i += DRAM_THREADS) {
+            double *d = W + 16 * tidx(nt4, i >> 2, i >> 2) + 5 * (i & 3);
+            *d = i < npar ? *d + a.qcovadj : 1.0;
         }
         __syncthreads();
         SUBP(10);
@@ -786,11 +780,12 @@ __device__ __noinline__ int adapt(const RunArgs &a, const ChainCtx &cx, int isim
         __syncthreads();
         SUBP(11);
         if (ok) {
-#pragma unroll 4
-            for (int e = tid; e < 16 * T4; e += DRAM_THREADS) {
-                const int t = e >> 4, r = (e >> 2) & 3, c = e & 3;
-                const int row = 4 * (tab[t] >> 8) + r, col = 4 * (tab[t] & 0xff) + c;
-                if (row <= col && col < npar) cx.gRb[pidx(npar, row, col)] = W[e] * cx.adascale;
+            {
+                const double2 *src = reinterpret_cast<const double2 *>(W);
+                double2 *dst = reinterpret_cast<double2 *>(cx.gRb);
+                const double sc = cx.adascale;
+#pragma unroll 8
+                for (int e = tid; e < 8 * T4; e += DRAM_THREADS) { const double2 v = src[e]; dst[e] = make_double2(v.x * sc, v.y * sc); }
             }
             ret = 1;
         } else {
@@ -962,7 +957,7 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
         if (seg == 0) {
             if (a.do_cov) {
 #pragma unroll 1
-                for (int i = tid; i < cx.npk; i += DRAM_THREADS) cx.gM2[i] = 0.0;
+                for (int i = tid; i < 16 * (((npar + 3) >> 2) * (((npar + 3) >> 2) + 1) / 2); i += DRAM_THREADS) cx.gM2[i] = 0.0;
             }
             // ring slot 0 = zero increments: row 0 evaluates ss(x0) through the same theta view as every step
 #pragma unroll 1
@@ -1598,8 +1593,8 @@ int tc_mcmc_run(const tc_cells *c, const tc_mcmc_opts *o, int nchains, const int
     for (int d : devs) if (!find_dev(c, d)) return fail(TC_EINVAL, "cells not resident on a requested device");
     ngpus = std::min(ngpus, nchains);
 
-    const int Nmax = c->Nmax, npmax = 7 + Nmax, npad = (npmax + 3) & ~3;
-    const int ldR = (npmax * (npmax + 1) / 2 + 1) & ~1;    // even: 16-byte cp.async granules
+    const int Nmax = c->Nmax, npmax = 7 + Nmax;
+    const int ldR = 16 * (((npmax + 3) / 4) * ((npmax + 3) / 4 + 1) / 2);   // proposal factor / scatter matrix in 4x4 tiles (chol_tiled)
     // does any adaptation with a covariance ever happen?
     bool do_cov = false;
     if (o->adaptint > 0)
