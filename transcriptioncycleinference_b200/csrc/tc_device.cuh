@@ -25,6 +25,7 @@ __device__ long long tc_ss_prof[8];
 // ------------------------------------------------------------------------------------------ RNG
 __device__ double tc_exp(double x);
 __device__ double tc_log(double x);
+__device__ void tc_exp3(double x0, double x1, double x2, double &e0, double &e1, double &e2);
 struct u32x4 { uint32_t x, y, z, w; };
 
 __host__ __device__ __forceinline__ void philox_round(uint32_t &c0, uint32_t &c1, uint32_t &c2,
@@ -124,6 +125,11 @@ __device__ __noinline__ double chi2_draw(uint64_t seed, uint64_t uid, uint32_t s
 // the instruction cache (ncu: icc hit rate 58 %, stall_no_instruction dominant before this).
 __device__ __noinline__ double tc_exp(double x) { return exp(x); }
 __device__ __noinline__ double tc_log(double x) { return log(x); }
+// three independent exponentials in one body: their dependent chains interleave (the DRAM acceptance ratios)
+__device__ __noinline__ void tc_exp3(double x0, double x1, double x2, double &e0, double &e1, double &e2)
+{
+    e0 = exp(x0); e1 = exp(x1); e2 = exp(x2);
+}
 
 // ------------------------------------------------------------------------------- reductions
 __device__ __forceinline__ double warp_sum(double v)

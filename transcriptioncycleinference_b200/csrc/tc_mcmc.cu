@@ -581,7 +581,7 @@ __device__ __noinline__ void cand_bounds(const ChainCtx &cx, int k, int C, Cand 
         const double2 *dd = reinterpret_cast<const double2 *>(tc_smem + cx.slot_o(k + c));
         double pr1 = 0.0, pr2 = 0.0;
         unsigned oob = 0;
-#pragma unroll 1
+#pragma unroll 4
         for (int j = lane; j < npar; j += 32) {
             const double2 dj = dd[j];
             const double xj = cx.x[j], a1 = xj + dj.x, a2 = xj + dj.y;
@@ -603,15 +603,24 @@ __device__ __noinline__ void cand_bounds(const ChainCtx &cx, int k, int C, Cand 
 __device__ __noinline__ StepOut resolve_step(const RunArgs &a, const double *sc, int oob, double pr1, double pr2, double ss1v,
                                              double ss2v, double ss, double pri, double s2p)
 {
+    // The three acceptance exponentials are evaluated up front, in one interleaved body, whether or not the step needs
+    // them all (an unused one may see garbage or Inf: it is never read):
+    //   a12 = exp(-1/2 ((ss1-ss)/s2 + pr1-pri)), a32 = exp(-1/2 ((ss1-ss2)/s2 + pr1-pr2)), exp(l2 + q1)
+    const bool o1 = (oob & 1) != 0, o2 = (oob & 2) != 0;
+    const double ss1 = o1 ? INFINITY : ss1v;
+    if (o1) pr1 = 0.0;
+    const double ss2 = ss2v;
+    const double q1 = -0.5 * (sc[3] - sc[4]);
+    double e12, e32, e13;
+    tc_exp3(-0.5 * ((ss1 - ss) / s2p + pr1 - pri), -0.5 * ((ss1 - ss2) / s2p + pr1 - pr2), -0.5 * ((ss2 - ss) / s2p + pr2 - pri) + q1, e12, e32, e13);
     StepOut r;
     int fl = 0, accept = 0, nev = 0, noob = 0;
-    double ss1, a12;
-    if (oob & 1) {
-        ss1 = INFINITY; pr1 = 0.0; a12 = 0.0; fl |= TC_FL_OOB1; ++noob;
+    double a12;
+    if (o1) {
+        a12 = 0.0; fl |= TC_FL_OOB1; ++noob;
     } else {
-        ss1 = ss1v;
         ++nev;
-        a12 = tc_exp(-0.5 * ((ss1 - ss) / s2p + pr1 - pri));
+        a12 = e12;
         if (a12 <= 0.0) accept = 0;
         else if (a12 >= 1.0) accept = 1;
         else accept = a12 > sc[0];
@@ -619,17 +628,14 @@ __device__ __noinline__ StepOut resolve_step(const RunArgs &a, const double *sc,
     double ssn = ss1, prin = pr1;
     if (!accept && a.ntry >= 2) {                                // delayed rejection with R/drscale
         fl |= TC_FL_DR;
-        if (oob & 2) {
+        if (o2) {
             fl |= TC_FL_OOB2; ++noob;
         } else {
-            const double ss2 = ss2v;
             ++nev;
-            double a32 = tc_exp(-0.5 * ((ss1 - ss2) / s2p + pr1 - pr2));
+            double a32 = e32;
             a32 = a32 > 1.0 ? 1.0 : a32;
             if (!(a32 >= 0.0)) a32 = 0.0;
-            const double l2 = -0.5 * ((ss2 - ss) / s2p + pr2 - pri);
-            const double q1 = -0.5 * (sc[3] - sc[4]);
-            double a13 = tc_exp(l2 + q1) * (1.0 - a32) / (1.0 - a12);
+            double a13 = e13 * (1.0 - a32) / (1.0 - a12);
             a13 = a13 > 1.0 ? 1.0 : a13;
             if ((a13 >= 1.0) || (a13 > sc[1])) { accept = 2; fl |= TC_FL_STAGE2; ssn = ss2; prin = pr2; }
         }
@@ -1025,9 +1031,12 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
 
             // ---- one round = SPEC forward-model evaluations, one per warp, over as many future steps as they cover.
             // A. bounds + prior of both proposals of every ready step (an out-of-bounds proposal needs no evaluation)
-            const int C = gen_upto - k;                                     // candidates: 1 .. RING-1
+            const int C = min(gen_upto - k, SPEC);                          // candidates: one per warp (more are almost never covered)
+            SUBP_BEGIN;
             cand_bounds(cx, k, C, s_cand);
+            SUBP(16);
             __syncthreads();
+            SUBP(17);
             // B. task list, in step order: stage 1 (if in bounds), stage 2 (if in bounds; needed unless stage 1 accepts,
             //    which is rare); the round covers the longest prefix of steps whose tasks fit in SPEC warps.  Every warp
             //    derives the same list (lane = candidate step).
@@ -1051,11 +1060,14 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
                 const double v = ss_eval(a.cons, cx.cv, SumVec{cx.o_x, cx.slot_o(k + mc) + stage}, w, a.algo, false, nullptr, nullptr);
                 if (lane == 0) s_ssv[2 * mc + stage] = v;
             }
+            SUBP(18);
             __syncthreads();
+            SUBP(19);
             TC_PHASE(1);
             // D. accept/reject of every covered step under the hypothesis "the steps before it rejected" (lane = step; the
             //    sigma2 a step sees is the draw made at the end of the previous step from the unchanged ss).  Every warp
-            //    computes the same outcomes, so no barrier is needed before the commit.
+            //    computes the same outcomes, so no barrier is needed before the commit (and a warp running this alone is
+            //    no faster: measured).
             StepOut so_;
             so_.acc = 0; so_.fl = 0; so_.nev = 0; so_.noob = 0; so_.ssn = 0.0; so_.prin = 0.0;
             if (lane < nsteps) {
@@ -1072,18 +1084,35 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
             const int src = accd ? first : 0;
             const int acc_t = __shfl_sync(0xffffffffu, so_.acc, src);
             const double ssn_a = __shfl_sync(0xffffffffu, so_.ssn, src), prin_a = __shfl_sync(0xffffffffu, so_.prin, src);
+            SUBP(20);
             if (accd) {
                 // close the run of the old state at row r_acc and move x by the accepted increment
                 flush_run(a, cx, run_r0, r_acc, wcnt, ndist, cx.slot_o(r_acc) + (acc_t == 2 ? 1 : 0));
             }
+            SUBP(21);
             if (warp == 0) {
+                // per-row scalars of the committed rows (lane = row): sigma2 of the row (rows before the accept keep ss),
+                // s2chain statistics, optional per-step outputs; then the chain state for the next round
                 const double ss_new = accd ? ssn_a : ss;
-                emit_s2(a, cx, &s_s2, so_.fl, k, ncommit, first, ss, ss_new, sig2);
+                double s2 = 0.0, sq = 0.0;
+                if (lane < ncommit) {
+                    const int r = k + lane;
+                    const double ssr = lane < first ? ss : ss_new;
+                    s2 = a.updatesigma ? (a.N0 * a.S20 + ssr) / cx.slot_sc(r)[2] : sig2;
+                    sq = sqrt(s2);
+                    if (a.store_chain && a.s2chain) a.s2chain[(size_t)cx.ch * a.nsimu + r] = s2;
+                    if (a.flags) a.flags[(size_t)cx.ch * a.nsimu + r] = so_.fl;
+                    if (a.sschain) a.sschain[(size_t)cx.ch * a.nsimu + r] = ssr;
+                }
+                const double s2_last = __shfl_sync(0xffffffffu, s2, ncommit - 1);   // the sigma2 the next step sees
+#pragma unroll
+                for (int o = RING / 2; o > 0; o >>= 1) { s2 += __shfl_xor_sync(0xffffffffu, s2, o); sq += __shfl_xor_sync(0xffffffffu, sq, o); }
                 const int d_ss = __reduce_add_sync(0xffffffffu, lane < ncommit ? so_.nev : 0);
                 const int d_oob = __reduce_add_sync(0xffffffffu, lane < ncommit ? so_.noob : 0);
                 const int d_dr = __reduce_add_sync(0xffffffffu, (lane < ncommit && (so_.fl & TC_FL_DR)) ? 1 : 0);
                 const int d_spec = __shfl_sync(0xffffffffu, inc, nsteps - 1);       // evaluations of this round
                 if (lane == 0) {
+                    s_s2.sum += s2; s_s2.sq_sum += sq; s_s2.cnt += ncommit;
                     const int nrej = accd ? first : nsteps;
                     st.n_ss += d_ss; st.n_oob += d_oob; st.n_dr += d_dr; st.n_spec += d_spec;
                     st.rej += nrej; st.reju += nrej;
@@ -1094,11 +1123,13 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
                         if (a.do_cov && r_acc > run_r0) st.ndist = ndist + 1;
                         st.run_r0 = r_acc;
                     }
-                    if (a.updatesigma) st.sigma2 = (a.N0 * a.S20 + ss_new) / cx.slot_sc(k + ncommit - 1)[2];
+                    if (a.updatesigma) st.sigma2 = s2_last;
                 }
             }
+            SUBP(22);
             k += ncommit;
             __syncthreads();
+            SUBP(23);
 #ifdef TC_SUBPROF
             if (tid == 0 && cx.ch == 0) { tc_subprof[24] += 1; tc_subprof[25] += ncommit; }
 #endif
