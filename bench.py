@@ -107,7 +107,11 @@ def cpu_baseline(g, workload, n_burn, target_seconds, rank_offset=0):
     from transcriptioncycleinference_b200 import setup_cell
 
     cons = c_oracle.Construct.from_dict(forward_literal.CONSTRUCTS["P2P-MS2v5-LacZ-PP7v4"])
-    cores = c_oracle.max_threads()
+    # all the host cores this process may use (torchrun exports OMP_NUM_THREADS=1: ask the OS, not OpenMP)
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
 
     class HostCells:                      # the bits of engine.Cells that chain_inputs needs
         def __init__(s):
@@ -174,6 +178,7 @@ def run_ours(args, g):
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["NCCL_DEBUG"] = "WARN"            # keep NCCL's version banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():

@@ -29,6 +29,26 @@ def test_forward_golden_vectors(gpu_cells, results_npz):
     assert worst < 1e-12, worst
 
 
+def test_ss_slow_elongation_long_ramps(gpu_cells, cells_npz, orc):
+    """v -> 0: the ramp of the response spans tens to all of the lags (a regime real chains wander into: a cell whose
+    posterior has a mode at v ~ 0.01).  The O(1) prefix-sum form of the ramp (counts K and first moments S) must agree
+    with the literal m x n oracle there too."""
+    co, cons = orc
+    rng = np.random.default_rng(5)
+    n = 12000
+    cid = rng.integers(0, 299, n).astype(np.int32)
+    th = np.zeros((n, gpu_cells.ld))
+    for i, c in enumerate(cid):
+        N = int(cells_npz["N"][c]); th[i, :7 + N] = random_theta(rng, N, False)
+        th[i, 0] = 10.0 ** rng.uniform(-3.0, -0.3)           # v in [0.001, 0.5] kb/min
+        th[i, 1] = rng.uniform(0.0, 20.0)                     # tau over its whole range: L = L0 + tau v
+    ref = co.ss_batch(cons, cells_npz, cid, th)
+    for algo in (1, 0):
+        got = gpu_cells.ss_batch(cid, th, algo=algo)
+        rel = np.abs(got - ref) / np.maximum(np.abs(ref), 1e-300)
+        assert int((rel >= TOL).sum()) <= 1, (algo, rel.max())
+
+
 @pytest.mark.parametrize("algo", [0, 1])
 def test_ss_recorded_states(gpu_cells, chains_npz, cells_npz, orc, algo):
     """The 2 990 parameter vectors the reference itself recorded (MCMCchain) x their cell's data."""

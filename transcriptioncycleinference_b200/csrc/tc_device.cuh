@@ -183,10 +183,10 @@ struct GlobCell {         // the same view straight onto the device-resident dat
     __device__ __forceinline__ int ik(int i) const { return p_ik[i]; }
 };
 struct Work {             // one warp's forward-model scratch (offsets into tc_smem), each [N+2]
-    int K, n, G1, G2, F1, F2, thr;
+    int K, n, S, F1, F2, thr;
 };
 
-__host__ __device__ inline int work_doubles(int N) { return 6 * (N + 2) + 4 + 1; }
+__host__ __device__ inline int work_doubles(int N) { return 5 * (N + 2) + 4 + 1; }
 __host__ __device__ inline int cell_doubles(int N) { return 5 * (N + 1) + (N + 2) / 2 + 1; }
 
 // carve from offset `o` (doubles); returns the next free offset
@@ -207,8 +207,7 @@ __device__ inline int carve_work(int o, int N, Work &w)
     w.thr = o; o += 4;
     w.K = o; o += N + 2;
     w.n = o; o += N + 2;
-    w.G1 = o; o += N + 2;
-    w.G2 = o; o += N + 2;
+    w.S = o; o += N + 2;
     w.F1 = o; o += N + 2;
     w.F2 = o; o += N + 2;
     return o;
@@ -297,6 +296,9 @@ __device__ __noinline__ void scan_counts_sequential(Cell cv, Vec th, double R, d
 // warp scans per pass; if any partial sum lands within 1e-7 of an integer — where a different
 // association could flip a floor — lane 0 redoes the sum sequentially.  Error bound of either
 // order: (N-1) * eps * max(c) < 400 * 1.1e-16 * 3e4 << 1e-7, so the two paths agree otherwise.
+#ifndef TC_SS_UNR
+#define TC_SS_UNR 2         // time points per lane per pass of the forward model (unroll-and-jam factor; 4 doubles the code for no gain)
+#endif
 template <class Cell, class Vec>
 __device__ __forceinline__ void scan_counts(const Cell &cv, const Vec &th, double R, double ton, const Work &w,
                                             bool force_sequential)
@@ -308,25 +310,25 @@ __device__ __forceinline__ void scan_counts(const Cell &cv, const Vec &th, doubl
         double carry = 0.0, fprev = 0.0;           // fprev: floor of the last element of the previous row
         bool risky = false;
 #pragma unroll 1
-        for (int r0 = 0; r0 < n; r0 += 128) {
-            double v[4], tot[4];
+        for (int r0 = 0; r0 < n; r0 += 32 * TC_SS_UNR) {
+            double v[TC_SS_UNR], tot[TC_SS_UNR];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < TC_SS_UNR; ++u) {
                 const int i = r0 + 32 * u + lane;
                 v[u] = i < n ? load_increment(cv, th, i, R, ton) : 0.0;
             }
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < TC_SS_UNR; ++u) {
                     const double up = __shfl_up_sync(0xffffffffu, v[u], o);
                     if (lane >= o) v[u] = __dadd_rn(v[u], up);
                 }
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) tot[u] = __shfl_sync(0xffffffffu, v[u], 31);
+            for (int u = 0; u < TC_SS_UNR; ++u) tot[u] = __shfl_sync(0xffffffffu, v[u], 31);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < TC_SS_UNR; ++u) {
                 const int i = r0 + 32 * u + lane;
                 const double c = __dadd_rn(carry, v[u]);
                 const double f = floor(c);
@@ -349,6 +351,40 @@ __device__ __forceinline__ void scan_counts(const Cell &cv, const Vec &th, doubl
 #pragma unroll 1
         for (int i = lane; i < n; i += 32) tc_smem[w.n + i] = tc_smem[w.K + i + 1] - tc_smem[w.K + i];
     }
+}
+
+// First moments of the cohort sizes by ONE warp: S[m] = sum_{i<m} i n_i, m = 0..N-1 (exact: integers, 32-bit
+// integer shuffles).  With K[m] = sum_{i<m} n_i they give any ramp sum in O(1):
+//   sum_{i=a}^{b} (j - i) n_i = j (K[b+1] - K[a]) - (S[b+1] - S[a]).
+__device__ __forceinline__ void scan_moments(int N, const Work &w)
+{
+    const int lane = threadIdx.x & 31;
+    const int n = N - 1;
+    int carry = 0;
+#pragma unroll 1
+    for (int r0 = 0; r0 < n; r0 += 32 * TC_SS_UNR) {
+        int q[TC_SS_UNR];
+#pragma unroll
+        for (int u = 0; u < TC_SS_UNR; ++u) {
+            const int i = r0 + 32 * u + lane;
+            q[u] = i < n ? i * (int)tc_smem[w.n + i] : 0;
+        }
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll
+            for (int u = 0; u < TC_SS_UNR; ++u) {
+                const int up = __shfl_up_sync(0xffffffffu, q[u], o);
+                if (lane >= o) q[u] += up;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < TC_SS_UNR; ++u) {
+            const int i = r0 + 32 * u + lane;
+            if (i < n) tc_smem[w.S + i + 1] = (double)(carry + q[u]);
+            carry += __shfl_sync(0xffffffffu, q[u], 31);
+        }
+    }
+    if (lane == 0) tc_smem[w.S] = 0.0;
 }
 
 // smallest lag in [1, N] with v*(d*lag) > x (strict) or >= x; N when none.  inv_vd = 1/(v d) only seeds
@@ -417,6 +453,7 @@ __device__ __noinline__ double ss_eval(const tc_construct &C, Cell cv, Vec th, W
     // (a) loaded-polymerase counts K and cohort sizes n
     scan_counts(cv, th, R, ton, w, seq_scan);
     __syncwarp();
+    if (algo == TC_ALGO_TOEPLITZ) { scan_moments(N, w); __syncwarp(); }
     SS_MARK(0);
     // (b) fluorescence per time point, one loop set at a time: the basal clamp sits inside the
     //     per-set loop in the reference (GetFluorFromPolPos.m:47,57,69)
@@ -438,48 +475,34 @@ __device__ __noinline__ double ss_eval(const tc_construct &C, Cell cv, Vec th, W
                 thr[lane] = first_lag(v, cv.d, inv_vd, x, N, (q & 1) == 0);        // >s, >=e, >e, >=L
             }
             const double sc1 = f1 / (e1 - s1), sc2 = f2 / (e2 - s2);      // overlaps with the lanes above
+            const double vd = v * cv.d;
             __syncwarp();
             const int4 t1 = *reinterpret_cast<const int4 *>(thr), t2 = *reinterpret_cast<const int4 *>(thr + 4);
             const int la1 = t1.x, le1 = t1.y, lb1 = t1.z, lL1 = t1.w;
             const int la2 = t2.x, le2 = t2.y, lb2 = t2.z, lL2 = t2.w;
-            // ramp part of the per-lag response table
-#pragma unroll 1
-            for (int lag = la1 + lane; lag < le1; lag += 32) tc_smem[w.G1 + lag] = (v * (cv.d * (double)lag) - s1) * sc1;
-#pragma unroll 1
-            for (int lag = la2 + lane; lag < le2; lag += 32) tc_smem[w.G2 + lag] = (v * (cv.d * (double)lag) - s2) * sc2;
-            __syncwarp();
             SS_MARK(1);
-            // four time points per lane at once (unroll-and-jam): 8 independent FMA chains, the
-            // response table is read once per lag
+            // Per time point j, both parts of the response in O(1) from the prefix sums K (counts) and S (first moments):
+            //   ramp,    lags [la, min(le-1, j)]:  sc (v d sum lag n[j-lag] - s sum n[j-lag])   (cost independent of v: a chain
+            //            that wanders to v -> 0, where the ramp spans every lag, is no slower than any other)
+            //   plateau, lags [lb, min(lL-1, j)]:  whole polymerases -> exact count
 #pragma unroll 1
-            for (int jb = lane; jb < N; jb += 128) {
-                double a1[4], a2[4];
-                int l1[4], l2[4], len = 0;
+            for (int jb = lane; jb < N; jb += 32 * TC_SS_UNR) {
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int j = jb + 32 * u;
-                    a1[u] = 0.0; a2[u] = 0.0;
-                    l1[u] = j < N ? min(le1 - 1, j) - la1 + 1 : 0;
-                    l2[u] = j < N ? min(le2 - 1, j) - la2 + 1 : 0;
-                    len = max(len, max(l1[u], l2[u]));
-                }
-                const int n1o = w.n + (jb - la1), n2o = w.n + (jb - la2);
-#pragma unroll 1
-                for (int t = 0; t < len; ++t) {
-                    const double g1 = la1 + t < le1 ? tc_smem[w.G1 + la1 + t] : 0.0;
-                    const double g2 = la2 + t < le2 ? tc_smem[w.G2 + la2 + t] : 0.0;
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        if (t < l1[u]) a1[u] = fma(tc_smem[n1o + 32 * u - t], g1, a1[u]);
-                        if (t < l2[u]) a2[u] = fma(tc_smem[n2o + 32 * u - t], g2, a2[u]);
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < TC_SS_UNR; ++u) {
                     const int j = jb + 32 * u;
                     if (j < N) {
-                        double c1 = a1[u], c2 = a2[u];
-                        // plateau: cohorts with lag in [lb, lL) are whole polymerases -> exact count
+                        double c1 = 0.0, c2 = 0.0;
+                        const int lh1 = min(le1 - 1, j), lh2 = min(le2 - 1, j);
+                        if (lh1 >= la1) {
+                            const double dK = tc_smem[w.K + j - la1 + 1] - tc_smem[w.K + j - lh1];
+                            const double dS = tc_smem[w.S + j - la1 + 1] - tc_smem[w.S + j - lh1];
+                            c1 = sc1 * (vd * ((double)j * dK - dS) - s1 * dK);
+                        }
+                        if (lh2 >= la2) {
+                            const double dK = tc_smem[w.K + j - la2 + 1] - tc_smem[w.K + j - lh2];
+                            const double dS = tc_smem[w.S + j - la2 + 1] - tc_smem[w.S + j - lh2];
+                            c2 = sc2 * (vd * ((double)j * dK - dS) - s2 * dK);
+                        }
                         if (j >= lb1 && lb1 < lL1) c1 = fma(f1, tc_smem[w.K + j - lb1 + 1] - tc_smem[w.K + max(j - lL1 + 1, 0)], c1);
                         if (j >= lb2 && lb2 < lL2) c2 = fma(f2, tc_smem[w.K + j - lb2 + 1] - tc_smem[w.K + max(j - lL2 + 1, 0)], c2);
                         if (s > 0) { c1 += tc_smem[w.F1 + j]; c2 += tc_smem[w.F2 + j]; }
@@ -504,10 +527,12 @@ __device__ __noinline__ double ss_eval(const tc_construct &C, Cell cv, Vec th, W
     //     SumofSquares...m:51-64
     double acc = 0.0;
 #pragma unroll 1
-    for (int jb = lane; jb < N; jb += 128) {
-        double pa[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int jb = lane; jb < N; jb += 32 * TC_SS_UNR) {
+        double pa[TC_SS_UNR];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < TC_SS_UNR; ++u) pa[u] = 0.0;
+#pragma unroll
+        for (int u = 0; u < TC_SS_UNR; ++u) {
             const int j = jb + 32 * u;
             const int k = j < N ? cv.ik(j) : -1;
             if (k >= 0) {
@@ -520,7 +545,8 @@ __device__ __noinline__ double ss_eval(const tc_construct &C, Cell cv, Vec th, W
                 if (r2 == r2) pa[u] = fma(r2, r2, pa[u]);
             }
         }
-        acc += (pa[0] + pa[1]) + (pa[2] + pa[3]);
+#pragma unroll
+        for (int u = 0; u < TC_SS_UNR; ++u) acc += pa[u];
     }
     SS_MARK(3);
     acc = warp_sum(acc);
