@@ -450,6 +450,7 @@ __device__ __noinline__ double ss_eval(const tc_construct &C, Cell cv, Vec th, W
 #ifdef TC_SS_PROFILE
     long long tp__ = clock64();
 #endif
+    const double vd = v * cv.d, inv_vd = 1.0 / vd;              // started here: the division overlaps with the scan
     // (a) loaded-polymerase counts K and cohort sizes n
     scan_counts(cv, th, R, ton, w, seq_scan);
     __syncwarp();
@@ -468,14 +469,12 @@ __device__ __noinline__ double ss_eval(const tc_construct &C, Cell cv, Vec th, W
             // ramp = [la, le), plateau = [lb, lL); lanes 0-3: MS2, lanes 4-7: PP7
             int *thr = reinterpret_cast<int *>(tc_smem + w.thr);
             if (lane < 8) {
-                const double inv_vd = 1.0 / (v * cv.d);
                 const bool c2 = lane >= 4;
                 const int q = lane & 3;
                 const double x = q == 0 ? (c2 ? s2 : s1) : (q == 3 ? (c2 ? L2 : L1) : (c2 ? e2 : e1));
                 thr[lane] = first_lag(v, cv.d, inv_vd, x, N, (q & 1) == 0);        // >s, >=e, >e, >=L
             }
             const double sc1 = f1 / (e1 - s1), sc2 = f2 / (e2 - s2);      // overlaps with the lanes above
-            const double vd = v * cv.d;
             __syncwarp();
             const int4 t1 = *reinterpret_cast<const int4 *>(thr), t2 = *reinterpret_cast<const int4 *>(thr + 4);
             const int la1 = t1.x, le1 = t1.y, lb1 = t1.z, lL1 = t1.w;
@@ -485,27 +484,29 @@ __device__ __noinline__ double ss_eval(const tc_construct &C, Cell cv, Vec th, W
             //   ramp,    lags [la, min(le-1, j)]:  sc (v d sum lag n[j-lag] - s sum n[j-lag])   (cost independent of v: a chain
             //            that wanders to v -> 0, where the ramp spans every lag, is no slower than any other)
             //   plateau, lags [lb, min(lL-1, j)]:  whole polymerases -> exact count
+            //   Branch-free: a part that is absent gets the index pair (0, 0), i.e. an empty prefix difference.
 #pragma unroll 1
             for (int jb = lane; jb < N; jb += 32 * TC_SS_UNR) {
 #pragma unroll
                 for (int u = 0; u < TC_SS_UNR; ++u) {
                     const int j = jb + 32 * u;
-                    if (j < N) {
-                        double c1 = 0.0, c2 = 0.0;
-                        const int lh1 = min(le1 - 1, j), lh2 = min(le2 - 1, j);
-                        if (lh1 >= la1) {
-                            const double dK = tc_smem[w.K + j - la1 + 1] - tc_smem[w.K + j - lh1];
-                            const double dS = tc_smem[w.S + j - la1 + 1] - tc_smem[w.S + j - lh1];
-                            c1 = sc1 * (vd * ((double)j * dK - dS) - s1 * dK);
-                        }
-                        if (lh2 >= la2) {
-                            const double dK = tc_smem[w.K + j - la2 + 1] - tc_smem[w.K + j - lh2];
-                            const double dS = tc_smem[w.S + j - la2 + 1] - tc_smem[w.S + j - lh2];
-                            c2 = sc2 * (vd * ((double)j * dK - dS) - s2 * dK);
-                        }
-                        if (j >= lb1 && lb1 < lL1) c1 = fma(f1, tc_smem[w.K + j - lb1 + 1] - tc_smem[w.K + max(j - lL1 + 1, 0)], c1);
-                        if (j >= lb2 && lb2 < lL2) c2 = fma(f2, tc_smem[w.K + j - lb2 + 1] - tc_smem[w.K + max(j - lL2 + 1, 0)], c2);
-                        if (s > 0) { c1 += tc_smem[w.F1 + j]; c2 += tc_smem[w.F2 + j]; }
+                    const bool in = j < N;
+                    const int jj = in ? j : 0;
+                    const double dj = (double)jj;
+                    const int lh1 = min(le1 - 1, jj), lh2 = min(le2 - 1, jj);
+                    const bool r1ok = lh1 >= la1, r2ok = lh2 >= la2;
+                    const bool p1ok = jj >= lb1 && lb1 < lL1, p2ok = jj >= lb2 && lb2 < lL2;
+                    const int a1i = r1ok ? jj - la1 + 1 : 0, b1i = r1ok ? jj - lh1 : 0;
+                    const int a2i = r2ok ? jj - la2 + 1 : 0, b2i = r2ok ? jj - lh2 : 0;
+                    const int p1a = p1ok ? jj - lb1 + 1 : 0, p1b = p1ok ? max(jj - lL1 + 1, 0) : 0;
+                    const int p2a = p2ok ? jj - lb2 + 1 : 0, p2b = p2ok ? max(jj - lL2 + 1, 0) : 0;
+                    const double dK1 = tc_smem[w.K + a1i] - tc_smem[w.K + b1i], dS1 = tc_smem[w.S + a1i] - tc_smem[w.S + b1i];
+                    const double dK2 = tc_smem[w.K + a2i] - tc_smem[w.K + b2i], dS2 = tc_smem[w.S + a2i] - tc_smem[w.S + b2i];
+                    const double pl1 = tc_smem[w.K + p1a] - tc_smem[w.K + p1b], pl2 = tc_smem[w.K + p2a] - tc_smem[w.K + p2b];
+                    double c1 = fma(f1, pl1, sc1 * (vd * (dj * dK1 - dS1) - s1 * dK1));
+                    double c2 = fma(f2, pl2, sc2 * (vd * (dj * dK2 - dS2) - s2 * dK2));
+                    if (s > 0) { c1 += tc_smem[w.F1 + jj]; c2 += tc_smem[w.F2 + jj]; }
+                    if (in) {
                         tc_smem[w.F1 + j] = c1 < b1 ? b1 : c1;                  // :57
                         tc_smem[w.F2 + j] = c2 < b2 ? b2 : c2;                  // :69
                     }
@@ -534,16 +535,17 @@ __device__ __noinline__ double ss_eval(const tc_construct &C, Cell cv, Vec th, W
 #pragma unroll
         for (int u = 0; u < TC_SS_UNR; ++u) {
             const int j = jb + 32 * u;
-            const int k = j < N ? cv.ik(j) : -1;
-            if (k >= 0) {
-                const double wj = cv.iw(j);
-                const double m1 = A * tc_smem[w.F1 + k], m1n = A * tc_smem[w.F1 + k + 1];
-                const double r1 = cv.ms2(j) - (m1 + wj * (m1n - m1));
-                const double f2k = tc_smem[w.F2 + k];
-                const double r2 = cv.pp7(j) - (f2k + wj * (tc_smem[w.F2 + k + 1] - f2k));
-                if (r1 == r1) pa[u] = fma(r1, r1, pa[u]);                      // nansum
-                if (r2 == r2) pa[u] = fma(r2, r2, pa[u]);
-            }
+            const int jj = j < N ? j : 0;
+            const int k = j < N ? cv.ik(jj) : -1;                               // -1: outside the model grid (interp1 -> NaN)
+            const int kk = k >= 0 ? k : 0;
+            const double wj = cv.iw(jj);
+            const double m1 = A * tc_smem[w.F1 + kk], m1n = A * tc_smem[w.F1 + kk + 1];
+            double r1 = cv.ms2(jj) - (m1 + wj * (m1n - m1));
+            const double f2k = tc_smem[w.F2 + kk];
+            double r2 = cv.pp7(jj) - (f2k + wj * (tc_smem[w.F2 + kk + 1] - f2k));
+            r1 = (k >= 0 && r1 == r1) ? r1 : 0.0;                               // nansum
+            r2 = (k >= 0 && r2 == r2) ? r2 : 0.0;
+            pa[u] = fma(r2, r2, fma(r1, r1, pa[u]));
         }
 #pragma unroll
         for (int u = 0; u < TC_SS_UNR; ++u) acc += pa[u];

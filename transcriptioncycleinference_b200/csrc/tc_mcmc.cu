@@ -349,15 +349,17 @@ struct ChainCtx {
 // storage, and the distinct-row buffer of the current covariance block (row + weight); then, when
 // so >= 0, move the state: x += increment at tc_smem[so + 2 i].  Every thread owns the indices i = tid, tid+256, ..
 // so the whole thing is one pass.  The caller accounts for wcnt / ndist with the same formulas.
-__device__ __noinline__ void flush_run(const RunArgs &a, const ChainCtx &cx, int r0, int r1, double wcnt, int ndist, int so)
+__device__ __noinline__ void flush_run(const RunArgs &a, const ChainCtx &cx, int r0, int r1, double wcnt, int ndist, int so, int t0)
 {
-    const int tid = threadIdx.x, npar = cx.npar;
+    // threads t0 .. DRAM_THREADS-1 take part (t0 = 32 at an accept: warp 0 writes the per-row scalars meanwhile)
+    const int tid = (int)threadIdx.x - t0, nthr = DRAM_THREADS - t0, npar = cx.npar;
+    if (tid < 0) return;
     const int m_c = r1 - r0, rs = max(r0, cx.first_row), m_w = r1 - rs;
     const bool cov = a.do_cov && m_c > 0;
     const double nn = wcnt + m_w, f1 = m_w > 0 ? m_w / nn : 0.0, f2 = m_w > 0 ? wcnt * m_w / nn : 0.0;
     double *grow = cov ? cx.gRows + (size_t)ndist * cx.ld : nullptr;
 #pragma unroll 1
-    for (int i = tid; i < npar; i += DRAM_THREADS) {
+    for (int i = tid; i < npar; i += nthr) {
         const double xo = cx.x[i];
         if (m_w > 0) {
             const double d1 = xo - cx.wmean[i];
@@ -431,6 +433,7 @@ __device__ __noinline__ void generate(const RunArgs &a, const ChainCtx &cx, int 
             if (tid == 0) {
                 sc[0] = a.u1[(size_t)cx.ch * a.nsimu + st]; sc[1] = a.u2[(size_t)cx.ch * a.nsimu + st];
                 sc[2] = a.chi2[(size_t)cx.ch * a.nsimu + st];
+                sc[5] = tc_log(sc[0]);
             }
         }
     } else {
@@ -444,6 +447,7 @@ __device__ __noinline__ void generate(const RunArgs &a, const ChainCtx &cx, int 
             sc[0] = u01(ru.x, ru.y);
             sc[1] = u01(ru.z, ru.w);
             sc[2] = a.updatesigma ? chi2_draw(a.seed, cx.uid, st, a.N0 + 2.0 * cx.N) : 1.0;
+            sc[5] = tc_log(sc[0]);                                  // stage 1 is decided in the log domain
         }
         __syncwarp();
         const int npairs = (npar + 1) >> 1;
@@ -598,51 +602,24 @@ __device__ __noinline__ void cand_bounds(const ChainCtx &cx, int k, int C, Cand 
     }
 }
 
-// Round phase D: the accept/reject arithmetic of ONE step (one lane), given the SS of its proposals, from state
-// (ss, pri) seeing sigma2 = s2p.                                             mcmcstat DRAM: SURVEY.md 3.2
-__device__ __noinline__ StepOut resolve_step(const RunArgs &a, const double *sc, int oob, double pr1, double pr2, double ss1v,
-                                             double ss2v, double ss, double pri, double s2p)
+// Round phase D, part 2: the delayed-rejection arithmetic of ONE step (one lane) whose first stage rejected, from state
+// (ss, pri) seeing sigma2 = s2p.  The three exponentials are evaluated in one interleaved body (an unused one may see
+// garbage or Inf: it is never read):
+//   a12 = exp(-1/2 ((ss1-ss)/s2 + pr1-pri)), a32 = exp(-1/2 ((ss1-ss2)/s2 + pr1-pr2)), exp(l2 + q1)
+//                                                                             mcmcstat DRAM: SURVEY.md 3.2
+__device__ __noinline__ int resolve_dr(const double *sc, bool o1, double x12, double pr1, double pr2, double ss1, double ss2,
+                                       double ss, double pri, double s2p)
 {
-    // The three acceptance exponentials are evaluated up front, in one interleaved body, whether or not the step needs
-    // them all (an unused one may see garbage or Inf: it is never read):
-    //   a12 = exp(-1/2 ((ss1-ss)/s2 + pr1-pri)), a32 = exp(-1/2 ((ss1-ss2)/s2 + pr1-pr2)), exp(l2 + q1)
-    const bool o1 = (oob & 1) != 0, o2 = (oob & 2) != 0;
-    const double ss1 = o1 ? INFINITY : ss1v;
-    if (o1) pr1 = 0.0;
-    const double ss2 = ss2v;
     const double q1 = -0.5 * (sc[3] - sc[4]);
     double e12, e32, e13;
-    tc_exp3(-0.5 * ((ss1 - ss) / s2p + pr1 - pri), -0.5 * ((ss1 - ss2) / s2p + pr1 - pr2), -0.5 * ((ss2 - ss) / s2p + pr2 - pri) + q1, e12, e32, e13);
-    StepOut r;
-    int fl = 0, accept = 0, nev = 0, noob = 0;
-    double a12;
-    if (o1) {
-        a12 = 0.0; fl |= TC_FL_OOB1; ++noob;
-    } else {
-        ++nev;
-        a12 = e12;
-        if (a12 <= 0.0) accept = 0;
-        else if (a12 >= 1.0) accept = 1;
-        else accept = a12 > sc[0];
-    }
-    double ssn = ss1, prin = pr1;
-    if (!accept && a.ntry >= 2) {                                // delayed rejection with R/drscale
-        fl |= TC_FL_DR;
-        if (o2) {
-            fl |= TC_FL_OOB2; ++noob;
-        } else {
-            ++nev;
-            double a32 = e32;
-            a32 = a32 > 1.0 ? 1.0 : a32;
-            if (!(a32 >= 0.0)) a32 = 0.0;
-            double a13 = e13 * (1.0 - a32) / (1.0 - a12);
-            a13 = a13 > 1.0 ? 1.0 : a13;
-            if ((a13 >= 1.0) || (a13 > sc[1])) { accept = 2; fl |= TC_FL_STAGE2; ssn = ss2; prin = pr2; }
-        }
-    }
-    if (accept) fl |= TC_FL_ACCEPT;
-    r.acc = accept; r.fl = fl; r.nev = nev; r.noob = noob; r.ssn = ssn; r.prin = prin;
-    return r;
+    tc_exp3(x12, -0.5 * ((ss1 - ss2) / s2p + pr1 - pr2), -0.5 * ((ss2 - ss) / s2p + pr2 - pri) + q1, e12, e32, e13);
+    const double a12 = o1 ? 0.0 : e12;
+    double a32 = e32;
+    a32 = a32 > 1.0 ? 1.0 : a32;
+    if (!(a32 >= 0.0)) a32 = 0.0;
+    double a13 = e13 * (1.0 - a32) / (1.0 - a12);
+    a13 = a13 > 1.0 ? 1.0 : a13;
+    return ((a13 >= 1.0) || (a13 > sc[1])) ? 1 : 0;
 }
 
 // Adaptation after the step with isimu (a multiple of adaptint).  The block of the last adaptint chain rows
@@ -1068,14 +1045,43 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
             //    sigma2 a step sees is the draw made at the end of the previous step from the unchanged ss).  Every warp
             //    computes the same outcomes, so no barrier is needed before the commit (and a warp running this alone is
             //    no faster: measured).
+            //    Stage 1 is decided in the log domain (a12 > u  <=>  x12 > log u, log u drawn with the step's randomness), so
+            //    a step that accepts at once costs one division and no exponential; only the steps BEFORE the first such
+            //    accept can matter, and only they run the delayed-rejection arithmetic.
             StepOut so_;
             so_.acc = 0; so_.fl = 0; so_.nev = 0; so_.noob = 0; so_.ssn = 0.0; so_.prin = 0.0;
-            if (lane < nsteps) {
-                double s2p = sig2;
+            const bool act = lane < nsteps;
+            const bool o1 = (c_oob & 1) != 0, o2 = (c_oob & 2) != 0;
+            double s2p = sig2, x12 = 0.0, pr1 = 0.0, pr2 = 0.0, ss1 = INFINITY, ss2 = 0.0;
+            const double *scp = cx.slot_sc(k + (act ? lane : 0));
+            bool acc1 = false;
+            if (act) {
                 if (lane > 0 && a.updatesigma) s2p = (a.N0 * a.S20 + ss) / cx.slot_sc(k + lane - 1)[2];
-                so_ = resolve_step(a, cx.slot_sc(k + lane), c_oob, s_cand[lane].pr1, s_cand[lane].pr2, s_ssv[2 * lane], s_ssv[2 * lane + 1],
-                                   ss, pri, s2p);
+                pr2 = s_cand[lane].pr2; ss2 = s_ssv[2 * lane + 1];
+                if (!o1) {
+                    pr1 = s_cand[lane].pr1; ss1 = s_ssv[2 * lane];
+                    x12 = -0.5 * ((ss1 - ss) / s2p + pr1 - pri);
+                    acc1 = x12 >= 0.0 || x12 > scp[5];
+                }
             }
+            const unsigned m1 = __ballot_sync(0xffffffffu, act && acc1);
+            const int f1 = m1 ? __ffs(m1) - 1 : nsteps;                      // first step accepting at stage 1
+            if (act && lane <= f1) {
+                so_.ssn = ss1; so_.prin = pr1;
+                if (o1) { so_.fl |= TC_FL_OOB1; so_.noob = 1; } else so_.nev = 1;
+                if (acc1) so_.acc = 1;
+            }
+            if (f1 > 0 && a.ntry >= 2) {                                    // warp-uniform: someone needs the second stage
+                if (act && lane < f1) {
+                    so_.fl |= TC_FL_DR;
+                    if (o2) { so_.fl |= TC_FL_OOB2; ++so_.noob; }
+                    else {
+                        ++so_.nev;
+                        if (resolve_dr(scp, o1, x12, pr1, pr2, ss1, ss2, ss, pri, s2p)) { so_.acc = 2; so_.fl |= TC_FL_STAGE2; so_.ssn = ss2; so_.prin = pr2; }
+                    }
+                }
+            }
+            if (so_.acc) so_.fl |= TC_FL_ACCEPT;
             const unsigned amask = __ballot_sync(0xffffffffu, lane < nsteps && so_.acc != 0);
             const bool accd = amask != 0;
             const int first = accd ? __ffs(amask) - 1 : nsteps;
@@ -1087,7 +1093,7 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
             SUBP(20);
             if (accd) {
                 // close the run of the old state at row r_acc and move x by the accepted increment
-                flush_run(a, cx, run_r0, r_acc, wcnt, ndist, cx.slot_o(r_acc) + (acc_t == 2 ? 1 : 0));
+                flush_run(a, cx, run_r0, r_acc, wcnt, ndist, cx.slot_o(r_acc) + (acc_t == 2 ? 1 : 0), 32);
             }
             SUBP(21);
             if (warp == 0) {
@@ -1139,7 +1145,7 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
             if (a.adaptint > 0 && k % a.adaptint == 0) {
                 const int rr0 = st.run_r0, nd0 = st.ndist;
                 const double wc0 = st.wcnt;
-                flush_run(a, cx, rr0, k, wc0, nd0, -1);                     // close the run at the block boundary
+                flush_run(a, cx, rr0, k, wc0, nd0, -1, 0);                     // close the run at the block boundary
                 const int nd = nd0 + ((a.do_cov && k > rr0) ? 1 : 0);
                 const double rate = a.burnin_cumulative ? (double)st.rej / k : (double)st.reju / a.adaptint;
                 const double cov_n = st.cov_n;
@@ -1164,7 +1170,7 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
             // close the last run (the fit or the slice does not end on an adaptation boundary)
             const int rr0 = st.run_r0;
             const double wc0 = st.wcnt;
-            flush_run(a, cx, rr0, k, wc0, st.ndist, -1);
+            flush_run(a, cx, rr0, k, wc0, st.ndist, -1, 0);
             __syncthreads();
             if (tid == 0) { st.wcnt = wc0 + max(0, k - max(rr0, cx.first_row)); st.run_r0 = k; }
             __syncthreads();
