@@ -41,6 +41,9 @@ static int fail(int code, const std::string &msg)
 #define RING 16            // proposal increments are generated ahead of use, up to RING steps per call
 #define SS_WARPS 8
 #define SS_THREADS (32 * SS_WARPS)
+#ifndef SS_MIN_CTAS
+#define SS_MIN_CTAS 4          // 64 registers: 32 warps per SM hide the latency of streaming theta (measured +12 % over 2)
+#endif
 #define COV_RC 8           // rows of the chain block staged per pass of the scatter update
 #define COV_TPT 3          // 4x4 covariance tiles per thread (3*256 >= 595 tiles at npar = 136)
 
@@ -69,7 +72,7 @@ struct SsArgs {
 };
 
 // one warp per (cell, theta): no block barriers, cell data and theta read straight from HBM/L2
-__global__ void __launch_bounds__(SS_THREADS) ss_batch_kernel(const __grid_constant__ SsArgs a)
+__global__ void __launch_bounds__(SS_THREADS, SS_MIN_CTAS) ss_batch_kernel(const __grid_constant__ SsArgs a)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int base = warp * a.wsz;                          // this warp's scratch (offset into tc_smem)
