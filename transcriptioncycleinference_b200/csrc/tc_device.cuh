@@ -289,13 +289,17 @@ __device__ __noinline__ void scan_counts_sequential(Cell cv, Vec th, double R, d
     }
 }
 
-// Loaded-polymerase counts by ONE warp.  K[0] = 0, K[i+1] = floor(counter after step i), n[i] =
-// K[i+1]-K[i] (cohort loaded in step i)               ConstantElongationSim.m:53-61
-// floor() is discontinuous, so the running sum must give the same integers as the reference's
-// sequential order with separately rounded products (no FMA contraction).  Fast path: 4 interleaved
-// warp scans per pass; if any partial sum lands within 1e-7 of an integer — where a different
-// association could flip a floor — lane 0 redoes the sum sequentially.  Error bound of either
-// order: (N-1) * eps * max(c) < 400 * 1.1e-16 * 3e4 << 1e-7, so the two paths agree otherwise.
+// Loaded-polymerase counts and their prefix sums by ONE warp:
+//   K[0] = 0, K[i+1] = floor(counter after step i)   (= sum_{i'<=i} n_i')       ConstantElongationSim.m:53-61
+//   n[i] = K[i+1] - K[i]                               cohort loaded in step i
+//   S[m] = sum_{i<m} i n_i                             first moments (exact: integers, 32-bit integer shuffles)
+// With K and S any ramp sum is O(1):  sum_{i=a}^{b} (j - i) n_i = j (K[b+1] - K[a]) - (S[b+1] - S[a]).
+// floor() is discontinuous, so the running sum must give the same integers as the reference's sequential order
+// with separately rounded products (no FMA contraction).  Fast path: every lane owns 4 consecutive steps (local
+// prefix in the reference's own order), ONE warp scan of the lane totals per 128 steps; if any partial sum lands
+// within 1e-7 of an integer — where a different association could flip a floor — lane 0 redoes the sum
+// sequentially.  Error bound of either order: (N-1) * eps * max(c) < 400 * 1.1e-16 * 3e4 << 1e-7, so the two paths
+// agree otherwise.
 #ifndef TC_SS_UNR
 #define TC_SS_UNR 2         // time points per lane per pass of the forward model (unroll-and-jam factor; 4 doubles the code for no gain)
 #endif
@@ -307,42 +311,61 @@ __device__ __forceinline__ void scan_counts(const Cell &cv, const Vec &th, doubl
     const int n = cv.N - 1;                        // increments i = 0..n-1
     bool redo = force_sequential;
     if (!force_sequential) {
-        double carry = 0.0, fprev = 0.0;           // fprev: floor of the last element of the previous row
+        double carry = 0.0, fprev = 0.0;           // running counter / its floor at the end of the previous block of 128
+        int carryS = 0;
         bool risky = false;
 #pragma unroll 1
-        for (int r0 = 0; r0 < n; r0 += 32 * TC_SS_UNR) {
-            double v[TC_SS_UNR], tot[TC_SS_UNR];
+        for (int r0 = 0; r0 < n; r0 += 128) {
+            const int i0 = r0 + 4 * lane;
+            double p[4];
 #pragma unroll
-            for (int u = 0; u < TC_SS_UNR; ++u) {
-                const int i = r0 + 32 * u + lane;
-                v[u] = i < n ? load_increment(cv, th, i, R, ton) : 0.0;
-            }
+            for (int e = 0; e < 4; ++e) p[e] = i0 + e < n ? load_increment(cv, th, i0 + e, R, ton) : 0.0;
+            p[1] = __dadd_rn(p[0], p[1]); p[2] = __dadd_rn(p[1], p[2]); p[3] = __dadd_rn(p[2], p[3]);
+            double t = p[3];                       // inclusive scan of the lane totals
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-#pragma unroll
-                for (int u = 0; u < TC_SS_UNR; ++u) {
-                    const double up = __shfl_up_sync(0xffffffffu, v[u], o);
-                    if (lane >= o) v[u] = __dadd_rn(v[u], up);
-                }
+                const double up = __shfl_up_sync(0xffffffffu, t, o);
+                if (lane >= o) t = __dadd_rn(t, up);
             }
+            const double tot = __shfl_sync(0xffffffffu, t, 31);
+            double excl = __shfl_up_sync(0xffffffffu, t, 1);
+            if (lane == 0) excl = 0.0;
+            const double base = __dadd_rn(carry, excl);
+            double f[4];
 #pragma unroll
-            for (int u = 0; u < TC_SS_UNR; ++u) tot[u] = __shfl_sync(0xffffffffu, v[u], 31);
-#pragma unroll
-            for (int u = 0; u < TC_SS_UNR; ++u) {
-                const int i = r0 + 32 * u + lane;
-                const double c = __dadd_rn(carry, v[u]);
-                const double f = floor(c);
+            for (int e = 0; e < 4; ++e) {
+                const double c = __dadd_rn(base, p[e]);
+                f[e] = floor(c);
+                const double fr = c - f[e];
                 // c == 0: every increment so far is exactly 0 (they are all >= 0): exact in any order
-                risky |= (i < n) && (c != 0.0) && ((c - f < 1e-7) || (f + 1.0 - c < 1e-7));
-                // cohort size = f - (floor of the previous element): lane-1 of this row, or the end of the previous row
-                double fl = __shfl_up_sync(0xffffffffu, f, 1);
-                if (lane == 0) fl = fprev;
-                if (i < n) { tc_smem[w.K + i + 1] = f; tc_smem[w.n + i] = f - fl; }
-                fprev = __shfl_sync(0xffffffffu, f, 31);
-                carry = __dadd_rn(carry, tot[u]);
+                risky |= (i0 + e < n) && (c != 0.0) && (fr < 1e-7 || fr > 1.0 - 1e-7);
             }
+            double fl = __shfl_up_sync(0xffffffffu, f[3], 1);      // floor at the end of the previous lane
+            if (lane == 0) fl = fprev;
+            const double nn0 = f[0] - fl, nn1 = f[1] - f[0], nn2 = f[2] - f[1], nn3 = f[3] - f[2];
+            const int q0 = i0 < n ? i0 * (int)nn0 : 0;
+            const int q1 = q0 + (i0 + 1 < n ? (i0 + 1) * (int)nn1 : 0);
+            const int q2 = q1 + (i0 + 2 < n ? (i0 + 2) * (int)nn2 : 0);
+            const int q3 = q2 + (i0 + 3 < n ? (i0 + 3) * (int)nn3 : 0);
+            int ts = q3;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int up = __shfl_up_sync(0xffffffffu, ts, o);
+                if (lane >= o) ts += up;
+            }
+            const int totS = __shfl_sync(0xffffffffu, ts, 31);
+            int exS = __shfl_up_sync(0xffffffffu, ts, 1);
+            if (lane == 0) exS = 0;
+            exS += carryS;
+            if (i0 < n) { tc_smem[w.K + i0 + 1] = f[0]; tc_smem[w.n + i0] = nn0; tc_smem[w.S + i0 + 1] = (double)(exS + q0); }
+            if (i0 + 1 < n) { tc_smem[w.K + i0 + 2] = f[1]; tc_smem[w.n + i0 + 1] = nn1; tc_smem[w.S + i0 + 2] = (double)(exS + q1); }
+            if (i0 + 2 < n) { tc_smem[w.K + i0 + 3] = f[2]; tc_smem[w.n + i0 + 2] = nn2; tc_smem[w.S + i0 + 3] = (double)(exS + q2); }
+            if (i0 + 3 < n) { tc_smem[w.K + i0 + 4] = f[3]; tc_smem[w.n + i0 + 3] = nn3; tc_smem[w.S + i0 + 4] = (double)(exS + q3); }
+            fprev = __shfl_sync(0xffffffffu, f[3], 31);            // steps beyond n add exactly 0: lane 31 holds the block's last floor
+            carry = __dadd_rn(carry, tot);
+            carryS += totS;
         }
-        if (lane == 0) tc_smem[w.K] = 0.0;
+        if (lane == 0) { tc_smem[w.K] = 0.0; tc_smem[w.S] = 0.0; }
         redo = __any_sync(0xffffffffu, risky);
     }
     if (redo) {
@@ -350,41 +373,14 @@ __device__ __forceinline__ void scan_counts(const Cell &cv, const Vec &th, doubl
         __syncwarp();
 #pragma unroll 1
         for (int i = lane; i < n; i += 32) tc_smem[w.n + i] = tc_smem[w.K + i + 1] - tc_smem[w.K + i];
-    }
-}
-
-// First moments of the cohort sizes by ONE warp: S[m] = sum_{i<m} i n_i, m = 0..N-1 (exact: integers, 32-bit
-// integer shuffles).  With K[m] = sum_{i<m} n_i they give any ramp sum in O(1):
-//   sum_{i=a}^{b} (j - i) n_i = j (K[b+1] - K[a]) - (S[b+1] - S[a]).
-__device__ __forceinline__ void scan_moments(int N, const Work &w)
-{
-    const int lane = threadIdx.x & 31;
-    const int n = N - 1;
-    int carry = 0;
+        __syncwarp();
+        if (lane == 0) {
+            double sacc = 0.0;
+            tc_smem[w.S] = 0.0;
 #pragma unroll 1
-    for (int r0 = 0; r0 < n; r0 += 32 * TC_SS_UNR) {
-        int q[TC_SS_UNR];
-#pragma unroll
-        for (int u = 0; u < TC_SS_UNR; ++u) {
-            const int i = r0 + 32 * u + lane;
-            q[u] = i < n ? i * (int)tc_smem[w.n + i] : 0;
-        }
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-#pragma unroll
-            for (int u = 0; u < TC_SS_UNR; ++u) {
-                const int up = __shfl_up_sync(0xffffffffu, q[u], o);
-                if (lane >= o) q[u] += up;
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < TC_SS_UNR; ++u) {
-            const int i = r0 + 32 * u + lane;
-            if (i < n) tc_smem[w.S + i + 1] = (double)(carry + q[u]);
-            carry += __shfl_sync(0xffffffffu, q[u], 31);
+            for (int i = 0; i < n; ++i) { sacc += (double)i * tc_smem[w.n + i]; tc_smem[w.S + i + 1] = sacc; }
         }
     }
-    if (lane == 0) tc_smem[w.S] = 0.0;
 }
 
 // smallest lag in [1, N] with v*(d*lag) > x (strict) or >= x; N when none.  inv_vd = 1/(v d) only seeds
@@ -454,7 +450,6 @@ __device__ __noinline__ double ss_eval(const tc_construct &C, Cell cv, Vec th, W
     // (a) loaded-polymerase counts K and cohort sizes n
     scan_counts(cv, th, R, ton, w, seq_scan);
     __syncwarp();
-    if (algo == TC_ALGO_TOEPLITZ) { scan_moments(N, w); __syncwarp(); }
     SS_MARK(0);
     // (b) fluorescence per time point, one loop set at a time: the basal clamp sits inside the
     //     per-set loop in the reference (GetFluorFromPolPos.m:47,57,69)
