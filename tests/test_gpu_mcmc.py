@@ -183,3 +183,29 @@ def test_replay_option_variants(gpu_cells, cells_npz, orc, variant):
         assert np.array_equal(out["flags"][i], ref["flags"]), (variant, i)
         np.testing.assert_allclose(out["chain"][i][:, :npar], ref["chain"], rtol=0, atol=1e-7)
         np.testing.assert_allclose(out["s2chain"][i], ref["s2chain"], rtol=1e-9)
+
+
+def test_posterior_means_agree_with_independent_cpu_chains(gpu_cells, cells_npz, orc):
+    """north_star's second correctness criterion — posterior means of v, tau, t_on, R (and sigma) agree within Monte
+    Carlo standard error — against the only long reference-algorithm chains that can exist here: the CPU oracle's,
+    run with ITS OWN random numbers (xorshift, not Philox).  12 chains per side on each of 3 cells, same x0 per
+    chain index; the standard error is the between-chain one, the bound is 4 combined standard errors."""
+    from transcriptioncycleinference_b200 import _lib
+    co, cons = orc
+    cells3 = np.array([12, 150, 270], dtype=np.int32)
+    per = 12
+    cc = np.repeat(cells3, per)
+    nsimu, burn = 5000, 2500
+    inputs = _setup(gpu_cells, cc, 71)
+    opts = _lib.default_opts(nsimu=nsimu, burnintime=burn, n_burn=burn, seed=4242)
+    gpu = gpu_cells.mcmc_run(opts, cc, *inputs, chain_uid=np.arange(cc.size, dtype=np.uint64) + 900)
+    cmean, _, csig, _ = co.run_chains(cons, cells_npz, co.default_opts(nsimu, burn), burn, cc, *inputs, seed=99, nthreads=0)
+    for ci in range(cells3.size):
+        s = slice(ci * per, (ci + 1) * per)
+        for name, col in (("v", 0), ("tau", 1), ("ton", 2), ("R", 6)):
+            g, c = gpu["mean"][s, col], cmean[s, col]
+            se = np.sqrt(g.var(ddof=1) / per + c.var(ddof=1) / per)
+            assert abs(g.mean() - c.mean()) <= 4.0 * se + 1e-9, (int(cells3[ci]), name, g.mean(), c.mean(), se)
+        g, c = gpu["sig"][s, 0], csig[s, 0]
+        se = np.sqrt(g.var(ddof=1) / per + c.var(ddof=1) / per)
+        assert abs(g.mean() - c.mean()) <= 4.0 * se + 1e-9, (int(cells3[ci]), "sigma", g.mean(), c.mean(), se)
