@@ -159,97 +159,140 @@ __device__ __forceinline__ void st_tile(double *p, const double (&t)[16])
     for (int e = 0; e < 8; ++e) reinterpret_cast<double2 *>(p)[e] = make_double2(t[2 * e], t[2 * e + 1]);
 }
 
-// In-place upper Cholesky (R'R = A) of the tiled matrix W (n padded to 4*nt4).  Right-looking, panels of two
-// tile rows (8 matrix rows): (1) every lane of warp 0 factors the 8x8 diagonal block redundantly in registers
-// (a chain of 8 dependent rsqrt's, no communication), (2) the panel to its right is solved column by
-// column (one thread per column), (3) the trailing tiles get the rank-8 update in registers.  Returns
-// false when a pivot is not positive.
-__device__ __noinline__ bool chol_tiled(int nt4, double *W, const unsigned short *tab, double *s_dinv, int *s_fail)
+// Factor the 8x8 diagonal block that starts at tile row b0 (one 4x4 tile when it is the last row of an odd nt4): every
+// lane of the calling warp factors it redundantly in registers (a chain of 8 dependent rsqrt's, no communication),
+// lanes 0-2 write the three tiles back, lane 0 the reciprocal pivots.
+__device__ __forceinline__ void chol_diag(int nt4, double *W, int b0, double *s_dinv, int *s_fail)
 {
-    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int lane = threadIdx.x & 31;
+    const bool two = b0 + 1 < nt4;
+    double *t00 = W + 16 * tidx(nt4, b0, b0);
+    double *t01 = two ? W + 16 * tidx(nt4, b0, b0 + 1) : nullptr;
+    double *t11 = two ? W + 16 * tidx(nt4, b0 + 1, b0 + 1) : nullptr;
+    double A[8][8];                                       // upper triangle of the block, A[r][c], r <= c
+    {
+        double q[16];
+        ld_tile(t00, q);
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = r; c < 4; ++c) A[r][c] = q[4 * r + c];
+        if (two) {
+            ld_tile(t01, q);
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) A[r][4 + c] = q[4 * r + c];
+            ld_tile(t11, q);
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = r; c < 4; ++c) A[4 + r][4 + c] = q[4 * r + c];
+        } else {
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int c = (r < 4 ? 4 : r); c < 8; ++c) A[r][c] = (r == c) ? 1.0 : 0.0;
+        }
+    }
+    bool bad = false;
+    double dinv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const double d = A[j][j];
+        if (!(d > 0.0)) bad = true;
+        // 1/sqrt(d): single-precision seed + two Newton steps in FP64 (full precision; the IEEE sqrt + divide pair is
+        // ~60 dependent instructions per pivot, and the 8 pivots of a block are a serial chain on one warp)
+        double ri = (double)rsqrtf((float)d);
+        const double hd = 0.5 * d;
+        ri = ri * fma(-hd * ri, ri, 1.5);
+        ri = ri * fma(-hd * ri, ri, 1.5);
+        dinv[j] = ri;
+        A[j][j] = d * ri;
+#pragma unroll
+        for (int c = j + 1; c < 8; ++c) A[j][c] *= ri;
+#pragma unroll
+        for (int r = j + 1; r < 8; ++r)
+#pragma unroll
+            for (int c = r; c < 8; ++c) A[r][c] = fma(-A[j][r], A[j][c], A[r][c]);
+    }
+    if (lane == 0) {
+        double q[16];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) q[4 * r + c] = c >= r ? A[r][c] : 0.0;
+        st_tile(t00, q);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s_dinv[j] = dinv[j];
+        if (bad) *s_fail = 1;
+    } else if (lane == 1 && two) {
+        double q[16];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) q[4 * r + c] = A[r][4 + c];
+        st_tile(t01, q);
+    } else if (lane == 2 && two) {
+        double q[16];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) q[4 * r + c] = c >= r ? A[4 + r][4 + c] : 0.0;
+        st_tile(t11, q);
+    }
+}
+
+// rank-8 update of trailing tile t = (bi, bj) by the panel at tile rows b0, b0+1: C -= R12(:,bi)' R12(:,bj)
+__device__ __forceinline__ void chol_tile_update(int nt4, double *W, int b0, int t, int bi, int bj)
+{
+    double ai[16], aj[16], c[16];
+    ld_tile(W + 16 * t, c);
+    ld_tile(W + 16 * tidx(nt4, b0, bi), ai);
+    ld_tile(W + 16 * tidx(nt4, b0, bj), aj);
+#pragma unroll
+    for (int p_ = 0; p_ < 4; ++p_)
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) c[4 * ii + jj] = fma(-ai[4 * p_ + ii], aj[4 * p_ + jj], c[4 * ii + jj]);
+    ld_tile(W + 16 * tidx(nt4, b0 + 1, bi), ai);
+    ld_tile(W + 16 * tidx(nt4, b0 + 1, bj), aj);
+#pragma unroll
+    for (int p_ = 0; p_ < 4; ++p_)
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) c[4 * ii + jj] = fma(-ai[4 * p_ + ii], aj[4 * p_ + jj], c[4 * ii + jj]);
+    st_tile(W + 16 * t, c);
+}
+
+// In-place upper Cholesky (R'R = A) of the tiled matrix W (n padded to 4*nt4).  Right-looking, panels of two
+// tile rows (8 matrix rows), with one panel of LOOK-AHEAD: per panel (1) the tiles to the right of the (already
+// factored) diagonal block are solved column by column (one thread per column); (2) the trailing tiles get the
+// rank-8 update in registers by warps 1-7 while warp 0 updates just the NEXT diagonal block and factors it — so
+// the chain of dependent rsqrt's never sits on the critical path of the other warps.  Returns false when a
+// pivot is not positive.
+__device__ __noinline__ bool chol_tiled(int nt4, double *W, const unsigned short *tab, double *s_dinv, int *s_fail, bool prof)
+{
+#ifdef TC_SUBPROF
+    long long tq = clock64();
+#define CHP(i) do { if (threadIdx.x == 0 && prof) { const long long t__ = clock64(); tc_subprof[i] += t__ - tq; tq = t__; } } while (0)
+#else
+#define CHP(i)
+#endif
+    const int tid = threadIdx.x, nthr = blockDim.x, warp = tid >> 5, lane = tid & 31;
     const int T = nt4 * (nt4 + 1) / 2;
     if (tid == 0) *s_fail = 0;
     __syncthreads();
+    if (warp == 0) chol_diag(nt4, W, 0, s_dinv, s_fail);
+    __syncthreads();
+    if (*s_fail) return false;                            // uniform
 #pragma unroll 1
-    for (int b0 = 0; b0 < nt4; b0 += 2) {
-        const bool two = b0 + 1 < nt4;                    // the last panel of an odd nt4 has one tile row
-        double *t00 = W + 16 * tidx(nt4, b0, b0);
-        double *t01 = two ? W + 16 * tidx(nt4, b0, b0 + 1) : nullptr;
-        double *t11 = two ? W + 16 * tidx(nt4, b0 + 1, b0 + 1) : nullptr;
-        if (tid < 32) {
-            double A[8][8];                               // upper triangle of the block, A[r][c], r <= c
-            {
-                double q[16];
-                ld_tile(t00, q);
-#pragma unroll
-                for (int r = 0; r < 4; ++r)
-#pragma unroll
-                    for (int c = r; c < 4; ++c) A[r][c] = q[4 * r + c];
-                if (two) {
-                    ld_tile(t01, q);
-#pragma unroll
-                    for (int r = 0; r < 4; ++r)
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) A[r][4 + c] = q[4 * r + c];
-                    ld_tile(t11, q);
-#pragma unroll
-                    for (int r = 0; r < 4; ++r)
-#pragma unroll
-                        for (int c = r; c < 4; ++c) A[4 + r][4 + c] = q[4 * r + c];
-                } else {
-#pragma unroll
-                    for (int r = 0; r < 8; ++r)
-#pragma unroll
-                        for (int c = (r < 4 ? 4 : r); c < 8; ++c) A[r][c] = (r == c) ? 1.0 : 0.0;
-                }
-            }
-            bool bad = false;
-            double dinv[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const double d = A[j][j];
-                if (!(d > 0.0)) bad = true;
-                const double ri = rsqrt(d);
-                dinv[j] = ri;
-                A[j][j] = d * ri;
-#pragma unroll
-                for (int c = j + 1; c < 8; ++c) A[j][c] *= ri;
-#pragma unroll
-                for (int r = j + 1; r < 8; ++r)
-#pragma unroll
-                    for (int c = r; c < 8; ++c) A[r][c] = fma(-A[j][r], A[j][c], A[r][c]);
-            }
-            if (tid == 0) {
-                double q[16];
-#pragma unroll
-                for (int r = 0; r < 4; ++r)
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) q[4 * r + c] = c >= r ? A[r][c] : 0.0;
-                st_tile(t00, q);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) s_dinv[j] = dinv[j];
-                if (bad) *s_fail = 1;
-            } else if (tid == 1 && two) {
-                double q[16];
-#pragma unroll
-                for (int r = 0; r < 4; ++r)
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) q[4 * r + c] = A[r][4 + c];
-                st_tile(t01, q);
-            } else if (tid == 2 && two) {
-                double q[16];
-#pragma unroll
-                for (int r = 0; r < 4; ++r)
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) q[4 * r + c] = c >= r ? A[4 + r][4 + c] : 0.0;
-                st_tile(t11, q);
-            }
-        }
-        __syncthreads();
-        if (*s_fail) return false;                        // uniform
+    for (int b0 = 0; b0 + 2 < nt4; b0 += 2) {
         const int bnext = b0 + 2;
-        if (bnext >= nt4) break;
-        // (2) panel solve R12 = R11^-T A12: thread = one matrix column of the panel (tile column bj, column c)
+        double *t00 = W + 16 * tidx(nt4, b0, b0), *t01 = W + 16 * tidx(nt4, b0, b0 + 1), *t11 = W + 16 * tidx(nt4, b0 + 1, b0 + 1);
+        // (1) panel solve R12 = R11^-T A12: thread = one matrix column of the panel (tile column bj, column c)
         {
             double r11[8][8];                             // R11[p][r], p < r (broadcast reads)
 #pragma unroll
@@ -278,32 +321,46 @@ __device__ __noinline__ bool chol_tiled(int nt4, double *W, const unsigned short
                 for (int r = 0; r < 4; ++r) { u0[4 * r] = xv[r]; u1[4 * r] = xv[4 + r]; }
             }
         }
+        CHP(13);
         __syncthreads();
-        // (3) trailing update: C(bi,bj) -= R12(:,bi)' R12(:,bj) for bnext <= bi <= bj
+        CHP(14);
+        // (2) trailing update, with the next diagonal block taken out and factored at once by warp 0
+        const int tA = tidx(nt4, bnext, bnext);
+        const bool two = bnext + 1 < nt4;
+        const int tB = two ? tA + 1 : -1, tC = two ? tidx(nt4, bnext + 1, bnext + 1) : -1;
+        if (warp == 0) {
+            // the three tiles of the next diagonal block: 48 outputs, one 8-term dot product each, spread over the lanes
+            {
+                const double *p0 = W + 16 * tidx(nt4, b0, bnext), *p1 = W + 16 * tidx(nt4, b0 + 1, bnext);   // panel rows x tile columns bnext, bnext+1:
+#pragma unroll                                                                                            // adjacent tiles, 16 doubles apart
+                for (int h = 0; h < 2; ++h) {
+                    const int e = lane + 32 * h;
+                    if (e < (two ? 48 : 16)) {
+                        const int te = e >> 4, ii = (e >> 2) & 3, jj = e & 3;
+                        const int ci = 16 * (te >> 1) + ii, cj = 16 * ((te + 1) >> 1) + jj;        // (bi, bj) - bnext = (0,0), (0,1), (1,1)
+                        double *dst = W + 16 * (te == 0 ? tA : (te == 1 ? tB : tC)) + 4 * ii + jj;
+                        double acc = *dst;
+#pragma unroll
+                        for (int p_ = 0; p_ < 4; ++p_) acc = fma(-p0[4 * p_ + ci], p0[4 * p_ + cj], acc);
+#pragma unroll
+                        for (int p_ = 0; p_ < 4; ++p_) acc = fma(-p1[4 * p_ + ci], p1[4 * p_ + cj], acc);
+                        *dst = acc;
+                    }
+                }
+            }
+            __syncwarp();
+            chol_diag(nt4, W, bnext, s_dinv, s_fail);
+        } else {
 #pragma unroll 1
-        for (int t = tidx(nt4, bnext, bnext) + tid; t < T; t += nthr) {
-            const int bi = tab[t] >> 8, bj = tab[t] & 0xff;
-            double ai[16], aj[16], c[16];
-            ld_tile(W + 16 * t, c);
-            ld_tile(W + 16 * tidx(nt4, b0, bi), ai);
-            ld_tile(W + 16 * tidx(nt4, b0, bj), aj);
-#pragma unroll
-            for (int p_ = 0; p_ < 4; ++p_)
-#pragma unroll
-                for (int ii = 0; ii < 4; ++ii)
-#pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) c[4 * ii + jj] = fma(-ai[4 * p_ + ii], aj[4 * p_ + jj], c[4 * ii + jj]);
-            ld_tile(W + 16 * tidx(nt4, b0 + 1, bi), ai);
-            ld_tile(W + 16 * tidx(nt4, b0 + 1, bj), aj);
-#pragma unroll
-            for (int p_ = 0; p_ < 4; ++p_)
-#pragma unroll
-                for (int ii = 0; ii < 4; ++ii)
-#pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) c[4 * ii + jj] = fma(-ai[4 * p_ + ii], aj[4 * p_ + jj], c[4 * ii + jj]);
-            st_tile(W + 16 * t, c);
+            for (int t = tA + 1 + (tid - 32); t < T; t += nthr - 32) {
+                if (t == tB || t == tC) continue;
+                chol_tile_update(nt4, W, b0, t, tab[t] >> 8, tab[t] & 0xff);
+            }
         }
+        CHP(15);
         __syncthreads();
+        CHP(5);
+        if (*s_fail) return false;                        // uniform
     }
     return true;
 }
@@ -762,7 +819,7 @@ __device__ __noinline__ int adapt(const RunArgs &a, const ChainCtx &cx, int isim
         }
         __syncthreads();
         SUBP(10);
-        const bool ok = chol_tiled(nt4, W, tab, s_dinv, s_flag);
+        const bool ok = chol_tiled(nt4, W, tab, s_dinv, s_flag, cx.ch == 0);
         __syncthreads();
         SUBP(11);
         if (ok) {
