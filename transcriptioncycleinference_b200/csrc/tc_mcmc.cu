@@ -1,10 +1,10 @@
 // tc_mcmc.cu — kernels and C ABI of libtcmcmc.so (sm_100a).  See include/tcmcmc.h for the boundary
 // and DESIGN.md for the data layout and roofline of each kernel.
 //
-//   ss_batch_kernel   one CTA per (cell, theta): the batched ssfun
-//                     (replaces src/SumofSquaresFunction_TranscriptionCycleMCMC.m:1-65)
-//   forward_kernel    model curves for the best-fit plots (src/TranscriptionCycleMCMC.m:307-309)
-//   dram_kernel       one CTA per chain, the whole mcmcrun DRAM loop device-resident
+//   ss_batch_kernel   one warp per (cell, theta): the batched ssfun
+//                     (replaces src/SumofSquaresFunction_TranscriptionCycleMCMC.m:1-65), and, with output
+//                     pointers, the model curves for the best-fit plots (src/TranscriptionCycleMCMC.m:307-309)
+//   dram_kernel       persistent CTAs time-slicing the chains: the whole mcmcrun DRAM loop device-resident
 //                     (replaces the call at src/TranscriptionCycleMCMC.m:273 + summaries :276-303)
 //   rng_dump_kernel   the Philox streams of a chain, for the parity harness
 //   dfma_peak_kernel  FP64 pipe micro-benchmark (roofline denominator)
@@ -36,9 +36,9 @@ static int fail(int code, const std::string &msg)
             return fail(TC_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));       \
     } while (0)
 
-#define DRAM_THREADS 256   // 8 warps; warp w simulates future step k+w of the chain speculatively
-#define SPEC 8             // steps per speculative round (= warps per CTA)
-#define RING 16            // proposal increments are generated ahead of use, up to RING steps per call
+#define DRAM_THREADS 256   // 8 warps per chain
+#define SPEC 8             // forward-model evaluations per speculative round (= warps per CTA)
+#define RING 16            // ring of proposal increments: generated GEN_M steps at a time, ahead of use
 #define SS_WARPS 8
 #define SS_THREADS (32 * SS_WARPS)
 #ifndef SS_MIN_CTAS
@@ -56,9 +56,6 @@ __device__ long long tc_subprof[32];
 #define SUBP_BEGIN
 #define SUBP(i)
 #endif
-
-// packed upper-triangular row-major index of (i, j), j >= i
-__host__ __device__ __forceinline__ int pidx(int n, int i, int j) { return i * n - (i * (i - 1)) / 2 + (j - i); }
 
 // --------------------------------------------------------------------------------- SS / forward
 struct SsArgs {
@@ -392,7 +389,7 @@ struct ChainState {
 // Immutable per-chain context, built once in shared memory so that the out-of-line phases below
 // (kept out of line to keep the hot loop inside the instruction cache) can share it.
 struct ChainCtx {
-    int N, npar, npad, npk, ld, slot_sz, wsz, ch, first_row, nstore;
+    int N, npar, npad, ld, slot_sz, wsz, ch, first_row, nstore;
     unsigned long long uid;
     double adascale, inv_dr;
     SmemCell cv;
@@ -466,12 +463,13 @@ __device__ __noinline__ void emit_s2(const RunArgs &a, const ChainCtx &cx, S2Sta
 //      parameter); u1, u2, chi2 -> the scalars of the step's ring slot.
 //   2. the two norms entering q1, from z.
 //   3. increments z1 R and z2 R/drscale -> the ring slot.  With a full factor this is ONE pass over R on the
-//      FP64 tensor cores ([8 x npar] x [npar x npar] as mma.sync m8n8k4, A rows = the new steps).  Every
-//      element of R is needed exactly once per call, so the B fragments are loaded straight from HBM/L2,
-//      double-buffered GEN_UNR k-steps ahead of the MMAs, not staged in shared memory.
+//      FP64 tensor cores ([8 x npar] x [npar x npar] as mma.sync m8n8k4, A rows = the new steps, 4 interleaved
+//      accumulator sets).  Every element of R is needed exactly once per call, so R is not staged as a matrix:
+//      each lane pulls its own B elements HBM/L2 -> shared memory with 8-byte cp.async into private staging slots,
+//      two groups of 8 k-steps in flight.
 #define GEN_M 8
 #ifndef TC_NOLOAD
-#define TC_NOLOAD 0
+#define TC_NOLOAD 0        // development switch: 1 = skip the loads of R (isolates the MMA loop in scripts/subprof.py)
 #endif
 __device__ __noinline__ void generate(const RunArgs &a, const ChainCtx &cx, int g0, int nnew, bool r_diag)
 {
@@ -946,7 +944,7 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
             int o = carve_cell(0, N, cv);
             o += o & 1;
             if (tid == 0) {
-                cx.N = N; cx.npar = npar; cx.npad = (npar + 3) & ~3; cx.npk = npar * (npar + 1) / 2; cx.ld = a.ld;
+                cx.N = N; cx.npar = npar; cx.npad = (npar + 3) & ~3; cx.ld = a.ld;
                 cx.slot_sz = dram_slot(N); cx.wsz = a.wsz; cx.ch = ch; cx.first_row = a.n_burn - 1;
                 cx.nstore = a.nsimu - (a.n_burn - 1);
                 cx.uid = a.chain_uid ? a.chain_uid[ch] : (unsigned long long)ch;
@@ -963,7 +961,7 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
                 cx.ring = tc_smem + o; o += RING * dram_slot(N);
                 cx.o_U = o;
                 cx.U = tc_smem + o;
-                cx.gRb = a.gR + (size_t)ch * a.ldR;                 // the factor R lives in HBM/L2 (packed upper)
+                cx.gRb = a.gR + (size_t)ch * a.ldR;                 // the factor R lives in HBM/L2 (4x4 tiles)
                 cx.gM2 = a.gM2 ? a.gM2 + (size_t)ch * a.ldR : nullptr;
                 cx.gRows = a.gRows ? a.gRows + (size_t)ch * (size_t)a.adaptint * a.ld : nullptr;
                 cx.gWts = a.gWts ? a.gWts + (size_t)ch * (size_t)a.adaptint : nullptr;
