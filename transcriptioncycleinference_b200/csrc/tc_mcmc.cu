@@ -1571,12 +1571,23 @@ int tc_ss_batch_device(const tc_cells *c, int device, int64_t nbatch, const int3
 }  // extern "C"
 
 struct DevBuf {                      // RAII for device scratch
+    // With a stream: stream-ordered allocation from the device's default memory pool, whose release threshold
+    // tc_mcmc_run raises, so that the scratch of one fit (tens of MB) is recycled by the next instead of going
+    // through cudaMalloc/cudaFree every call.
     std::vector<void *> ptrs;
-    ~DevBuf() { for (void *p : ptrs) cudaFree(p); }
+    cudaStream_t st = nullptr;
+    bool pooled = false;
+    void release()
+    {
+        for (void *p : ptrs) { if (pooled) cudaFreeAsync(p, st); else cudaFree(p); }
+        ptrs.clear();
+    }
+    ~DevBuf() { release(); }
     template <typename T> cudaError_t alloc(T *&p, size_t n)
     {
         void *q = nullptr;
-        cudaError_t e = cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T));
+        const size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
+        cudaError_t e = pooled ? cudaMallocAsync(&q, bytes, st) : cudaMalloc(&q, bytes);
         if (e == cudaSuccess) { ptrs.push_back(q); p = static_cast<T *>(q); }
         return e;
     }
@@ -1641,9 +1652,10 @@ struct DevRun {
     ~DevRun()
     {
         if (device >= 0) cudaSetDevice(device);
+        buf.release();                                  // stream-ordered frees need the stream
         if (e0) cudaEventDestroy(e0);
         if (e1) cudaEventDestroy(e1);
-        if (st) cudaStreamDestroy(st);
+        if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
     }
 };
 
@@ -1718,6 +1730,16 @@ int tc_mcmc_run(const tc_cells *c, const tc_mcmc_opts *o, int nchains, const int
         const size_t o0 = (size_t)r.c0;
         CUDA_TRY(cudaSetDevice(r.device));
         CUDA_TRY(cudaStreamCreateWithFlags(&r.st, cudaStreamNonBlocking));
+        {
+            cudaMemPool_t pool = nullptr;
+            int pools = 0;
+            if (cudaDeviceGetAttribute(&pools, cudaDevAttrMemoryPoolsSupported, r.device) == cudaSuccess && pools &&
+                cudaDeviceGetDefaultMemPool(&pool, r.device) == cudaSuccess) {
+                unsigned long long keep = ~0ULL;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+                r.buf.st = r.st; r.buf.pooled = true;
+            }
+        }
         CUDA_TRY(cudaEventCreate(&r.e0));
         CUDA_TRY(cudaEventCreate(&r.e1));
         RunArgs &a = r.a;
@@ -1733,7 +1755,7 @@ int tc_mcmc_run(const tc_cells *c, const tc_mcmc_opts *o, int nchains, const int
         std::vector<unsigned long long> uid(nc);
         for (int i = 0; i < nc; ++i) uid[i] = chain_uid ? chain_uid[o0 + i] : (unsigned long long)(o0 + i);
         CUDA_TRY(r.buf.alloc(d_uid, nc));
-        CUDA_TRY(cudaMemcpy(d_uid, uid.data(), nc * sizeof(unsigned long long), cudaMemcpyHostToDevice)); a.chain_uid = d_uid;
+        CUDA_TRY(cudaMemcpyAsync(d_uid, uid.data(), nc * sizeof(unsigned long long), cudaMemcpyHostToDevice, r.st)); a.chain_uid = d_uid;   // pageable source: staged before the call returns
         CUDA_TRY(up(r.buf, d, theta0 + o0 * ld, (size_t)nc * ld, r.st)); a.theta0 = d;
         CUDA_TRY(up(r.buf, d, qcov_diag + o0 * ld, (size_t)nc * ld, r.st)); a.qcov_diag = d;
         CUDA_TRY(up(r.buf, d, low + o0 * ld, (size_t)nc * ld, r.st)); a.low = d;
