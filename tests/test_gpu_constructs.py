@@ -75,3 +75,41 @@ def test_truncated_window_cells(cells_npz, orc):
     for c in range(cells.ncells):
         assert np.array_equal(cells.t_interp(c), co.t_interp(ts[c]))
     cells.close()
+
+
+@pytest.mark.parametrize("N", [12, 200])
+def test_series_length_extremes_replay(orc, N):
+    """Series much shorter / longer than TestData's 113-129 points: N = 12 (npar = 19: 3 column tiles, 5 Cholesky tile
+    rows) and N = 200 (npar = 207: one CTA per SM, 26 column tiles, several passes of the scatter update).  Synthetic
+    irregular time grid with missing data; the DRAM replay must match the oracle flag for flag."""
+    from transcriptioncycleinference_b200 import _lib, setup_cell
+    from transcriptioncycleinference_b200.engine import Cells
+    if _lib.device_count() < 1:
+        pytest.skip("no CUDA device")
+    co, cons = orc
+    rng = np.random.default_rng(100 + N)
+    ts, m2s, p7s = [], [], []
+    for c in range(3):
+        t = np.concatenate([[0.0], np.cumsum(rng.uniform(0.15, 0.35, N - 1))])
+        m2 = rng.uniform(0, 3, N); p7 = rng.uniform(0, 10, N)
+        m2[rng.random(N) < 0.4] = np.nan; p7[rng.random(N) < 0.2] = np.nan
+        ts.append(t); m2s.append(m2); p7s.append(p7)
+    cells = Cells(ts, m2s, p7s)
+    packed = dict(N=cells.N, off=cells.off, t=cells.t, ms2=cells.ms2, pp7=cells.pp7)
+    cc = np.arange(3, dtype=np.int32)
+    inputs = setup_cell.chain_inputs(cells, cc, np.random.default_rng(7))
+    nsimu, burn = 330, 100
+    g = np.random.default_rng(8)
+    st = dict(z1=g.standard_normal((3, nsimu, cells.ld)), u1=g.random((3, nsimu)), z2=g.standard_normal((3, nsimu, cells.ld)),
+              u2=g.random((3, nsimu)), chi2=g.chisquare(1 + 2 * N, (3, nsimu)))
+    opts = _lib.default_opts(nsimu=nsimu, burnintime=burn, n_burn=1, store_chain=1, replay=1)
+    out = cells.mcmc_run(opts, cc, *inputs, replay=st, want_flags=True)
+    npar = 7 + N
+    for i in range(3):
+        o = int(cells.off[i])
+        sti = dict(z1=st["z1"][i][:, :npar], u1=st["u1"][i], z2=st["z2"][i][:, :npar], u2=st["u2"][i], chi2=st["chi2"][i])
+        ref = co.dram(cons, packed["t"][o:o + N], packed["ms2"][o:o + N], packed["pp7"][o:o + N], co.default_opts(nsimu, burn),
+                      *[x[i, :npar] for x in inputs], streams=sti)
+        assert np.array_equal(out["flags"][i], ref["flags"]), (N, i)
+        np.testing.assert_allclose(out["chain"][i][:, :npar], ref["chain"], rtol=0, atol=1e-7)
+    cells.close()
