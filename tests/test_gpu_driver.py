@@ -87,3 +87,34 @@ def test_load_previous_and_custom_construct(tmp_path, cells_npz):
         assert np.all(np.abs(ch["v_chain"] - v0) <= 1e-5 + 1e-15)                 # v in [v0 - 1e-5, v0 + 1e-5]
     with pytest.raises(NameError):
         mcmc.TranscriptionCycleMCMC("fileDir", str(d), "saveLoc", str(s2), "construct", "undefined-construct")
+
+
+def test_multiple_chains_per_cell_pool_and_diagnose(tmp_path, cells_npz):
+    """'numChains' > 1 (BASELINE config 3 through the drop-in driver): the chains of a cell are pooled into the
+    reference's MCMCresults layout (pooled mean / population std = those of the concatenated chains) and the extra
+    variable MCMCdiagnostics carries Rhat / n_eff per parameter."""
+    from transcriptioncycleinference_b200 import _lib, mcmc
+    if _lib.device_count() < 1:
+        pytest.skip("no CUDA device")
+    idx = [3, 77, 200]
+    d = tmp_path / "in"; s = tmp_path / "out"; d.mkdir()
+    _write_dataset(str(d / "TestData.mat"), cells_npz, idx)
+    mcmc.TranscriptionCycleMCMC("fileDir", str(d), "saveLoc", str(s), "numParPools", 1, "n_burn", 200, "n_steps", 600,
+                                "numChains", 4, "seed", 5)
+    base = "%s-TestData" % mcmc.matlab_date()
+    res = sio.loadmat(str(s / (base + ".mat")), mat_dtype=True)
+    raw = sio.loadmat(str(s / (base + "_RawChain.mat")), mat_dtype=True)
+    assert res["MCMCresults"].shape == (1, 3) and res["MCMCresults"].dtype.names == mcmc.RESULT_FIELDS
+    assert res["MCMCdiagnostics"].dtype.names == mcmc.DIAG_FIELDS and res["MCMCdiagnostics"].shape == (1, 3)
+    for k, c in enumerate(idx):
+        n = int(cells_npz["N"][c])
+        ch, r, dg = raw["MCMCchain"][0, k], res["MCMCresults"][0, k], res["MCMCdiagnostics"][0, k]
+        assert ch["v_chain"].shape == (4 * 401, 1) and ch["s2chain"].shape == (4 * 600, 1)
+        assert abs(_f(r["mean_v"]) - ch["v_chain"].mean()) < 1e-10 and abs(_f(r["sigma_v"]) - ch["v_chain"].std()) < 1e-8
+        np.testing.assert_allclose(r["sigma_dR"][0], ch["dR_chain"].std(axis=0), rtol=1e-7, atol=1e-9)
+        assert dg["Rhat"].shape == (1, 7 + n) and _f(dg["numChains"]) == 4 and _f(dg["cell_index"]) == k + 1
+        # recompute Rhat of v from the raw chains
+        v = ch["v_chain"].reshape(4, 401)
+        W = v.var(axis=1, ddof=1).mean(); B = 401 * v.mean(axis=1).var(ddof=1)
+        assert abs(dg["Rhat"][0, 0] - np.sqrt((400 / 401 * W + B / 401) / W)) < 1e-8
+        assert _f(dg["Rhat_max"]) >= 1.0 - 1e-12

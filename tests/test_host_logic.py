@@ -140,3 +140,19 @@ def test_sharded_fit_world2_gloo():
         np.testing.assert_array_equal(res[r]["counters"][:, 0], cc)
         assert set(res[r]["owner"]) == {0, 1}               # both ranks did work
         assert np.all(np.diff(res[r]["owner"]) >= 0)         # contiguous blocks
+
+
+def test_rhat_from_summaries_matches_raw_chain_formula():
+    """Gelman-Rubin Rhat / n_eff computed from per-chain (mean, population std, n) == the textbook formula on raw chains."""
+    from transcriptioncycleinference_b200 import diagnostics
+    rng = np.random.default_rng(3)
+    m, n, p = 6, 400, 5
+    chains = rng.standard_normal((m, n, p)) + rng.standard_normal((m, 1, p)) * np.array([0.0, 0.05, 0.3, 1.0, 3.0])
+    rh, ne = diagnostics.rhat_from_summaries(chains.mean(axis=1), chains.std(axis=1), n)
+    W = chains.var(axis=1, ddof=1).mean(axis=0); B = n * chains.mean(axis=1).var(axis=0, ddof=1)
+    Vp = (n - 1) / n * W + B / n
+    np.testing.assert_allclose(rh, np.sqrt(Vp / W), rtol=1e-12)
+    assert rh[0] < 1.02 and rh[-1] > 2.0 and np.all(np.diff(rh) > 0)
+    assert np.all(ne <= m * n) and ne[-1] < 20
+    with pytest.raises(ValueError):
+        diagnostics.rhat_from_summaries(chains.mean(axis=1)[:1], chains.std(axis=1)[:1], n)

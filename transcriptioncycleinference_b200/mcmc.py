@@ -16,7 +16,8 @@ Differences that are deliberate and documented:
     results file in fileDir whose DatasetName matches; cells are matched on cell_index, unmatched
     cells are skipped and removed, ApprovedFits is carried over.
   * new optional arguments: 'files', 'previousResults', 'numChains' (default 1), 'seed',
-    'saveChains' (default True), 'verbose', 'returnResults'.
+    'saveChains' (default True), 'verbose', 'returnResults'.  With numChains > 1 the chains of a cell are
+    pooled in MCMCresults and an extra variable MCMCdiagnostics (Rhat, n_eff per parameter) is saved.
 """
 import datetime
 import glob
@@ -24,7 +25,7 @@ import os
 
 import numpy as np
 
-from . import _lib, setup_cell
+from . import _lib, diagnostics, setup_cell
 from .constructs import DEFAULT_CONSTRUCT, get_construct
 from .engine import Cells
 
@@ -32,6 +33,7 @@ RESULT_FIELDS = ("mean_v", "sigma_v", "mean_ton", "sigma_ton", "mean_A", "sigma_
                  "mean_MS2_basal", "sigma_MS2_basal", "mean_PP7_basal", "sigma_PP7_basal", "mean_R", "sigma_R",
                  "mean_dR", "sigma_dR", "mean_sigma", "sigma_sigma", "cell_index", "ApprovedFits")  # :151-155
 PLOT_FIELDS = ("t_plot", "MS2_plot", "PP7_plot", "simMS2", "simPP7")                                 # :156-157
+DIAG_FIELDS = ("cell_index", "numChains", "Rhat", "n_eff", "Rhat_max")   # extension, only with numChains > 1
 CHAIN_FIELDS = ("v_chain", "ton_chain", "A_chain", "tau_chain", "MS2_basal_chain", "PP7_basal_chain", "R_chain",
                 "dR_chain", "s2chain")                                                              # :149-150
 _IDX = dict(v=0, tau=1, ton=2, MS2_basal=3, PP7_basal=4, A=5, R=6)
@@ -155,7 +157,7 @@ def fit_dataset(cells_in, o, devices):
         out = cells.mcmc_run(opts, cc, *inputs, chain_uid=uid)
         # pool the chains of a cell (numChains > 1 is an extension; with 1 chain this is the identity)
         MCMCchain, MCMCresults, MCMCplot = [], [], []
-        means = []
+        means, diags = [], []
         for k, ci in enumerate(kept):
             N = len(ts[k]); npar = 7 + N
             sl = slice(k * nchains, (k + 1) * nchains)
@@ -178,6 +180,11 @@ def fit_dataset(cells_in, o, devices):
                 sigma_sigma = float(sg[:, 1].mean()) if nchains == 1 else float(np.sqrt((sg[:, 1] ** 2).mean()))
                 MCMCchain.append({f: np.zeros((0, 0)) for f in CHAIN_FIELDS})
             means.append(mean)
+            if nchains > 1:
+                # order of theta: [v, tau, ton, MS2_basal, PP7_basal, A, R, dR_1..dR_N]
+                rh, ne = diagnostics.rhat_from_summaries(mu_c, sd_c, n_steps - n_burn + 1)
+                diags.append(dict(cell_index=float(ci + 1), numChains=float(nchains), Rhat=rh.reshape(1, -1),
+                                  n_eff=ne.reshape(1, -1), Rhat_max=float(np.nanmax(rh[:7]))))
             r = dict(mean_v=mean[0], sigma_v=std[0], mean_tau=mean[1], sigma_tau=std[1], mean_ton=mean[2],
                      sigma_ton=std[2], mean_MS2_basal=mean[3], sigma_MS2_basal=std[3], mean_PP7_basal=mean[4],
                      sigma_PP7_basal=std[4], mean_A=mean[5], sigma_A=std[5], mean_R=mean[6], sigma_R=std[6],
@@ -192,6 +199,7 @@ def fit_dataset(cells_in, o, devices):
             MCMCplot.append(dict(t_plot=ts[k].reshape(1, -1), MS2_plot=m2s[k].reshape(1, -1),
                                  PP7_plot=p7s[k].reshape(1, -1), simMS2=sim1[k, :N].reshape(1, -1),
                                  simPP7=sim2[k, :N].reshape(1, -1)))
+        o["_diagnostics"] = diags
         return MCMCchain, MCMCresults, MCMCplot
     finally:
         cells.close()
@@ -237,9 +245,12 @@ def TranscriptionCycleMCMC(*varargin):
         chain, results, plot = fit_dataset(cells_in, oo, devices)
         os.makedirs(save_loc, exist_ok=True)
         base = "%s-%s" % (matlab_date(), name)
-        sio.savemat(os.path.join(save_loc, base + ".mat"),
-                    dict(MCMCresults=_struct_array(RESULT_FIELDS, results), MCMCplot=_struct_array(PLOT_FIELDS, plot),
-                         DatasetName=name))
+        mat = dict(MCMCresults=_struct_array(RESULT_FIELDS, results), MCMCplot=_struct_array(PLOT_FIELDS, plot),
+                   DatasetName=name)
+        diags = oo.get("_diagnostics") or []
+        if diags:
+            mat["MCMCdiagnostics"] = _struct_array(DIAG_FIELDS, diags)
+        sio.savemat(os.path.join(save_loc, base + ".mat"), mat)
         if o["saveChains"]:
             nbytes = sum(sum(np.asarray(v).nbytes for v in c.values()) for c in chain)
             if nbytes >= 2 ** 31:
@@ -249,6 +260,6 @@ def TranscriptionCycleMCMC(*varargin):
             else:
                 sio.savemat(os.path.join(save_loc, base + "_RawChain.mat"),
                             dict(MCMCchain=_struct_array(CHAIN_FIELDS, chain)))
-        ret.append(dict(DatasetName=name, MCMCresults=results, MCMCplot=plot, MCMCchain=chain))
+        ret.append(dict(DatasetName=name, MCMCresults=results, MCMCplot=plot, MCMCchain=chain, MCMCdiagnostics=diags))
     print("MCMC analysis complete. Information stored in: %s" % save_loc)
     return ret if o["returnResults"] else None
