@@ -44,8 +44,7 @@ static int fail(int code, const std::string &msg)
 #ifndef SS_MIN_CTAS
 #define SS_MIN_CTAS 4          // 64 registers: 32 warps per SM hide the latency of streaming theta (measured +12 % over 2)
 #endif
-#define COV_RC 8           // rows of the chain block staged per pass of the scatter update
-#define COV_TPT 3          // 4x4 covariance tiles per thread (3*256 >= 595 tiles at npar = 136)
+#define COV_CR 32          // weighted rows of the covariance block staged per pass of the scatter update
 
 // development aid: cycle counts of sub-phases, chain 0 only (build with -DTC_SUBPROF; see scripts/subprof.py)
 #ifdef TC_SUBPROF
@@ -688,9 +687,8 @@ __device__ __noinline__ int resolve_dr(const double *sc, bool o1, double x12, do
 __device__ __noinline__ int adapt(const RunArgs &a, const ChainCtx &cx, int isimu, double cov_n, double rate, bool r_diag,
                                   int ndist, double *s_dinv, int *s_flag)
 {
-    const int tid = threadIdx.x, npar = cx.npar, npad = cx.npad, ld = cx.ld;
-    double *chunk = cx.ring;                           // workspace: ring + per-warp areas (idle now)
-    double *sw = cx.ring + COV_RC * npad;                             // sqrt(weight) per row
+    const int tid = threadIdx.x, npar = cx.npar, ld = cx.ld;
+    double *sw = cx.ring;                              // workspace: ring + per-warp areas (idle now); sqrt(weight) per row first
     SUBP_BEGIN;
     if (a.do_cov) {
         const int m = a.adaptint;
@@ -702,73 +700,75 @@ __device__ __noinline__ int adapt(const RunArgs &a, const ChainCtx &cx, int isim
             cx.mb[i] = mbi;
             cx.dm[i] = mbi - __ldcg(cx.cmean + i);
         }
+        // M2 += U'U on the FP64 tensor cores, U = the weighted, centred rows (COV_CR of them per pass, staged in shared
+        // memory): per 8x8 block of M2 one mma.sync m8n8k4 per 4 rows (A = U' fragment, B = U fragment), two blocks
+        // interleaved per warp; the block is then added to the scatter matrix in HBM/L2, which uses the same 4x4-tile
+        // layout as the Cholesky workspace (a lane's two adjacent columns are one 16-byte access).
+        const int warp = tid >> 5, lane = tid & 31, ar = lane >> 2, ak = lane & 3;
+        const int nt4 = (npar + 3) >> 2, NT = (npar + 7) >> 3, NB = NT * (NT + 1) / 2;
+        const int ldu = 8 * NT + 4;                                   // row stride of U (doubles); + 4: rows 0..3 of a k-step hit different banks
+        double *U = cx.ring + COV_CR + 8;                             // after sw[COV_CR]
 #pragma unroll 1
-        for (int r = tid; r < nrows; r += DRAM_THREADS) sw[r] = r < ndist ? sqrt(__ldcg(cx.gWts + r)) : sqrt(fcorr);
-        const int ntile = (npar + 3) >> 2, T = ntile * (ntile + 1) / 2;
+        for (int r0 = 0; r0 < nrows; r0 += COV_CR) {
+            const int rc = min(COV_CR, nrows - r0), rc4 = (rc + 3) & ~3;
+            __syncthreads();
+            if (tid < rc) sw[tid] = r0 + tid < ndist ? sqrt(__ldcg(cx.gWts + r0 + tid)) : sqrt(fcorr);
+            __syncthreads();
+            // warp w stages rows w, w+8, ..: coalesced along the row, several rows' loads in flight
 #pragma unroll 1
-        for (int base = 0; base < T; base += COV_TPT * DRAM_THREADS) {
-            int bi[COV_TPT], bj[COV_TPT];
-            bool on[COV_TPT];
-            double acc[COV_TPT][16];
+            for (int c = lane; c < 8 * NT; c += 32) {
+                const double mbc = c < npar ? cx.mb[c] : 0.0, dmc = c < npar ? cx.dm[c] : 0.0;
+                double v[COV_CR / SPEC];
 #pragma unroll
-            for (int u = 0; u < COV_TPT; ++u) {
-                const int tix = base + u * DRAM_THREADS + tid;
-                on[u] = tix < T;
-                int rem = on[u] ? tix : 0, b = 0;
-                while (rem >= ntile - b) { rem -= ntile - b; ++b; }
-                bi[u] = b; bj[u] = b + rem;
-#pragma unroll
-                for (int e = 0; e < 16; ++e) acc[u][e] = 0.0;
-            }
-#pragma unroll 1
-            for (int r0 = 0; r0 < nrows; r0 += COV_RC) {
-                const int rc = min(COV_RC, nrows - r0);
-                __syncthreads();
-#pragma unroll 1
-                for (int c = tid; c < npad; c += DRAM_THREADS) {
-                    double v[COV_RC];
-#pragma unroll
-                    for (int r = 0; r < COV_RC; ++r) {                // independent loads in flight
-                        const int rr = r0 + r;
-                        v[r] = (c < npar && rr < ndist) ? __ldcg(cx.gRows + (size_t)rr * ld + c) : 0.0;
-                    }
-                    const double mbc = c < npar ? cx.mb[c] : 0.0, dmc = c < npar ? cx.dm[c] : 0.0;
-#pragma unroll
-                    for (int r = 0; r < COV_RC; ++r) {
-                        const int rr = r0 + r;
-                        if (r < rc) chunk[r * npad + c] = c < npar ? sw[rr] * (rr < ndist ? v[r] - mbc : dmc) : 0.0;
-                    }
+                for (int q = 0; q < COV_CR / SPEC; ++q) {
+                    const int r = warp + SPEC * q, rr = r0 + r;
+                    v[q] = (c < npar && r < rc && rr < ndist) ? __ldcg(cx.gRows + (size_t)rr * ld + c) : 0.0;
                 }
-                __syncthreads();
 #pragma unroll
-                for (int u = 0; u < COV_TPT; ++u) {
-                    if (!on[u]) continue;
-#pragma unroll 1
-                    for (int r = 0; r < rc; ++r) {
-                        const double2 *ra = reinterpret_cast<const double2 *>(chunk + r * npad + 4 * bi[u]);
-                        const double2 *rb = reinterpret_cast<const double2 *>(chunk + r * npad + 4 * bj[u]);
-                        const double2 a0 = ra[0], a1 = ra[1], b0 = rb[0], b1 = rb[1];
-                        const double av[4] = {a0.x, a0.y, a1.x, a1.y}, bv[4] = {b0.x, b0.y, b1.x, b1.y};
-#pragma unroll
-                        for (int ii = 0; ii < 4; ++ii)
-#pragma unroll
-                            for (int jj = 0; jj < 4; ++jj) acc[u][4 * ii + jj] = fma(av[ii], bv[jj], acc[u][4 * ii + jj]);
-                    }
+                for (int q = 0; q < COV_CR / SPEC; ++q) {
+                    const int r = warp + SPEC * q, rr = r0 + r;
+                    if (r < rc4) U[r * ldu + c] = (c < npar && r < rc) ? sw[r] * (rr < ndist ? v[q] - mbc : dmc) : 0.0;
                 }
             }
-            SUBP(8);
-            // the scatter matrix lives in HBM/L2 in the same 4x4-tile layout: tile tix is 16 contiguous doubles
-#pragma unroll
-            for (int u = 0; u < COV_TPT; ++u) {
-                if (!on[u]) continue;
-                double2 *g = reinterpret_cast<double2 *>(cx.gM2 + 16 * (size_t)(base + u * DRAM_THREADS + tid));
-                double2 old[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) old[e] = __ldcg(g + e);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) g[e] = make_double2(old[e].x + acc[u][2 * e], old[e].y + acc[u][2 * e + 1]);
+            __syncthreads();
+#pragma unroll 1
+            for (int b = warp; b < NB; b += 2 * SPEC) {
+                // blocks b and b + SPEC (upper triangle of 8x8 blocks, row-major)
+                int bi0 = 0, rem = b;
+                while (rem >= NT - bi0) { rem -= NT - bi0; ++bi0; }
+                const int bj0 = bi0 + rem;
+                const bool two = b + SPEC < NB;
+                int bi1 = 0; rem = two ? b + SPEC : 0;
+                while (rem >= NT - bi1) { rem -= NT - bi1; ++bi1; }
+                const int bj1 = bi1 + rem;
+                // the old values of the two blocks: loaded first, so that their L2 latency overlaps with the MMAs
+                double2 *g0 = nullptr, *g1 = nullptr;
+                {
+                    const int row = 8 * bi0 + ar, col = 8 * bj0 + 2 * ak, tr = row >> 2, tcn = col >> 2;
+                    if (tr <= tcn && tcn < nt4)                       // the tile exists (upper triangle, inside the padded matrix)
+                        g0 = reinterpret_cast<double2 *>(cx.gM2 + 16 * (size_t)tidx(nt4, tr, tcn) + 4 * (row & 3) + (col & 3));
+                }
+                if (two) {
+                    const int row = 8 * bi1 + ar, col = 8 * bj1 + 2 * ak, tr = row >> 2, tcn = col >> 2;
+                    if (tr <= tcn && tcn < nt4)
+                        g1 = reinterpret_cast<double2 *>(cx.gM2 + 16 * (size_t)tidx(nt4, tr, tcn) + 4 * (row & 3) + (col & 3));
+                }
+                double2 o0 = make_double2(0.0, 0.0), o1 = o0;
+                if (g0) o0 = __ldcg(g0);
+                if (g1) o1 = __ldcg(g1);
+                double d00 = 0.0, d01 = 0.0, d10 = 0.0, d11 = 0.0;
+                const double *ua0 = U + ak * ldu + 8 * bi0 + ar, *ub0 = U + ak * ldu + 8 * bj0 + ar;
+                const double *ua1 = U + ak * ldu + 8 * bi1 + ar, *ub1 = U + ak * ldu + 8 * bj1 + ar;
+#pragma unroll 2
+                for (int kk = 0; kk < rc4; kk += 4) {
+                    dmma_m8n8k4(d00, d01, ua0[kk * ldu], ub0[kk * ldu]);
+                    if (two) dmma_m8n8k4(d10, d11, ua1[kk * ldu], ub1[kk * ldu]);      // warp-uniform
+                }
+                if (g0) *g0 = make_double2(o0.x + d00, o0.y + d01);
+                if (g1) *g1 = make_double2(o1.x + d10, o1.y + d11);
             }
         }
+        SUBP(8);
         __syncthreads();
 #pragma unroll 1
         for (int i = tid; i < npar; i += DRAM_THREADS) { cx.cmean[i] = __ldcg(cx.cmean + i) + cx.dm[i] * (m / (cov_n + m)); cx.mb[i] = 0.0; }
