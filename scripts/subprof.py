@@ -22,7 +22,7 @@ print("chain 0 (cell %d, N=%d): %d steps, %d rounds (%.2f steps/round), acc %.3f
 print("  phase cycles/step: generate %.0f speculate %.0f commit %.0f - %.0f - %.0f adapt %.0f" % tuple(c[8:14] / nsimu))
 names = {0: "gen: randomness + sync", 1: "gen: norms", 2: "gen: dmma (B from L2)", 3: "gen: sync + write + sync (or diag scale)",
          16: "round: A bounds+prior (warp 0)", 17: "round: barrier 1", 18: "round: B tasks + C evaluation (warp 0)", 19: "round: barrier 2", 20: "round: D resolve", 21: "round: flush_run (accepts)", 22: "round: rows + state (warp 0)", 23: "round: barrier 3",
-         13: "chol: panel solve (thread 0)", 14: "chol: barrier after solve", 15: "chol: next diag (warp 0) / trailing", 5: "chol: barrier after trailing",
+         13: "chol: panel solve (thread 0)", 14: "chol: barrier after solve", 6: "chol: next-diag tile update (warp 0)", 7: "chol: next-diag factorisation (warp 0)", 15: "chol: rest until barrier", 5: "chol: barrier after trailing",
          8: "adapt: means + scatter accumulate", 9: "adapt: M2 rmw + cmean", 10: "adapt: load cov / burn-in scale", 11: "adapt: cholesky", 12: "adapt: write R"}
 gcalls = max(sp[26], 1)
 print("  generate calls %d (%.1f new steps/call)" % (gcalls, sp[27] / gcalls))

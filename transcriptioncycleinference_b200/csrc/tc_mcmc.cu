@@ -345,7 +345,9 @@ __device__ __noinline__ bool chol_tiled(int nt4, double *W, const unsigned short
                 }
             }
             __syncwarp();
+            CHP(6);
             chol_diag(nt4, W, bnext, s_dinv, s_fail);
+            CHP(7);
         } else {
 #pragma unroll 1
             for (int t = tA + 1 + (tid - 32); t < T; t += nthr - 32) {
