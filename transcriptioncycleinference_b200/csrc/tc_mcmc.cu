@@ -1046,14 +1046,16 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
         }
 
         int k = seg == 0 ? 1 : seg * a.seglen;      // next step to decide
+        // the step whose isimu = k is the next multiple of adaptint triggers the adaptation (kept as a running value:
+        // an integer division per round is ~40 dependent instructions)
+        int next_adapt = a.adaptint > 0 ? ((k + a.adaptint) / a.adaptint) * a.adaptint : 0x7fffffff;
         int gen_upto = k;                           // increments are ready for steps [k, gen_upto)
         const bool bad0 = st.bad0 != 0;
 #pragma unroll 1
         while (k < k_end && !bad0) {
             // the round never crosses an adaptation: the step whose isimu = st+1 is a multiple of adaptint
             // is the last one that may use the current R
-            int bound = k_end;
-            if (a.adaptint > 0) bound = min(bound, ((k + a.adaptint) / a.adaptint) * a.adaptint);   // exclusive step bound
+            const int bound = min(k_end, next_adapt);                       // exclusive step bound
             // chain state of this round (thread 0 rewrites st only in the commit phase, after two barriers)
             const double ss = st.ss, pri = st.pri, sig2 = st.sigma2, wcnt = st.wcnt;
             const int run_r0 = st.run_r0, ndist = st.ndist;
@@ -1202,7 +1204,7 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
             TC_PHASE(2);
 
             // adaptation after the step with isimu = k, a multiple of adaptint
-            if (a.adaptint > 0 && k % a.adaptint == 0) {
+            if (k == next_adapt) {
                 const int rr0 = st.run_r0, nd0 = st.ndist;
                 const double wc0 = st.wcnt;
                 flush_run(a, cx, rr0, k, wc0, nd0, -1, 0);                     // close the run at the block boundary
@@ -1221,6 +1223,7 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
                     st.reju = 0;
                 }
                 __syncthreads();
+                next_adapt += a.adaptint;
                 TC_PHASE(5);
             }
         }
