@@ -510,9 +510,10 @@ __device__ __noinline__ void generate(const RunArgs &a, const ChainCtx &cx, int 
         }
         __syncwarp();
         const int npairs = (npar + 1) >> 1;
-#pragma unroll 1
+        const float inv_np = 1.0f / (float)npairs;                  // it / npairs without an integer division: exact here
+#pragma unroll 1                                                    // (it + 0.5 is >= 0.5/npairs away from a multiple of npairs)
         for (int it = (tid + 32) & (DRAM_THREADS - 1); it < nnew * npairs; it += DRAM_THREADS) {
-            const int sidx = it / npairs, q2 = it - sidx * npairs;
+            const int sidx = (int)(((float)it + 0.5f) * inv_np), q2 = it - sidx * npairs;
             double *dz = Z + (size_t)sidx * zs;
             const double4 z = normal_quad(a.seed, cx.uid, g0 + sidx, q2);
             *reinterpret_cast<double2 *>(dz + 4 * q2) = make_double2(z.x, z.z);          // (z1, z2) of parameter 2q
