@@ -94,7 +94,12 @@ typedef struct tc_mcmc_opts {
     double sigma2_0;          /* model.sigma2 = 1 (:212,259) */
     uint64_t seed;            /* Philox key; draws are addressed by (seed, chain_uid, step, slot) so
                                  results do not depend on the GPU count */
+    int32_t layout;           /* TC_LAYOUT_AUTO (0), or TC_LAYOUT_BIG to force the large-series layout (ring of 8 proposal
+                                 slots, proposal factor factorised through HBM/L2) that series with more than ~210
+                                 points get automatically; same chain either way (parity tests) */
+    int32_t _pad;
 } tc_mcmc_opts;
+enum { TC_LAYOUT_AUTO = 0, TC_LAYOUT_BIG = 1 };
 
 /* Per-chain counters returned by tc_mcmc_run (int64 each) */
 enum {

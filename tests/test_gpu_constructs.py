@@ -77,11 +77,13 @@ def test_truncated_window_cells(cells_npz, orc):
     cells.close()
 
 
-@pytest.mark.parametrize("N", [12, 200])
+@pytest.mark.parametrize("N", [12, 200, 250, 400])
 def test_series_length_extremes_replay(orc, N):
     """Series much shorter / longer than TestData's 113-129 points: N = 12 (npar = 19: 3 column tiles, 5 Cholesky tile
-    rows) and N = 200 (npar = 207: one CTA per SM, 26 column tiles, several passes of the scatter update).  Synthetic
-    irregular time grid with missing data; the DRAM replay must match the oracle flag for flag."""
+    rows), N = 200 (npar = 207: one CTA per SM, 26 column tiles, several passes of the scatter update), and N = 250 /
+    N = 400 (BASELINE config 5's length; npar = 257 / 407: the big layout — ring of 8 slots, bounds read from HBM/L2, proposal
+    factor factorised through HBM/L2 by chol_global; 257 has an odd number of 4x4 tile rows).  Synthetic irregular time
+    grid with missing data; the DRAM replay must match the oracle flag for flag."""
     from transcriptioncycleinference_b200 import _lib, setup_cell
     from transcriptioncycleinference_b200.engine import Cells
     if _lib.device_count() < 1:

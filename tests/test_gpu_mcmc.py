@@ -209,3 +209,30 @@ def test_posterior_means_agree_with_independent_cpu_chains(gpu_cells, cells_npz,
         g, c = gpu["sig"][s, 0], csig[s, 0]
         se = np.sqrt(g.var(ddof=1) / per + c.var(ddof=1) / per)
         assert abs(g.mean() - c.mean()) <= 4.0 * se + 1e-9, (int(cells3[ci]), "sigma", g.mean(), c.mean(), se)
+
+
+def test_big_layout_matches_oracle_and_regular_layout(gpu_cells, cells_npz, orc):
+    """The large-series layout (TC_LAYOUT_BIG: what series with more than ~210 points get) forced onto TestData cells:
+    (1) replay against the oracle over burn-in + 5 covariance adaptations, flags identical; (2) production Philox run,
+    regular vs big layout: the two differ only in the rounding of the Cholesky factor (shared-memory right-looking vs
+    left-looking through L2), so the accept/reject sequence and the counters must be identical and the means equal to rounding."""
+    from transcriptioncycleinference_b200 import _lib
+    chain_cell = np.array([0, 57, 130, 298], dtype=np.int32)
+    inputs = _setup(gpu_cells, chain_cell, 21)
+    nsimu, burn = 600, 200
+    st = _streams(len(chain_cell), nsimu, gpu_cells.ld, [int(cells_npz["N"][c]) for c in chain_cell], 22)
+    opts = _lib.default_opts(nsimu=nsimu, burnintime=burn, n_burn=1, store_chain=1, replay=1, layout=1)
+    out = gpu_cells.mcmc_run(opts, chain_cell, *inputs, replay=st, want_flags=True)
+    for i, c in enumerate(chain_cell):
+        npar = 7 + int(cells_npz["N"][c])
+        ref = _oracle_chain(orc, cells_npz, int(c), dict(nsimu=nsimu, burnintime=burn), inputs, i, st)
+        assert np.array_equal(out["flags"][i], ref["flags"]), c
+        np.testing.assert_allclose(out["chain"][i][:, :npar], ref["chain"], rtol=0, atol=1e-7)
+        assert out["counters"][i][4] == 5 and out["counters"][i][5] == 0          # adaptations at 200..600, no Cholesky failure
+    res = []
+    for layout in (0, 1):
+        opts = _lib.default_opts(nsimu=3000, burnintime=500, n_burn=500, layout=layout, seed=99)
+        res.append(gpu_cells.mcmc_run(opts, chain_cell, *inputs, want_flags=True))
+    assert np.array_equal(res[0]["flags"], res[1]["flags"])
+    assert np.array_equal(res[0]["counters"][:, :8], res[1]["counters"][:, :8])
+    np.testing.assert_allclose(res[0]["mean"], res[1]["mean"], rtol=0, atol=1e-6)

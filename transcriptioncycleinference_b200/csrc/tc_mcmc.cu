@@ -95,7 +95,7 @@ struct RunArgs {
     double drscale, adascale, qcovadj, burnin_scale, N0, S20, sigma2_0;
     unsigned long long seed;
     // chains
-    int nchains, ld, ldR, do_cov, wsz;
+    int nchains, ld, ldR, do_cov, wsz, big;
     const int *chain_cell;
     const unsigned long long *chain_uid;
     const double *theta0, *qcov_diag, *low, *upp, *pmu, *psig;
@@ -107,6 +107,7 @@ struct RunArgs {
     double *sschain;
     // scratch (global)
     double *gR, *gM2, *gRows, *gWts, *gCmean, *gState;
+    double *gW;                                         // big layout: one Cholesky workspace (ldR doubles) per CTA
     // time slicing
     int seglen;
     int *cstate;
@@ -125,19 +126,26 @@ __host__ __device__ inline int chol_ws_doubles(int n)
 }
 
 __host__ __device__ inline int dram_slot(int N) { return 2 * (7 + N) + 2 + 8; }
-__host__ __device__ inline int dram_wsz(int N)
+// Two shared-memory layouts:
+//   regular (big = 0): ring of RING = 16 slots, all 10 per-parameter vectors in shared memory, the Cholesky workspace
+//                      of the proposal factor inside ring + per-warp areas (N up to ~210);
+//   big     (big = 1): ring of 8 slots (randomness is generated when the ring is empty), bounds and prior means read
+//                      from HBM/L2, the factorisation done through HBM/L2 by chol_global (N up to ~410, BASELINE config 5).
+__host__ __device__ inline int dram_wsz(int N, int big)
 {
     const int npar = 7 + N;
     int w = (work_doubles(N) + 1) & ~1;
-    const int need = (chol_ws_doubles(npar) - RING * dram_slot(N) + SPEC - 1) / SPEC + 2;
-    if (w < need) w = need;
+    if (!big) {
+        const int need = (chol_ws_doubles(npar) - RING * dram_slot(N) + SPEC - 1) / SPEC + 2;
+        if (w < need) w = need;
+    }
     const int need2 = 2 * ((npar + 3) & ~3) + 16 * 32;        // generate(): a row of Z + the warp's B staging (16 k-steps x 32 lanes)
     if (w < need2) w = need2;
     return (w + 1) & ~1;
 }
-__host__ __device__ inline int dram_smem_doubles(int N)
+__host__ __device__ inline int dram_smem_doubles(int N, int big)
 {
-    return cell_doubles(N) + 10 * (7 + N) + 4 + RING * dram_slot(N) + SPEC * dram_wsz(N) + 16;
+    return cell_doubles(N) + (big ? 7 : 10) * (7 + N) + 4 + (big ? RING / 2 : RING) * dram_slot(N) + SPEC * dram_wsz(N, big) + 16;
 }
 
 // ---- Cholesky of the proposal covariance, in shared memory, by the whole CTA
@@ -153,6 +161,33 @@ __device__ __forceinline__ void st_tile(double *p, const double (&t)[16])
 {
 #pragma unroll
     for (int e = 0; e < 8; ++e) reinterpret_cast<double2 *>(p)[e] = make_double2(t[2 * e], t[2 * e + 1]);
+}
+
+// Upper Cholesky of an 8x8 block held in registers (A[r][c], r <= c), in place; dinv = reciprocal pivots.  Returns true
+// when a pivot is not positive.
+__device__ __forceinline__ bool chol8(double (&A)[8][8], double (&dinv)[8])
+{
+    bool bad = false;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const double d = A[j][j];
+        if (!(d > 0.0)) bad = true;
+        // 1/sqrt(d): single-precision seed + two Newton steps in FP64 (full precision; the IEEE sqrt + divide pair is
+        // ~60 dependent instructions per pivot, and the 8 pivots of a block are a serial chain on one warp)
+        double ri = (double)rsqrtf((float)d);
+        const double hd = 0.5 * d;
+        ri = ri * fma(-hd * ri, ri, 1.5);
+        ri = ri * fma(-hd * ri, ri, 1.5);
+        dinv[j] = ri;
+        A[j][j] = d * ri;
+#pragma unroll
+        for (int c = j + 1; c < 8; ++c) A[j][c] *= ri;
+#pragma unroll
+        for (int r = j + 1; r < 8; ++r)
+#pragma unroll
+            for (int c = r; c < 8; ++c) A[r][c] = fma(-A[j][r], A[j][c], A[r][c]);
+    }
+    return bad;
 }
 
 // Factor the 8x8 diagonal block that starts at tile row b0 (one 4x4 tile when it is the last row of an odd nt4): every
@@ -191,27 +226,8 @@ __device__ __forceinline__ void chol_diag(int nt4, double *W, int b0, double *s_
                 for (int c = (r < 4 ? 4 : r); c < 8; ++c) A[r][c] = (r == c) ? 1.0 : 0.0;
         }
     }
-    bool bad = false;
     double dinv[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const double d = A[j][j];
-        if (!(d > 0.0)) bad = true;
-        // 1/sqrt(d): single-precision seed + two Newton steps in FP64 (full precision; the IEEE sqrt + divide pair is
-        // ~60 dependent instructions per pivot, and the 8 pivots of a block are a serial chain on one warp)
-        double ri = (double)rsqrtf((float)d);
-        const double hd = 0.5 * d;
-        ri = ri * fma(-hd * ri, ri, 1.5);
-        ri = ri * fma(-hd * ri, ri, 1.5);
-        dinv[j] = ri;
-        A[j][j] = d * ri;
-#pragma unroll
-        for (int c = j + 1; c < 8; ++c) A[j][c] *= ri;
-#pragma unroll
-        for (int r = j + 1; r < 8; ++r)
-#pragma unroll
-            for (int c = r; c < 8; ++c) A[r][c] = fma(-A[j][r], A[j][c], A[r][c]);
-    }
+    const bool bad = chol8(A, dinv);
     if (lane == 0) {
         double q[16];
 #pragma unroll
@@ -371,6 +387,145 @@ __device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, do
                  : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
+// Left-looking blocked Cholesky THROUGH HBM/L2, for proposal factors too large for shared memory (big layout):
+// R'R = gA * invn + qcovadj I (identity on the padding), gA and the result gW in the 4x4-tile layout of chol_tiled.
+// Panels of two tile rows (8 matrix rows).  Per panel:
+//  (1) S = A(panel rows, columns >= panel) - sum over the tile rows above of R(row, panel cols)' R(row, cols) on the FP64
+//      tensor cores: one mma.sync m8n8k4 per tile row above per 8-column block, fragments read straight from L2 (the 32
+//      B elements of a warp are two adjacent tiles = 256 contiguous bytes), column blocks dealt round-robin to the
+//      warps, 4 tile rows of loads (20 per lane) in flight;
+//  (2) warp 0 factors the 8x8 diagonal block in registers; (3) the rest of the panel is solved one column per thread;
+//  (4) the panel is written to gW.
+// S = shared-memory buffer [8][8 ceil(nt4 / 2) + 4].  Returns false when a pivot is not positive (gW is then
+// garbage; the caller keeps the old R).  Reads 11 MB from L2 at npar = 407 (a right-looking sweep would move 34 MB).
+__device__ __noinline__ bool chol_global(int nt4, int npar, const double *gA, double invn, double qcovadj, double *gW,
+                                         double *S, double *s_dinv, int *s_fail)
+{
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, ar = lane >> 2, ak = lane & 3;
+    const int ldS = 8 * ((nt4 + 1) >> 1) + 4;
+    const int th = ar >> 2, inner = 4 * ak + (ar & 3);
+    if (tid == 0) *s_fail = 0;
+    __syncthreads();
+#pragma unroll 1
+    for (int b0 = 0; b0 < nt4; b0 += 2) {
+        const bool two = b0 + 1 < nt4;
+        const int ntc = nt4 - b0, nb = (ntc + 1) >> 1;
+        // (1) accumulate
+#pragma unroll 1
+        for (int jg = warp; jg < nb; jg += 4 * SPEC) {
+            double acc[4][2];
+            int offq[4];
+            bool okq[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int j = jg + SPEC * q;
+                acc[q][0] = 0.0; acc[q][1] = 0.0;
+                okq[q] = j < nb && b0 + 2 * j + th < nt4;
+                offq[q] = 16 * (2 * j + th) + inner;
+            }
+            const bool oka = b0 + th < nt4;
+            const int offa = 16 * th + inner;
+            const double *pl = gW + 16 * (size_t)b0;               // tile (0, b0); tile (pr+1, b0) sits 16 (nt4 - pr - 1) doubles further
+            int dpl = 16 * (nt4 - 1);
+#define CG_BATCH(NR)                                                                                       \
+    {                                                                                                      \
+        double av[NR], bv[NR][4];                                                                          \
+        _Pragma("unroll") for (int u = 0; u < NR; ++u) {                                                   \
+            av[u] = oka ? __ldcg(pl + offa) : 0.0;                                                         \
+            _Pragma("unroll") for (int q = 0; q < 4; ++q) bv[u][q] = okq[q] ? __ldcg(pl + offq[q]) : 0.0;  \
+            pl += dpl; dpl -= 16;                                                                          \
+        }                                                                                                  \
+        _Pragma("unroll") for (int u = 0; u < NR; ++u)                                                     \
+            _Pragma("unroll") for (int q = 0; q < 4; ++q)                                                  \
+                if (jg + SPEC * q < nb) dmma_m8n8k4(acc[q][0], acc[q][1], av[u], bv[u][q]);                \
+    }
+            int pr = 0;
+#pragma unroll 1
+            for (; pr + 4 <= b0; pr += 4) CG_BATCH(4)
+            if (pr < b0) CG_BATCH(2)                               // b0 is even
+#undef CG_BATCH
+            // S = A - acc: lane holds rows ar, columns 2 ak, 2 ak + 1 of each of its blocks
+            const int tr = b0 + th, rin = ar & 3, row = 4 * tr + rin;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int j = jg + SPEC * q;
+                if (j >= nb) continue;
+                const int tcn = b0 + 2 * j + (ak >> 1), col = 4 * tcn + 2 * (ak & 1);
+                double2 v = make_double2(0.0, 0.0);
+                if (tr <= tcn && tcn < nt4 && tr < nt4) {
+                    v = __ldcg(reinterpret_cast<const double2 *>(gA + 16 * (size_t)tidx(nt4, tr, tcn) + 4 * rin + 2 * (ak & 1)));
+                    v.x *= invn; v.y *= invn;
+                    if (row == col) v.x = row < npar ? v.x + qcovadj : 1.0;
+                    if (row == col + 1) v.y = row < npar ? v.y + qcovadj : 1.0;
+                }
+                *reinterpret_cast<double2 *>(S + ar * ldS + 8 * j + 2 * ak) = make_double2(v.x - acc[q][0], v.y - acc[q][1]);
+            }
+        }
+        __syncthreads();
+        // (2) the diagonal block
+        if (warp == 0) {
+            double A[8][8], dinv[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int c = r; c < 8; ++c) A[r][c] = (two || c < 4) ? S[r * ldS + c] : (r == c ? 1.0 : 0.0);
+            const bool bad = chol8(A, dinv);
+            if (lane == 0) {
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+#pragma unroll
+                    for (int c = r; c < 8; ++c) S[r * ldS + c] = A[r][c];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) s_dinv[j] = dinv[j];
+                if (bad) *s_fail = 1;
+            }
+        }
+        __syncthreads();
+        if (*s_fail) return false;                                // uniform
+        // (3) panel solve R12 = R11^-T A12: thread = one matrix column
+        if (4 * ntc > 8) {
+            double r11[8][8], di[8];
+#pragma unroll
+            for (int p_ = 0; p_ < 8; ++p_)
+#pragma unroll
+                for (int r = p_ + 1; r < 8; ++r) r11[p_][r] = S[p_ * ldS + r];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) di[j] = s_dinv[j];
+#pragma unroll 1
+            for (int cc = 8 + tid; cc < 4 * ntc; cc += DRAM_THREADS) {
+                double xv[8];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) xv[r] = S[r * ldS + cc];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    double sacc = xv[r];
+#pragma unroll
+                    for (int p_ = 0; p_ < r; ++p_) sacc = fma(-r11[p_][r], xv[p_], sacc);
+                    xv[r] = sacc * di[r];
+                }
+#pragma unroll
+                for (int r = 0; r < 8; ++r) S[r * ldS + cc] = xv[r];
+            }
+            __syncthreads();
+        }
+        // (4) the panel goes to gW (tiles (b0, b0..), (b0+1, b0+1..)); zeros below the diagonal
+        {
+            const int nT = ntc + (two ? ntc - 1 : 0);
+#pragma unroll 1
+            for (int e = tid; e < 8 * nT; e += DRAM_THREADS) {
+                const int u = e >> 3, r = (e >> 1) & 3, c2 = e & 1;
+                const int h = u < ntc ? 0 : 1, tcl = h ? u - ntc + 1 : u;
+                const double2 v = *reinterpret_cast<const double2 *>(S + (4 * h + r) * ldS + 4 * tcl + 2 * c2);
+                const bool dg = tcl == h;
+                const double v0 = (dg && 2 * c2 < r) ? 0.0 : v.x, v1 = (dg && 2 * c2 + 1 < r) ? 0.0 : v.y;
+                *reinterpret_cast<double2 *>(gW + 16 * (size_t)tidx(nt4, b0 + h, b0 + tcl) + 4 * r + 2 * c2) = make_double2(v0, v1);
+            }
+        }
+        __syncthreads();                                          // the next panel reads these tiles back from L2 (ld.cg)
+    }
+    return true;
+}
+
 // per-candidate-step record of a round: out-of-bounds bits and prior sums of the two proposals (shared memory)
 struct Cand { double pr1, pr2; int oob, pad; };
 // outcome of one step under the hypothesis "every earlier step of the round rejected" (registers of lane = step)
@@ -390,16 +545,16 @@ struct ChainState {
 // Immutable per-chain context, built once in shared memory so that the out-of-line phases below
 // (kept out of line to keep the hot loop inside the instruction cache) can share it.
 struct ChainCtx {
-    int N, npar, npad, ld, slot_sz, wsz, ch, first_row, nstore;
+    int N, npar, npad, ld, slot_sz, wsz, ch, first_row, nstore, ring_mask;
     unsigned long long uid;
     double adascale, inv_dr;
     SmemCell cv;
     int o_x, o_ring, o_U;                               // offsets (doubles) into tc_smem
     double *ring, *x, *lo, *hi, *mu, *pinv, *wmean, *wM2, *rdiag, *mb, *dm, *U;
     double *gRb, *gM2, *gRows, *gWts, *cmean;
-    __device__ __forceinline__ int slot_o(int step) const { return o_ring + (step & (RING - 1)) * slot_sz; }
-    __device__ __forceinline__ double *slot_d(int step) const { return ring + (size_t)(step & (RING - 1)) * slot_sz; }
-    __device__ __forceinline__ double *slot_sc(int step) const { return ring + (size_t)(step & (RING - 1)) * slot_sz + (slot_sz - 8); }
+    __device__ __forceinline__ int slot_o(int step) const { return o_ring + (step & ring_mask) * slot_sz; }
+    __device__ __forceinline__ double *slot_d(int step) const { return ring + (size_t)(step & ring_mask) * slot_sz; }
+    __device__ __forceinline__ double *slot_sc(int step) const { return ring + (size_t)(step & ring_mask) * slot_sz + (slot_sz - 8); }
 };
 
 // The chain rows [r0, r1) all equal the current state x (a run: the accept at row r0, then rejections).
@@ -797,6 +952,22 @@ __device__ __noinline__ int adapt(const RunArgs &a, const ChainCtx &cx, int isim
         // R = chol(cov + qcovadj I) * adascale, factorised in shared memory (tiled layout), kept in HBM/L2
         const double invn = 1.0 / (cov_n - 1.0);
         const int nt4 = (npar + 3) >> 2, T4 = nt4 * (nt4 + 1) / 2;
+        if (a.big) {
+            // the factor does not fit in shared memory: factorise through HBM/L2 into this CTA's workspace
+            double *gW = a.gW + (size_t)blockIdx.x * a.ldR;
+            const bool ok = chol_global(nt4, npar, cx.gM2, invn, a.qcovadj, gW, cx.ring, s_dinv, s_flag);
+            SUBP(11);
+            if (ok) {
+                const double2 *src = reinterpret_cast<const double2 *>(gW);
+                double2 *dst = reinterpret_cast<double2 *>(cx.gRb);
+                const double sc = cx.adascale;
+#pragma unroll 8
+                for (int e = tid; e < 8 * T4; e += DRAM_THREADS) { const double2 v = __ldcg(src + e); dst[e] = make_double2(v.x * sc, v.y * sc); }
+            }
+            __syncthreads();
+            SUBP(12);
+            return ok ? 1 : 2;
+        }
         double *W = cx.ring;
         unsigned short *tab = reinterpret_cast<unsigned short *>(W + 16 * T4);
 #pragma unroll 1
@@ -955,13 +1126,21 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
                 cx.inv_dr = 1.0 / a.drscale;
                 cx.cv = cv; cx.cv.d = a.cells.dmean[cid];
                 cx.o_x = o;
-                cx.x = tc_smem + o; o += npar;     cx.lo = tc_smem + o; o += npar;    cx.hi = tc_smem + o; o += npar;
-                cx.mu = tc_smem + o; o += npar;    cx.pinv = tc_smem + o; o += npar;  cx.wmean = tc_smem + o; o += npar;
+                cx.x = tc_smem + o; o += npar;
+                if (a.big) {
+                    // bounds and prior means stay in HBM/L2 (read once per candidate step by cand_bounds)
+                    cx.lo = const_cast<double *>(a.low) + (size_t)ch * a.ld; cx.hi = const_cast<double *>(a.upp) + (size_t)ch * a.ld;
+                    cx.mu = const_cast<double *>(a.pmu) + (size_t)ch * a.ld;
+                } else {
+                    cx.lo = tc_smem + o; o += npar;    cx.hi = tc_smem + o; o += npar;    cx.mu = tc_smem + o; o += npar;
+                }
+                cx.pinv = tc_smem + o; o += npar;  cx.wmean = tc_smem + o; o += npar;
                 cx.wM2 = tc_smem + o; o += npar;   cx.rdiag = tc_smem + o; o += npar; cx.mb = tc_smem + o; o += npar;
                 cx.dm = tc_smem + o; o += npar;
                 o += o & 1;
                 cx.o_ring = o;
-                cx.ring = tc_smem + o; o += RING * dram_slot(N);
+                cx.ring_mask = (a.big ? RING / 2 : RING) - 1;
+                cx.ring = tc_smem + o; o += (cx.ring_mask + 1) * dram_slot(N);
                 cx.o_U = o;
                 cx.U = tc_smem + o;
                 cx.gRb = a.gR + (size_t)ch * a.ldR;                 // the factor R lives in HBM/L2 (4x4 tiles)
@@ -979,9 +1158,11 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
 #pragma unroll 1
         for (int i = tid; i < npar; i += DRAM_THREADS) {
             const size_t g = (size_t)ch * a.ld + i;
-            cx.lo[i] = a.low[g];
-            cx.hi[i] = a.upp[g];
-            cx.mu[i] = a.pmu[g];
+            if (!a.big) {
+                cx.lo[i] = a.low[g];
+                cx.hi[i] = a.upp[g];
+                cx.mu[i] = a.pmu[g];
+            }
             const double sg = a.psig[g];
             cx.pinv[i] = isinf(sg) ? 0.0 : 1.0 / sg;
             cx.mb[i] = 0.0;
@@ -1061,8 +1242,9 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
             const double ss = st.ss, pri = st.pri, sig2 = st.sigma2, wcnt = st.wcnt;
             const int run_r0 = st.run_r0, ndist = st.ndist;
 
-            if (gen_upto < bound && gen_upto - k < SPEC) {
-                // fewer than SPEC steps ready => at least GEN_M of the RING slots are free
+            if (gen_upto < bound && gen_upto - k < (a.big ? 1 : SPEC)) {
+                // fewer than SPEC steps ready => at least GEN_M of the RING slots are free (big layout: ring of GEN_M
+                // slots, refilled when empty)
                 const int glim = min(gen_upto + GEN_M, bound);
                 generate(a, cx, gen_upto, glim - gen_upto, st.r_diag != 0);
                 gen_upto = glim;
@@ -1795,13 +1977,18 @@ int tc_mcmc_run(const tc_cells *c, const tc_mcmc_opts *o, int nchains, const int
             CUDA_TRY(r.buf.alloc(a.gWts, (size_t)nc * o->adaptint));
             CUDA_TRY(r.buf.alloc(a.gCmean, (size_t)nc * ld));
         }
-        a.wsz = dram_wsz(Nmax);
-        const size_t smem = sizeof(double) * (size_t)dram_smem_doubles(Nmax);
         int optin = 0;
         CUDA_TRY(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, r.device));
-        if (smem > (size_t)optin || npmax > 256)
+        cudaFuncAttributes fa;
+        CUDA_TRY(cudaFuncGetAttributes(&fa, dram_kernel));
+        const size_t avail = (size_t)optin > fa.sharedSizeBytes ? (size_t)optin - fa.sharedSizeBytes : 0;
+        // regular layout when the Cholesky workspace fits in one SM's shared memory, else the big one
+        a.big = (sizeof(double) * (size_t)dram_smem_doubles(Nmax, 0) > avail || o->layout == TC_LAYOUT_BIG) ? 1 : 0;
+        a.wsz = dram_wsz(Nmax, a.big);
+        const size_t smem = sizeof(double) * (size_t)dram_smem_doubles(Nmax, a.big);
+        if (smem > avail || (npmax + 3) / 4 > 255)
             return fail(TC_EINVAL, "max(N) = " + std::to_string(Nmax) + " is too large for the shared-memory layout of this build "
-                                   "(the Cholesky workspace of the proposal factor must fit in one SM)");
+                                   "(one CTA per chain: the cell, the chain state, 8 proposal slots and 8 forward-model scratch areas must fit in one SM)");
         CUDA_TRY(cudaFuncSetAttribute(dram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         // time slices: a multiple of adaptint, ~32 per chain; persistent grid = resident CTA slots
         {
@@ -1819,6 +2006,7 @@ int tc_mcmc_run(const tc_cells *c, const tc_mcmc_opts *o, int nchains, const int
         CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, r.device));
         if (per_sm < 1) return fail(TC_EINVAL, "sampler kernel does not fit on this device");
         const int grid = std::min(nc, per_sm * sms);           // every CTA resident: slices may wait on each other
+        if (a.big && do_cov) CUDA_TRY(r.buf.alloc(a.gW, (size_t)grid * ldR));
         CUDA_TRY(cudaEventRecord(r.e0, r.st));
         dram_kernel<<<grid, DRAM_THREADS, smem, r.st>>>(a);
         CUDA_TRY(cudaGetLastError());

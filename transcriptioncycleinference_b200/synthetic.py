@@ -1,0 +1,43 @@
+"""Synthetic scale-up workload (BASELINE config 5): cells with N time points generated from the
+forward model with known parameters, for parameter-recovery checks and large-N throughput runs.
+
+t = cumulative sum of dt ~ U(0.15, 0.35) min starting at 0 (irregular like the data); truth drawn from the x0 / prior ranges
+of src/TranscriptionCycleMCMC.m:193-210 (v in [1,3], tau in [0,4], ton in [0,4], A in [0,1], MS2_basal, PP7_basal in [0,2],
+R = 15, dR ~ N(0,3)); signals = forward model on the raw grid (the plot call, :307-309, through tc_forward) + N(0, sigma)
+noise; NaN mask Bernoulli(0.5) on MS2 and (0.2) on PP7; numpy Philox generator, seed 20201028."""
+import numpy as np
+
+from .constructs import DEFAULT_CONSTRUCT
+from .engine import Cells
+
+
+def make_cells(ncells, N=400, seed=20201028, noise=1.0, construct=DEFAULT_CONSTRUCT, devices=(0,), batch=4096):
+    """-> (Cells resident on `devices`, truth [ncells, 7+N])"""
+    rng = np.random.Generator(np.random.Philox(seed))
+    t = np.concatenate([np.zeros((ncells, 1)), np.cumsum(rng.uniform(0.15, 0.35, (ncells, N - 1)), axis=1)], axis=1)
+    truth = np.zeros((ncells, 7 + N))
+    truth[:, 0] = rng.uniform(1, 3, ncells)
+    truth[:, 1] = rng.uniform(0, 4, ncells)
+    truth[:, 2] = rng.uniform(0, 4, ncells)
+    truth[:, 3] = rng.uniform(0, 2, ncells)
+    truth[:, 4] = rng.uniform(0, 2, ncells)
+    truth[:, 5] = rng.uniform(0, 1, ncells)
+    truth[:, 6] = 15.0
+    truth[:, 7:] = rng.normal(0.0, 3.0, (ncells, N))
+    ms2 = np.zeros((ncells, N)); pp7 = np.zeros((ncells, N))
+    for b0 in range(0, ncells, batch):
+        b1 = min(ncells, b0 + batch)
+        tmp = Cells(list(t[b0:b1]), list(np.zeros((b1 - b0, N))), list(np.zeros((b1 - b0, N))), construct=construct,
+                    devices=devices[:1])
+        m1, m2 = tmp.forward(np.arange(b1 - b0, dtype=np.int32), truth[b0:b1], on_raw_grid=True)
+        tmp.close()
+        ms2[b0:b1] = m1[:, :N]; pp7[b0:b1] = m2[:, :N]
+    ms2 += rng.normal(0.0, noise, ms2.shape); pp7 += rng.normal(0.0, noise, pp7.shape)
+    ms2[rng.random(ms2.shape) < 0.5] = np.nan
+    pp7[rng.random(pp7.shape) < 0.2] = np.nan
+    return Cells(list(t), list(ms2), list(pp7), construct=construct, devices=devices), truth
+
+
+def recovery(truth, mean, std, idx=(0, 1, 2), nsig=3.0):
+    """fraction of cells whose true (v, tau, ton) lie within posterior mean +- nsig sigma, per parameter"""
+    return [float(np.mean(np.abs(truth[:, i] - mean[:, i]) <= nsig * std[:, i])) for i in idx]
