@@ -141,6 +141,8 @@ __host__ __device__ inline int dram_wsz(int N, int big)
     }
     const int need2 = 2 * ((npar + 3) & ~3) + 16 * 32;        // generate(): a row of Z + the warp's B staging (16 k-steps x 32 lanes)
     if (w < need2) w = need2;
+    const int need3 = 4 * ((npar + 3) & ~3) + 48;              // gen_increments_tma(): one of the 8 ring stages (zero tile + tile row + slack)
+    if (big && w < need3) w = need3;
     return (w + 1) & ~1;
 }
 __host__ __device__ inline int dram_smem_doubles(int N, int big)
@@ -387,81 +389,246 @@ __device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, do
                  : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
+// ---- TMA bulk copies (cp.async.bulk, global -> shared, completion on an mbarrier) for the big layout.  A tile row of the
+// tiled upper-triangular matrices (tiles (r, c0..nt4-1)) is ONE contiguous segment of 128 (nt4 - c0) bytes, so the
+// factor streams through a ring of shared-memory stages with one bulk copy per tile row, issued by thread 0; the 8 warps
+// consume a stage (full barrier) and release it (empty barrier, one arrival per warp).
+#define TMA_MAXST 8
+__shared__ __align__(8) unsigned long long tc_mbar[2 * TMA_MAXST];          // full[0..7], empty[0..7]
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *b, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_inval(unsigned long long *b)
+{
+    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *b, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *b)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *b, unsigned parity)
+{
+    const unsigned addr = smem_u32(b);
+    unsigned ok;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// generic-proxy writes (st.global / st.shared) that a later bulk copy reads or overwrites: order them before the async proxy
+__device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// ring bookkeeping: use number g of the ring -> stage g % NS (NS a power of two); producer side (thread 0) and consumer
+// side (everyone)
+template <int NS>
+struct TmaRing {
+    static_assert(NS <= TMA_MAXST && (NS & (NS - 1)) == 0, "ring size");
+    int o0, sst;                                         // first stage (offset into tc_smem, doubles), stage stride
+    __device__ __forceinline__ void init(int o0_, int sst_)
+    {
+        o0 = o0_; sst = sst_;
+        fence_async_proxy();                             // the stages were last written by ordinary stores
+        __syncthreads();
+        if (threadIdx.x == 0)
+            for (int s_ = 0; s_ < NS; ++s_) { mbar_init(tc_mbar + s_, 1); mbar_init(tc_mbar + TMA_MAXST + s_, SPEC); }
+        __syncthreads();
+    }
+    // thread 0: arm use g for `total` bytes (waits until every warp has released the stage's previous use), then copy pieces
+    __device__ __forceinline__ void begin(int g, unsigned total) const
+    {
+        const int s_ = g & (NS - 1);
+        if (g >= NS) mbar_wait(tc_mbar + TMA_MAXST + s_, (unsigned)((g / NS - 1) & 1));
+        mbar_expect_tx(tc_mbar + s_, total);
+    }
+    __device__ __forceinline__ void copy(int g, int off, const double *src, unsigned bytes) const
+    {
+        const int s_ = g & (NS - 1);
+        bulk_g2s(tc_smem + o0 + s_ * sst + off, src, bytes, tc_mbar + s_);
+    }
+    __device__ __forceinline__ void issue(int g, const double *src, unsigned bytes) const { begin(g, bytes); copy(g, 0, src, bytes); }
+    __device__ __forceinline__ int acquire(int g) const  // -> offset of the stage into tc_smem (doubles)
+    {
+        const int s_ = g & (NS - 1);
+        mbar_wait(tc_mbar + s_, (unsigned)((g / NS) & 1));
+        return o0 + s_ * sst;
+    }
+    __device__ __forceinline__ void release(int g) const
+    {
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(tc_mbar + TMA_MAXST + (g & (NS - 1)));
+    }
+    __device__ __forceinline__ void fini() const         // after a __syncthreads that follows the last release
+    {
+        if (threadIdx.x == 0)
+            for (int s_ = 0; s_ < NS; ++s_) { mbar_inval(tc_mbar + s_); mbar_inval(tc_mbar + TMA_MAXST + s_); }
+    }
+};
+
+// chol_global, accumulation over `nr` staged tile rows (stride `rs` doubles) for the NM column blocks of this warp: per row one
+// A fragment and NM B fragments (constant offsets: block m sits 256 m doubles after the warp's first block) + NM MMAs.
+// Lanes whose tile column lies beyond the matrix read whatever follows the row (finite or not): those are columns / rows
+// of the 8x8 outputs that nobody reads.
+template <int NM>
+__device__ __forceinline__ void cg_accumulate(int oa, int ob, int nr, int rs, double (&acc)[7][2])
+{
+    // few column blocks = few independent MMA chains: split the rows over KS accumulator sets so that 4+ chains are in flight
+    constexpr int KS = NM >= 4 ? 1 : (NM >= 2 ? 2 : 4);
+    constexpr int U = KS > 1 ? KS : 2;
+    double loc[KS][NM][2];
+#pragma unroll
+    for (int s_ = 0; s_ < KS; ++s_)
+#pragma unroll
+        for (int m = 0; m < NM; ++m) { loc[s_][m][0] = s_ == 0 ? acc[m][0] : 0.0; loc[s_][m][1] = s_ == 0 ? acc[m][1] : 0.0; }
+#pragma unroll 1
+    for (int q = 0; q < nr; q += U, oa += U * rs, ob += U * rs) {
+        double av[U], bv[U][NM];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const bool on = q + u < nr;                                             // warp-uniform
+            av[u] = on ? tc_smem[oa + u * rs] : 0.0;
+#pragma unroll
+            for (int m = 0; m < NM; ++m) bv[u][m] = on ? tc_smem[ob + u * rs + 256 * m] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int m = 0; m < NM; ++m) dmma_m8n8k4(loc[u % KS][m][0], loc[u % KS][m][1], av[u], bv[u][m]);   // unconditional: a
+    }                                                                                                           // conditional mma.sync costs a WARPSYNC
+#pragma unroll
+    for (int m = 0; m < NM; ++m) {
+        double s0 = loc[0][m][0], s1 = loc[0][m][1];
+#pragma unroll
+        for (int s_ = 1; s_ < KS; ++s_) { s0 += loc[s_][m][0]; s1 += loc[s_][m][1]; }
+        acc[m][0] = s0; acc[m][1] = s1;
+    }
+}
+
 // Left-looking blocked Cholesky THROUGH HBM/L2, for proposal factors too large for shared memory (big layout):
 // R'R = gA * invn + qcovadj I (identity on the padding), gA and the result gW in the 4x4-tile layout of chol_tiled.
 // Panels of two tile rows (8 matrix rows).  Per panel:
 //  (1) S = A(panel rows, columns >= panel) - sum over the tile rows above of R(row, panel cols)' R(row, cols) on the FP64
-//      tensor cores: one mma.sync m8n8k4 per tile row above per 8-column block, fragments read straight from L2 (the 32
-//      B elements of a warp are two adjacent tiles = 256 contiguous bytes), column blocks dealt round-robin to the
-//      warps, 4 tile rows of loads (20 per lane) in flight;
-//  (2) warp 0 factors the 8x8 diagonal block in registers; (3) the rest of the panel is solved one column per thread;
-//  (4) the panel is written to gW.
-// S = shared-memory buffer [8][8 ceil(nt4 / 2) + 4].  Returns false when a pivot is not positive (gW is then
-// garbage; the caller keeps the old R).  Reads 11 MB from L2 at npar = 407 (a right-looking sweep would move 34 MB).
+//      tensor cores: one mma.sync m8n8k4 per tile row above per 8-column block.  The tile rows above stream through
+//      the TMA ring (one bulk copy of 128 (nt4 - b0) bytes per tile row, up to 7 in flight); a warp owns the column
+//      blocks w, w+8, .. (<= CG_MAXB), its accumulators stay in registers for the whole panel; fragment reads from
+//      a stage are conflict-free (the 32 B elements of a warp are two adjacent tiles);
+//  (2) warp 0 factors the 8x8 diagonal block in registers; (3) the rest of the panel is solved one column per thread
+//      while the first tile rows of the NEXT panel are already in flight; (4) the panel is written to gW.
+// S = shared-memory buffer [8][8 ceil(nt4 / 2) + 4] at `ws`, the ring stages after it (`ws_doubles` in all).  Returns
+// false when a pivot is not positive (gW is then garbage; the caller keeps the old R).  Reads 11 MB from L2 at
+// npar = 407 (a right-looking sweep would move 34 MB).
+#define CG_MAXB 7          // column blocks per warp: npar <= 8 * 8 * 7 = 448
+#define CG_NS 8            // ring stages (a power of two)
+#define CG_RPS 8           // tile rows per stage, at most
 __device__ __noinline__ bool chol_global(int nt4, int npar, const double *gA, double invn, double qcovadj, double *gW,
-                                         double *S, double *s_dinv, int *s_fail)
+                                         int o_ws, int ws_doubles, double *s_dinv, int *s_fail)
 {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, ar = lane >> 2, ak = lane & 3;
     const int ldS = 8 * ((nt4 + 1) >> 1) + 4;
     const int th = ar >> 2, inner = 4 * ak + (ar & 3);
+    double *S = tc_smem + o_ws;                        // (offset arithmetic on tc_smem compiles to LDS / STS)
+    TmaRing<CG_NS> ring;
+    {
+        // CG_NS stages of equal capacity; a stage holds as many tile rows of the current panel as fit (<= CG_RPS); 32 doubles of
+        // slack after the last one (cg_accumulate reads up to two tiles past a row)
+        const int o = (8 * ldS + 1) & ~1;
+        ring.init(o_ws + o, ((ws_doubles - o - 32) / CG_NS) & ~1);
+    }
     if (tid == 0) *s_fail = 0;
-    __syncthreads();
+#ifdef TC_SUBPROF
+    long long tq = clock64();
+#define CGP(i) do { if (tid == 0 && blockIdx.x == 0) { const long long t__ = clock64(); tc_subprof[i] += t__ - tq; tq = t__; } } while (0)
+#else
+#define CGP(i)
+#endif
+    int gi = 0, gc = 0, si = 0;        // ring uses issued (thread 0) / consumed; stages of the current panel already issued
+    bool ok = true;
+    // thread 0: issue stage u of the panel at b0 (rows u rps .. of the tile rows above, each 16 ntc doubles)
+#define CG_ISSUE(b0_, ntc_, rps_, u_)                                                                       \
+    {                                                                                                       \
+        const int r0__ = (u_) * (rps_), nr__ = min((rps_), (b0_) - r0__);                                     \
+        ring.begin(gi, 128u * (unsigned)((ntc_) * nr__));                                                   \
+        for (int q__ = 0; q__ < nr__; ++q__)                                                                \
+            ring.copy(gi, 16 * (ntc_) * q__, gW + 16 * (size_t)tidx(nt4, r0__ + q__, (b0_)), 128u * (unsigned)(ntc_)); \
+        ++gi;                                                                                               \
+    }
 #pragma unroll 1
     for (int b0 = 0; b0 < nt4; b0 += 2) {
         const bool two = b0 + 1 < nt4;
         const int ntc = nt4 - b0, nb = (ntc + 1) >> 1;
-        // (1) accumulate
-#pragma unroll 1
-        for (int jg = warp; jg < nb; jg += 4 * SPEC) {
-            double acc[4][2];
-            int offq[4];
-            bool okq[4];
+        const int rps = max(1, min(CG_RPS, ring.sst / (16 * ntc))), nst = (b0 + rps - 1) / rps;
+        // (1) accumulate over the tile rows 0 .. b0-1
+        {
+            double acc[CG_MAXB][2];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int j = jg + SPEC * q;
-                acc[q][0] = 0.0; acc[q][1] = 0.0;
-                okq[q] = j < nb && b0 + 2 * j + th < nt4;
-                offq[q] = 16 * (2 * j + th) + inner;
+            for (int m = 0; m < CG_MAXB; ++m) { acc[m][0] = 0.0; acc[m][1] = 0.0; }
+            if (tid == 0)
+                while (si < nst && si < CG_NS - 2) { CG_ISSUE(b0, ntc, rps, si) ++si; }
+            const int nmine = nb > warp ? (nb - warp + SPEC - 1) / SPEC : 0;          // column blocks warp, warp + 8, .. < nb
+            // the covariance entries of the panel are needed after the accumulation: pull them into L2 now
+            if (lane < 2 * nmine) {
+                const int j = warp + SPEC * (lane >> 1), tcn = b0 + 2 * j, trp = b0 + (lane & 1);
+                if (trp < nt4 && trp <= tcn)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(gA + 16 * (size_t)tidx(nt4, trp, tcn)));
+                if (trp < nt4 && tcn + 1 < nt4)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(gA + 16 * (size_t)tidx(nt4, trp, tcn + 1)));
             }
-            const bool oka = b0 + th < nt4;
-            const int offa = 16 * th + inner;
-            const double *pl = gW + 16 * (size_t)b0;               // tile (0, b0); tile (pr+1, b0) sits 16 (nt4 - pr - 1) doubles further
-            int dpl = 16 * (nt4 - 1);
-#define CG_BATCH(NR)                                                                                       \
-    {                                                                                                      \
-        double av[NR], bv[NR][4];                                                                          \
-        _Pragma("unroll") for (int u = 0; u < NR; ++u) {                                                   \
-            av[u] = oka ? __ldcg(pl + offa) : 0.0;                                                         \
-            _Pragma("unroll") for (int q = 0; q < 4; ++q) bv[u][q] = okq[q] ? __ldcg(pl + offq[q]) : 0.0;  \
-            pl += dpl; dpl -= 16;                                                                          \
-        }                                                                                                  \
-        _Pragma("unroll") for (int u = 0; u < NR; ++u)                                                     \
-            _Pragma("unroll") for (int q = 0; q < 4; ++q)                                                  \
-                if (jg + SPEC * q < nb) dmma_m8n8k4(acc[q][0], acc[q][1], av[u], bv[u][q]);                \
-    }
-            int pr = 0;
 #pragma unroll 1
-            for (; pr + 4 <= b0; pr += 4) CG_BATCH(4)
-            if (pr < b0) CG_BATCH(2)                               // b0 is even
-#undef CG_BATCH
-            // S = A - acc: lane holds rows ar, columns 2 ak, 2 ak + 1 of each of its blocks
+            for (int u = 0; u < nst; ++u) {
+                // issued CG_NS - 2 uses ahead: the stage being re-armed was released an iteration ago, so thread 0 does not
+                // hold the other warps in lock step
+                if (tid == 0 && si < nst) { CG_ISSUE(b0, ntc, rps, si) ++si; }
+                const int nr = min(rps, b0 - u * rps);
+                const int pa = ring.acquire(gc) + 16 * th + inner, pb = pa + 32 * warp;
+                switch (nmine) {                                                    // warp-uniform
+                case 7: cg_accumulate<7>(pa, pb, nr, 16 * ntc, acc); break;
+                case 6: cg_accumulate<6>(pa, pb, nr, 16 * ntc, acc); break;
+                case 5: cg_accumulate<5>(pa, pb, nr, 16 * ntc, acc); break;
+                case 4: cg_accumulate<4>(pa, pb, nr, 16 * ntc, acc); break;
+                case 3: cg_accumulate<3>(pa, pb, nr, 16 * ntc, acc); break;
+                case 2: cg_accumulate<2>(pa, pb, nr, 16 * ntc, acc); break;
+                case 1: cg_accumulate<1>(pa, pb, nr, 16 * ntc, acc); break;
+                default: break;
+                }
+                ring.release(gc);
+                ++gc;
+            }
+            CGP(13);
+            // S = A - acc: lane holds row ar, columns 2 ak, 2 ak + 1 of each of its blocks (all loads first: one L2 round trip)
             const int tr = b0 + th, rin = ar & 3, row = 4 * tr + rin;
+            double2 vin[CG_MAXB];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int j = jg + SPEC * q;
+            for (int m = 0; m < CG_MAXB; ++m) {
+                const int j = warp + SPEC * m, tcn = b0 + 2 * j + (ak >> 1);
+                vin[m] = make_double2(0.0, 0.0);
+                if (j < nb && tr <= tcn && tcn < nt4 && tr < nt4)
+                    vin[m] = __ldcg(reinterpret_cast<const double2 *>(gA + 16 * (size_t)tidx(nt4, tr, tcn) + 4 * rin + 2 * (ak & 1)));
+            }
+#pragma unroll
+            for (int m = 0; m < CG_MAXB; ++m) {
+                const int j = warp + SPEC * m;
                 if (j >= nb) continue;
                 const int tcn = b0 + 2 * j + (ak >> 1), col = 4 * tcn + 2 * (ak & 1);
-                double2 v = make_double2(0.0, 0.0);
+                double2 v = vin[m];
                 if (tr <= tcn && tcn < nt4 && tr < nt4) {
-                    v = __ldcg(reinterpret_cast<const double2 *>(gA + 16 * (size_t)tidx(nt4, tr, tcn) + 4 * rin + 2 * (ak & 1)));
                     v.x *= invn; v.y *= invn;
                     if (row == col) v.x = row < npar ? v.x + qcovadj : 1.0;
                     if (row == col + 1) v.y = row < npar ? v.y + qcovadj : 1.0;
                 }
-                *reinterpret_cast<double2 *>(S + ar * ldS + 8 * j + 2 * ak) = make_double2(v.x - acc[q][0], v.y - acc[q][1]);
+                *reinterpret_cast<double2 *>(S + ar * ldS + 8 * j + 2 * ak) = make_double2(v.x - acc[m][0], v.y - acc[m][1]);
             }
         }
         __syncthreads();
+        CGP(14);
         // (2) the diagonal block
         if (warp == 0) {
             double A[8][8], dinv[8];
@@ -481,7 +648,14 @@ __device__ __noinline__ bool chol_global(int nt4, int npar, const double *gA, do
             }
         }
         __syncthreads();
-        if (*s_fail) return false;                                // uniform
+        CGP(7);
+        if (*s_fail) { ok = false; break; }                       // uniform; nothing is in flight here
+        // the first stages of the next panel that hold only final rows (< b0) start streaming now
+        si = 0;
+        if (tid == 0 && b0 + 2 < nt4) {
+            const int ntc2 = ntc - 2, rps2 = max(1, min(CG_RPS, ring.sst / (16 * ntc2)));
+            while ((si + 1) * rps2 <= b0 && si < CG_NS - 2) { CG_ISSUE(b0 + 2, ntc2, rps2, si) ++si; }
+        }
         // (3) panel solve R12 = R11^-T A12: thread = one matrix column
         if (4 * ntc > 8) {
             double r11[8][8], di[8];
@@ -521,9 +695,15 @@ __device__ __noinline__ bool chol_global(int nt4, int npar, const double *gA, do
                 *reinterpret_cast<double2 *>(gW + 16 * (size_t)tidx(nt4, b0 + h, b0 + tcl) + 4 * r + 2 * c2) = make_double2(v0, v1);
             }
         }
-        __syncthreads();                                          // the next panel reads these tiles back from L2 (ld.cg)
+        fence_async_proxy();                                      // the next panels read these tiles back with bulk copies
+        __syncthreads();
+        CGP(15);
     }
-    return true;
+#undef CG_ISSUE
+#undef CGP
+    __syncthreads();
+    ring.fini();
+    return ok;
 }
 
 // per-candidate-step record of a round: out-of-bounds bits and prior sums of the two proposals (shared memory)
@@ -614,6 +794,129 @@ __device__ __noinline__ void emit_s2(const RunArgs &a, const ChainCtx &cx, S2Sta
     if (lane == 0) { st->sum += s2; st->sq_sum += sq; st->cnt += cnt; }
 }
 
+#define GEN_M 8
+// Big layout: the increments z1 R and z2 R/drscale of the GEN_M new steps (rows of Z = the ring slots) with R streamed through
+// the TMA ring: one bulk copy per tile row kk of R (tiles (kk, kk..nt4-1), 128 (nt4 - kk) bytes), consecutive tile rows
+// packed into a stage as long as they fit (<= GENB_RPS), so the mbarrier round trip (~90 cycles each way) is paid per stage
+// of 2-8 rows.  Row kk is k-step kk of every column tile: warp w owns the column tiles w, w+8, .. (<= GENB_MAXT) and keeps
+// their accumulators in registers for the whole pass (2 x GENB_MAXT independent MMA chains), so R crosses the SM once per
+// call and no lane issues per-element copies; the B fragment of tile column bj sits 16 (bj - kk) doubles into the row.
+#define GENB_MAXT 7        // column tiles per warp: npar <= 8 * 8 * 7 = 448
+#define GENB_NS 4          // ring stages
+#define GENB_RPS 8         // tile rows per stage, at most
+// one k-step for the NA column tiles that still have rows: accumulator j belongs to the j-th tile from the TOP (so the live
+// ones are always a prefix and the code is straight-line: a conditional mma.sync costs a WARPSYNC each); `bt` = B fragment
+// of the top tile, tile j sits 256 j doubles before it.  EDGE: the lowest live tile (j = NA-1) is in its last k-step,
+// where the lanes of its first tile column have nothing stored (below the diagonal).
+template <int NA, bool EDGE>
+__device__ __forceinline__ void genb_row(int bt, bool lowhalf, double2 za, double (&acc)[GENB_MAXT][4])
+{
+    double bv[NA];
+#pragma unroll
+    for (int j = 0; j < NA; ++j) bv[j] = tc_smem[bt - 256 * j];
+    if (EDGE && lowhalf) bv[NA - 1] = 0.0;
+#pragma unroll
+    for (int j = 0; j < NA; ++j) {
+        dmma_m8n8k4(acc[j][0], acc[j][1], za.x, bv[j]);
+        dmma_m8n8k4(acc[j][2], acc[j][3], za.y, bv[j]);
+    }
+}
+template <bool EDGE>
+__device__ __forceinline__ void genb_row_n(int na, int bt, bool lowhalf, double2 za, double (&acc)[GENB_MAXT][4])
+{
+    switch (na) {                                                       // warp-uniform
+    case 7: genb_row<7, EDGE>(bt, lowhalf, za, acc); break;
+    case 6: genb_row<6, EDGE>(bt, lowhalf, za, acc); break;
+    case 5: genb_row<5, EDGE>(bt, lowhalf, za, acc); break;
+    case 4: genb_row<4, EDGE>(bt, lowhalf, za, acc); break;
+    case 3: genb_row<3, EDGE>(bt, lowhalf, za, acc); break;
+    case 2: genb_row<2, EDGE>(bt, lowhalf, za, acc); break;
+    case 1: genb_row<1, EDGE>(bt, lowhalf, za, acc); break;
+    default: break;
+    }
+}
+#ifdef TC_SUBPROF
+#define GSP_T0 long long gt__ = clock64()
+#define GSP(i) do { if (threadIdx.x == 0 && cx.ch == 0) { const long long t__ = clock64(); tc_subprof[i] += t__ - gt__; gt__ = t__; } } while (0)
+#else
+#define GSP_T0
+#define GSP(i)
+#endif
+__device__ __noinline__ void gen_increments_tma(const ChainCtx &cx, int g0, int nnew)
+{
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, npar = cx.npar;
+    const int nt4 = (npar + 3) >> 2, NT = (npar + 7) >> 3;
+    const int ar = lane >> 2, ak = lane & 3, th = ar >> 2, inner = 4 * ak + (ar & 3);
+    TmaRing<GENB_NS> ring;
+    // the stages fill the per-warp areas (Z lives in the ring slots); one tile of room before the first stage and two after
+    // the last row of a stage: the fragment reads of a half-stored tile pair fall there and are discarded
+    const int sst = ((SPEC * cx.wsz - 16) / GENB_NS) & ~1, cap = sst - 32;
+    ring.init(cx.o_U + 16, sst);
+    // thread 0: next tile row to issue / its address (tile (pk, pk); the next diagonal tile is (nt4 - pk) tiles further) / stages issued
+    int pk = 0, pg = 0;
+    const double *src = cx.gRb;
+#define GENB_ISSUE()                                                                                        \
+    {                                                                                                       \
+        int kend__ = pk, used__ = 0;                                                                        \
+        while (kend__ < nt4 && kend__ - pk < GENB_RPS && used__ + 16 * (nt4 - kend__) <= cap) { used__ += 16 * (nt4 - kend__); ++kend__; } \
+        ring.issue(pg, src, 8u * (unsigned)used__);     /* consecutive tile rows are contiguous: ONE copy */ \
+        src += used__; pk = kend__;                                                                         \
+        ++pg;                                                                                               \
+    }
+    if (tid == 0)
+        while (pk < nt4 && pg < GENB_NS - 2) GENB_ISSUE()
+    double acc[GENB_MAXT][4];
+#pragma unroll
+    for (int m = 0; m < GENB_MAXT; ++m) { acc[m][0] = 0.0; acc[m][1] = 0.0; acc[m][2] = 0.0; acc[m][3] = 0.0; }
+    const int oa = cx.slot_o(g0 + ar) + 2 * ak;                     // A row of this lane = ring slot of step g0 + ar (slots of rows >= nnew
+                                                                    // hold stale data: their results are dropped)
+    const int mcnt = NT > warp ? (NT - warp + SPEC - 1) / SPEC : 0; // column tiles warp, warp + 8, .. < NT
+    int na = mcnt;                                                  // column tiles that still have rows at kk: the top `na` ones
+    int last = 2 * warp + 1;                                        // last tile row of the lowest live tile
+    // B fragment of the top tile (warp + 8 (mcnt - 1)), row kk: row start + ob - 16 kk
+    const int ob = 16 * (2 * (warp + SPEC * (mcnt - 1)) + th) + inner;
+    const int kmax = min(nt4, 2 * (warp + SPEC * (mcnt - 1)) + 2);  // rows this warp has MMAs for
+    int kk = 0;
+#pragma unroll 1
+    for (int g = 0; kk < nt4; ++g) {
+        GSP_T0;
+        if (tid == 0 && pk < nt4) GENB_ISSUE()
+        GSP(28);
+        int kend = kk, used = 0;                                    // the rows of stage g: the producer's packing rule
+        while (kend < nt4 && kend - kk < GENB_RPS && used + 16 * (nt4 - kend) <= cap) { used += 16 * (nt4 - kend); ++kend; }
+        int ro = ring.acquire(g);                                   // start of row kk
+        GSP(29);
+#pragma unroll 1
+        for (; kk < kend; ro += 16 * (nt4 - kk), ++kk) {
+            if (kk >= kmax) continue;
+            double2 za = make_double2(0.0, 0.0);
+            if (4 * kk + ak < npar) za = *reinterpret_cast<const double2 *>(tc_smem + oa + 8 * kk);
+            if (kk != last) genb_row_n<false>(na, ro + ob - 16 * kk, th == 0, za, acc);
+            else {
+                genb_row_n<true>(na, ro + ob - 16 * kk, th == 0, za, acc);
+                --na; last += 2 * SPEC;
+            }
+        }
+        GSP(30);
+        ring.release(g);
+        GSP(31);
+    }
+#undef GENB_ISSUE
+    __syncthreads();                                                // every warp is done reading Z: the increments overwrite it
+    if (ar < nnew) {
+        const int oo = cx.slot_o(g0 + ar);
+        const double inv_dr = cx.inv_dr;
+#pragma unroll
+        for (int j = 0; j < GENB_MAXT; ++j) {
+            const int jc = 8 * (warp + SPEC * (mcnt - 1 - j)) + 2 * ak;     // accumulator j = the j-th tile from the top
+            if (j < mcnt && jc < npar) *reinterpret_cast<double2 *>(tc_smem + oo + 2 * jc) = make_double2(acc[j][0], acc[j][2] * inv_dr);
+            if (j < mcnt && jc + 1 < npar) *reinterpret_cast<double2 *>(tc_smem + oo + 2 * jc + 2) = make_double2(acc[j][1], acc[j][3] * inv_dr);
+        }
+    }
+    __syncthreads();
+    ring.fini();
+}
+
 // Randomness and proposal increments for steps [g0, g0+nnew), nnew <= GEN_M = 8 (one MMA row group).
 //   1. Philox normals z1, z2 -> scratch Z (the idle per-warp areas; row = step - g0, (z1, z2) interleaved per
 //      parameter); u1, u2, chi2 -> the scalars of the step's ring slot.
@@ -623,7 +926,10 @@ __device__ __noinline__ void emit_s2(const RunArgs &a, const ChainCtx &cx, S2Sta
 //      accumulator sets).  Every element of R is needed exactly once per call, so R is not staged as a matrix:
 //      each lane pulls its own B elements HBM/L2 -> shared memory with 8-byte cp.async into private staging slots,
 //      two groups of 8 k-steps in flight.
-#define GEN_M 8
+#ifndef TC_TMA_ALL
+#define TC_TMA_ALL 0        // development switch: 1 = the TMA-staged increments for the regular layout too (measured 5 % slower at N = 120:
+                            // R is 76 KB there, and the per-lane cp.async stream needs no CTA-wide stage hand-over)
+#endif
 #ifndef TC_NOLOAD
 #define TC_NOLOAD 0        // development switch: 1 = skip the loads of R (isolates the MMA loop in scripts/subprof.py)
 #endif
@@ -631,7 +937,10 @@ __device__ __noinline__ void generate(const RunArgs &a, const ChainCtx &cx, int 
 {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, npar = cx.npar;
     const int zs = 2 * cx.npad;                                   // doubles per row of Z
-    double *Z = cx.U;
+    // big layout: row sidx of Z is the ring slot of step g0 + sidx itself (the increments overwrite it at the end), which
+    // leaves the per-warp areas to the TMA stages of R
+    const bool big = a.big != 0;
+#define ZROW(sidx) ((big || TC_TMA_ALL) ? cx.slot_d(g0 + (sidx)) : cx.U + (size_t)(sidx) * zs)
     SUBP_BEGIN;
 #ifdef TC_SUBPROF
     if (tid == 0 && cx.ch == 0) { tc_subprof[26] += 1; tc_subprof[27] += nnew; }
@@ -640,7 +949,7 @@ __device__ __noinline__ void generate(const RunArgs &a, const ChainCtx &cx, int 
 #pragma unroll 1
         for (int sidx = 0; sidx < nnew; ++sidx) {
             const int st = g0 + sidx;
-            double *dz = Z + (size_t)sidx * zs, *sc = cx.slot_sc(st);
+            double *dz = ZROW(sidx), *sc = cx.slot_sc(st);
             const size_t g = ((size_t)cx.ch * a.nsimu + st) * cx.ld;
 #pragma unroll 1
             for (int i = tid; i < npar; i += DRAM_THREADS) { dz[2 * i] = a.z1[g + i]; dz[2 * i + 1] = a.z2[g + i]; }
@@ -669,7 +978,7 @@ __device__ __noinline__ void generate(const RunArgs &a, const ChainCtx &cx, int 
 #pragma unroll 1                                                    // (it + 0.5 is >= 0.5/npairs away from a multiple of npairs)
         for (int it = (tid + 32) & (DRAM_THREADS - 1); it < nnew * npairs; it += DRAM_THREADS) {
             const int sidx = (int)(((float)it + 0.5f) * inv_np), q2 = it - sidx * npairs;
-            double *dz = Z + (size_t)sidx * zs;
+            double *dz = ZROW(sidx);
             const double4 z = normal_quad(a.seed, cx.uid, g0 + sidx, q2);
             *reinterpret_cast<double2 *>(dz + 4 * q2) = make_double2(z.x, z.z);          // (z1, z2) of parameter 2q
             if (2 * q2 + 1 < npar) *reinterpret_cast<double2 *>(dz + 4 * q2 + 2) = make_double2(z.y, z.w);
@@ -679,7 +988,7 @@ __device__ __noinline__ void generate(const RunArgs &a, const ChainCtx &cx, int 
     SUBP(0);
     // q1 = -1/2 (|(y1-y2) R^-1|^2 - |(y1-x) R^-1|^2) = -1/2 (|z1 - z2/drscale|^2 - |z1|^2)
     if (warp < nnew) {
-        const double2 *dz = reinterpret_cast<const double2 *>(Z + (size_t)warp * zs);
+        const double2 *dz = reinterpret_cast<const double2 *>(ZROW(warp));
         double n1 = 0.0, n0 = 0.0;
 #pragma unroll 1
         for (int i = lane; i < npar; i += 32) {
@@ -695,7 +1004,7 @@ __device__ __noinline__ void generate(const RunArgs &a, const ChainCtx &cx, int 
     if (r_diag) {
 #pragma unroll 1
         for (int sidx = 0; sidx < nnew; ++sidx) {
-            const double2 *dz = reinterpret_cast<const double2 *>(Z + (size_t)sidx * zs);
+            const double2 *dz = reinterpret_cast<const double2 *>(ZROW(sidx));
             double2 *out = reinterpret_cast<double2 *>(cx.slot_d(g0 + sidx));
 #pragma unroll 1
             for (int j = tid; j < npar; j += DRAM_THREADS) {
@@ -704,6 +1013,9 @@ __device__ __noinline__ void generate(const RunArgs &a, const ChainCtx &cx, int 
                 out[j] = make_double2(zz.x * r, zz.y * (r * cx.inv_dr));
             }
         }
+    } else if (big || TC_TMA_ALL) {
+        gen_increments_tma(cx, g0, nnew);
+        SUBP(2);
     } else {
         const int NT = (npar + 7) >> 3;                              // column tiles of 8
         const int ar = lane >> 2, ak = lane & 3;                     // A[row = step][k], B[k][col]
@@ -781,6 +1093,7 @@ __device__ __noinline__ void generate(const RunArgs &a, const ChainCtx &cx, int 
     }
     __syncthreads();
     SUBP(3);
+#undef ZROW
 }
 
 __device__ __forceinline__ void warp_sum2(double &p, double &q)
@@ -835,6 +1148,23 @@ __device__ __noinline__ int resolve_dr(const double *sc, bool o1, double x12, do
     double a13 = e13 * (1.0 - a32) / (1.0 - a12);
     a13 = a13 > 1.0 ? 1.0 : a13;
     return ((a13 >= 1.0) || (a13 > sc[1])) ? 1 : 0;
+}
+
+// dst[e] = src[e] * sc, e < n 16-byte units, src in HBM/L2: 8 independent loads in flight per thread (written as one loop
+// the compiler keeps every load behind the previous store: dst may alias src for all it knows)
+__device__ __forceinline__ void scaled_copy_cg(double2 *dst, const double2 *src, int n, double sc)
+{
+    int e = threadIdx.x;
+#pragma unroll 1
+    for (; e + 7 * DRAM_THREADS < n; e += 8 * DRAM_THREADS) {
+        double2 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldcg(src + e + u * DRAM_THREADS);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) dst[e + u * DRAM_THREADS] = make_double2(v[u].x * sc, v[u].y * sc);
+    }
+#pragma unroll 1
+    for (; e < n; e += DRAM_THREADS) { const double2 v = __ldcg(src + e); dst[e] = make_double2(v.x * sc, v.y * sc); }
 }
 
 // Adaptation after the step with isimu (a multiple of adaptint).  The block of the last adaptint chain rows
@@ -946,6 +1276,7 @@ __device__ __noinline__ int adapt(const RunArgs &a, const ChainCtx &cx, int isim
             } else {
 #pragma unroll 1
                 for (int i = tid; i < 16 * (((npar + 3) >> 2) * (((npar + 3) >> 2) + 1) / 2); i += DRAM_THREADS) cx.gRb[i] = __ldcg(cx.gRb + i) * f;
+                if (a.big) fence_async_proxy();
             }
         }
     } else {
@@ -955,14 +1286,11 @@ __device__ __noinline__ int adapt(const RunArgs &a, const ChainCtx &cx, int isim
         if (a.big) {
             // the factor does not fit in shared memory: factorise through HBM/L2 into this CTA's workspace
             double *gW = a.gW + (size_t)blockIdx.x * a.ldR;
-            const bool ok = chol_global(nt4, npar, cx.gM2, invn, a.qcovadj, gW, cx.ring, s_dinv, s_flag);
+            const bool ok = chol_global(nt4, npar, cx.gM2, invn, a.qcovadj, gW, cx.o_ring, (cx.ring_mask + 1) * cx.slot_sz + SPEC * cx.wsz, s_dinv, s_flag);
             SUBP(11);
             if (ok) {
-                const double2 *src = reinterpret_cast<const double2 *>(gW);
-                double2 *dst = reinterpret_cast<double2 *>(cx.gRb);
-                const double sc = cx.adascale;
-#pragma unroll 8
-                for (int e = tid; e < 8 * T4; e += DRAM_THREADS) { const double2 v = __ldcg(src + e); dst[e] = make_double2(v.x * sc, v.y * sc); }
+                scaled_copy_cg(reinterpret_cast<double2 *>(cx.gRb), reinterpret_cast<const double2 *>(gW), 8 * T4, cx.adascale);
+                fence_async_proxy();                                // generate() reads R back with bulk copies
             }
             __syncthreads();
             SUBP(12);
@@ -976,12 +1304,7 @@ __device__ __noinline__ int adapt(const RunArgs &a, const ChainCtx &cx, int isim
             while (rem >= nt4 - b) { rem -= nt4 - b; ++b; }
             tab[t] = (unsigned short)((b << 8) | (b + rem));
         }
-        {
-            const double2 *src = reinterpret_cast<const double2 *>(cx.gM2);
-            double2 *dst = reinterpret_cast<double2 *>(W);
-#pragma unroll 8
-            for (int e = tid; e < 8 * T4; e += DRAM_THREADS) { const double2 v = __ldcg(src + e); dst[e] = make_double2(v.x * invn, v.y * invn); }
-        }
+        scaled_copy_cg(reinterpret_cast<double2 *>(W), reinterpret_cast<const double2 *>(cx.gM2), 8 * T4, invn);
         __syncthreads();
         // + qcovadj I; identity on the padding rows (the rest of the padding is zero: it only ever accumulated zeros)
 #pragma unroll 1
