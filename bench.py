@@ -60,6 +60,7 @@ def parse():
     ap.add_argument("--n-burn", type=int, default=10000)
     ap.add_argument("--cpu-sample-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-config5", action="store_true", help="skip the secondary N = 400 leg")
     return ap.parse_args()
 
 
@@ -271,12 +272,32 @@ def run_ours(args, g):
     # secondary: the batched SS kernel alone (device-resident inputs), the compute-bound leg
     if rank == 0:
         line["ss_kernel"] = ss_kernel_leg(cells, g, peak_dfma, torch)
+        if not args.no_config5:
+            line["config5_scale"] = config5_leg(local)
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(g, args.workload, args.n_burn, args.cpu_sample_seconds)
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def config5_leg(device, ncells=1184, N=400, nsteps=2000):
+    """Secondary: BASELINE config 5's series length (N = 400, npar = 407: the big layout of the sampler) at a single-GPU
+    scale — synthetic cells from the forward model (transcriptioncycleinference_b200/synthetic.py), 8 chains per SM."""
+    from transcriptioncycleinference_b200 import _lib, setup_cell, synthetic
+    cells5, _ = synthetic.make_cells(ncells, N, devices=(device,))
+    cc = np.arange(ncells, dtype=np.int32)
+    inputs = setup_cell.chain_inputs(cells5, cc, np.random.default_rng(5))
+    opts = _lib.default_opts(nsimu=nsteps, burnintime=nsteps // 2, n_burn=nsteps // 2, ngpus=1)
+    opts.devices[0] = device
+    ks = []
+    for _ in range(3):
+        ks.append(cells5.mcmc_run(opts, cc, *inputs)["kernel_seconds"])
+    cells5.close()
+    t = float(np.mean(ks[1:]))
+    return dict(workload="%d synthetic cells x N=%d (npar=%d), 1 chain each, n_steps=%d, n_burn=%d" % (ncells, N, N + 7, nsteps, nsteps // 2),
+                chain_steps_per_s=ncells * nsteps / t, ms=t * 1e3)
 
 
 def ss_kernel_leg(cells, g, peak_dfma, torch):

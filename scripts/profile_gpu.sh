@@ -5,7 +5,7 @@ R=${1:-r01}
 mkdir -p gpurun_out
 python bench.py > gpurun_out/bench_$R.json 2> gpurun_out/bench_$R.err || exit 1
 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/bench_ref_$R.json 2>> gpurun_out/bench_$R.err
-CMD="python bench.py --steps 1 --warmup 3 --n-steps 20000 --no-cpu-baseline"
+CMD="python bench.py --steps 1 --warmup 3 --n-steps 20000 --no-cpu-baseline --no-config5"
 $CMD > gpurun_out/plain_$R.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$R.csv $CMD > gpurun_out/ncu_list_$R.log 2>&1
 $CMD > gpurun_out/plain2_$R.log 2>&1 &&

@@ -13,7 +13,7 @@ def raw(rep):
     txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
     return rows[0], rows[1], rows[2]
-for name in ("dram", "ss"):
+for name in ("dram", "ss", "c5"):
     rep = "gpurun_out/prof_%s_%s.ncu-rep" % (name, R)
     if not os.path.exists(rep):
         continue

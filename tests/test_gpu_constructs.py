@@ -115,3 +115,32 @@ def test_series_length_extremes_replay(orc, N):
         assert np.array_equal(out["flags"][i], ref["flags"]), (N, i)
         np.testing.assert_allclose(out["chain"][i][:, :npar], ref["chain"], rtol=0, atol=1e-7)
     cells.close()
+
+
+def test_synthetic_config5_workload_big_layout():
+    """BASELINE config 5 at a small scale: synthetic N = 400 cells from the forward model (synthetic.make_cells), production
+    Philox run on the big layout.  Checks what does not depend on how well the reference's sampler mixes: every adaptation
+    factorised (no Cholesky failure), the fit explains the data better than the start (posterior sigma below the initial
+    one), chains independent of how they are batched (bit-identical), summaries inside the bounds."""
+    from transcriptioncycleinference_b200 import _lib, setup_cell, synthetic
+    if _lib.device_count() < 1:
+        pytest.skip("no CUDA device")
+    cells, truth = synthetic.make_cells(12, 400)
+    assert cells.Nmax == 400 and truth.shape == (12, 407)
+    assert 0.35 < np.isnan(cells.ms2).mean() < 0.65 and 0.1 < np.isnan(cells.pp7).mean() < 0.3
+    cc = np.arange(12, dtype=np.int32)
+    inputs = setup_cell.chain_inputs(cells, cc, np.random.default_rng(5))
+    opts = _lib.default_opts(nsimu=1500, burnintime=500, n_burn=500)
+    out = cells.mcmc_run(opts, cc, *inputs)
+    cnt = out["counters"]
+    assert np.all(cnt[:, 4] == 11) and np.all(cnt[:, 5] == 0)             # adaptations at 500, 600, .., 1500
+    ss0 = cells.ss_batch(cc, inputs[0])
+    n_obs = np.array([np.sum(~np.isnan(cells.cell(c)[1])) + np.sum(~np.isnan(cells.cell(c)[2])) for c in cc])
+    assert np.all(out["sig"][:, 0] < np.sqrt(ss0 / n_obs))
+    lo, hi = inputs[2], inputs[3]
+    assert np.all(out["mean"] >= lo - 1e-12) and np.all(out["mean"] <= hi + 1e-12)
+    sub = cells.mcmc_run(opts, cc[5:7], *[x[5:7] for x in inputs], chain_uid=np.array([5, 6], dtype=np.uint64))
+    assert np.array_equal(sub["mean"], out["mean"][5:7]) and np.array_equal(sub["sig"], out["sig"][5:7])
+    rec = synthetic.recovery(truth, out["mean"], out["std"])
+    assert len(rec) == 3 and all(0.0 <= r <= 1.0 for r in rec)
+    cells.close()

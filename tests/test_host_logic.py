@@ -156,3 +156,11 @@ def test_rhat_from_summaries_matches_raw_chain_formula():
     assert np.all(ne <= m * n) and ne[-1] < 20
     with pytest.raises(ValueError):
         diagnostics.rhat_from_summaries(chains.mean(axis=1)[:1], chains.std(axis=1)[:1], n)
+
+
+def test_synthetic_recovery_fraction():
+    """synthetic.recovery: fraction of cells whose truth lies within mean +- 3 sigma, per parameter (config 5's check)."""
+    from transcriptioncycleinference_b200 import synthetic
+    truth = np.zeros((4, 10)); mean = np.zeros((4, 10)); std = np.ones((4, 10))
+    mean[0, 0] = 2.9; mean[1, 0] = 3.1; mean[2, 1] = -4.0
+    assert synthetic.recovery(truth, mean, std) == [0.75, 0.75, 1.0]
