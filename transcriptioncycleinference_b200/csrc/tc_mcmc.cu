@@ -821,20 +821,30 @@ __device__ __forceinline__ void genb_row(int bt, bool lowhalf, double2 za, doubl
         dmma_m8n8k4(acc[j][2], acc[j][3], za.y, bv[j]);
     }
 }
-template <bool EDGE>
-__device__ __forceinline__ void genb_row_n(int na, int bt, bool lowhalf, double2 za, double (&acc)[GENB_MAXT][4])
+// k-steps [kk, kend) of the NA live tiles, none of them an edge row: a tight loop (the dispatch on NA is paid once per run
+// of rows, not per row).  bt = B fragment of the top tile in row kk; it moves on by one tile row minus one tile per row.
+template <int NA>
+__device__ __forceinline__ void genb_rows(int kk, int kend, int &bt, int oa, int nt4, int npar, int ak, double (&acc)[GENB_MAXT][4])
 {
-    switch (na) {                                                       // warp-uniform
-    case 7: genb_row<7, EDGE>(bt, lowhalf, za, acc); break;
-    case 6: genb_row<6, EDGE>(bt, lowhalf, za, acc); break;
-    case 5: genb_row<5, EDGE>(bt, lowhalf, za, acc); break;
-    case 4: genb_row<4, EDGE>(bt, lowhalf, za, acc); break;
-    case 3: genb_row<3, EDGE>(bt, lowhalf, za, acc); break;
-    case 2: genb_row<2, EDGE>(bt, lowhalf, za, acc); break;
-    case 1: genb_row<1, EDGE>(bt, lowhalf, za, acc); break;
-    default: break;
+    int dbt = 16 * (nt4 - kk - 1);
+#pragma unroll 2
+    for (; kk < kend; ++kk, bt += dbt, dbt -= 16) {
+        double2 za = make_double2(0.0, 0.0);                            // rows of the padding carry no increment
+        if (4 * kk + ak < npar) za = *reinterpret_cast<const double2 *>(tc_smem + oa + 8 * kk);
+        genb_row<NA, false>(bt, false, za, acc);
     }
 }
+#define GENB_DISPATCH(na_, CALL)                                                                            \
+    switch (na_) {                                                      /* warp-uniform */                  \
+    case 7: { constexpr int NA_ = 7; CALL; } break;                                                         \
+    case 6: { constexpr int NA_ = 6; CALL; } break;                                                         \
+    case 5: { constexpr int NA_ = 5; CALL; } break;                                                         \
+    case 4: { constexpr int NA_ = 4; CALL; } break;                                                         \
+    case 3: { constexpr int NA_ = 3; CALL; } break;                                                         \
+    case 2: { constexpr int NA_ = 2; CALL; } break;                                                         \
+    case 1: { constexpr int NA_ = 1; CALL; } break;                                                         \
+    default: break;                                                                                         \
+    }
 #ifdef TC_SUBPROF
 #define GSP_T0 long long gt__ = clock64()
 #define GSP(i) do { if (threadIdx.x == 0 && cx.ch == 0) { const long long t__ = clock64(); tc_subprof[i] += t__ - gt__; gt__ = t__; } } while (0)
@@ -884,19 +894,26 @@ __device__ __noinline__ void gen_increments_tma(const ChainCtx &cx, int g0, int 
         GSP(28);
         int kend = kk, used = 0;                                    // the rows of stage g: the producer's packing rule
         while (kend < nt4 && kend - kk < GENB_RPS && used + 16 * (nt4 - kend) <= cap) { used += 16 * (nt4 - kend); ++kend; }
-        int ro = ring.acquire(g);                                   // start of row kk
+        int bt = ring.acquire(g) + ob - 16 * kk;                    // B fragment of the top tile in row kk (stage start = row kk)
         GSP(29);
+        int k = kk;
 #pragma unroll 1
-        for (; kk < kend; ro += 16 * (nt4 - kk), ++kk) {
-            if (kk >= kmax) continue;
-            double2 za = make_double2(0.0, 0.0);
-            if (4 * kk + ak < npar) za = *reinterpret_cast<const double2 *>(tc_smem + oa + 8 * kk);
-            if (kk != last) genb_row_n<false>(na, ro + ob - 16 * kk, th == 0, za, acc);
-            else {
-                genb_row_n<true>(na, ro + ob - 16 * kk, th == 0, za, acc);
-                --na; last += 2 * SPEC;
+        while (k < kend && k < kmax) {
+            const int kto = min(kend, min(last, kmax));             // the rows before the next edge row
+            if (k < kto) {
+                GENB_DISPATCH(na, genb_rows<NA_>(k, kto, bt, oa, nt4, npar, ak, acc))
+                k = kto;
+            }
+            if (k < kend && k == last && k < kmax) {
+                // the lowest live tile is in its last k-step: the lanes of its first tile column have nothing stored there
+                double2 za = make_double2(0.0, 0.0);
+                if (4 * k + ak < npar) za = *reinterpret_cast<const double2 *>(tc_smem + oa + 8 * k);
+                GENB_DISPATCH(na, (genb_row<NA_, true>(bt, th == 0, za, acc)))
+                bt += 16 * (nt4 - k - 1);
+                ++k; --na; last += 2 * SPEC;
             }
         }
+        kk = kend;
         GSP(30);
         ring.release(g);
         GSP(31);
@@ -1048,16 +1065,20 @@ __device__ __noinline__ void generate(const RunArgs &a, const ChainCtx &cx, int 
             const double *pl = gR + 16 * bj + inner;
             // B fragments: 8-byte cp.async into this lane's private staging slots, two groups of 8 k-steps in flight
             // (commit / wait_group order the arrivals; a register pipeline would have to share the warp's 6 scoreboards)
-#define GEN_ISSUE(slot)                                                                                     \
+#define GEN_ISSUE(slot, live)                                                                               \
     {                                                                                                       \
-        if (il <= bj && !TC_NOLOAD) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sstg + 256u * (unsigned)(slot)), "l"(pl) : "memory"); \
+        if ((live) && il <= bj && !TC_NOLOAD) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sstg + 256u * (unsigned)(slot)), "l"(pl) : "memory"); \
         else tc_smem[ostg + 32 * (slot)] = 0.0;                                                             \
         pl += dpl; dpl -= 16; il += 1;                                                                      \
     }
+            // k-steps are consumed in groups of 8; the slots of a group past the last k-step are zero-filled, so that the MMAs
+            // of a group are unconditional (an mma.sync under a condition costs a WARPSYNC + predicate each)
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
+                if (8 * g < ks) {
 #pragma unroll
-                for (int u = 0; u < 8; ++u) if (8 * g + u < ks) GEN_ISSUE(8 * g + u)
+                    for (int u = 0; u < 8; ++u) GEN_ISSUE(8 * g + u, 8 * g + u < ks)
+                }
                 asm volatile("cp.async.commit_group;" ::: "memory");
             }
 #pragma unroll 1
@@ -1066,17 +1087,17 @@ __device__ __noinline__ void generate(const RunArgs &a, const ChainCtx &cx, int 
                 const int base = kk & 15;
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
-                    if (kk + u < ks) {                               // warp-uniform
-                        const double bv = tc_smem[ostg + 32 * (base + u)];
-                        double2 za = make_double2(0.0, 0.0);
-                        if (ic < npar) za = *reinterpret_cast<const double2 *>(tc_smem + oa + 2 * ic);
-                        dmma_m8n8k4(acc[u & 3][0], acc[u & 3][1], za.x, bv);
-                        dmma_m8n8k4(acc[u & 3][2], acc[u & 3][3], za.y, bv);
-                        ic += 4;
-                    }
+                    const double bv = tc_smem[ostg + 32 * (base + u)];
+                    double2 za = make_double2(0.0, 0.0);
+                    if (ic < npar) za = *reinterpret_cast<const double2 *>(tc_smem + oa + 2 * ic);
+                    dmma_m8n8k4(acc[u & 3][0], acc[u & 3][1], za.x, bv);
+                    dmma_m8n8k4(acc[u & 3][2], acc[u & 3][3], za.y, bv);
+                    ic += 4;
                 }
+                if (kk + 16 < ks) {
 #pragma unroll
-                for (int u = 0; u < 8; ++u) if (kk + 16 + u < ks) GEN_ISSUE(base + u)
+                    for (int u = 0; u < 8; ++u) GEN_ISSUE(base + u, kk + 16 + u < ks)
+                }
                 asm volatile("cp.async.commit_group;" ::: "memory");
             }
             asm volatile("cp.async.wait_group 0;" ::: "memory");
