@@ -1197,7 +1197,8 @@ __device__ __noinline__ int adapt(const RunArgs &a, const ChainCtx &cx, int isim
                                   int ndist, double *s_dinv, int *s_flag)
 {
     const int tid = threadIdx.x, npar = cx.npar, ld = cx.ld;
-    double *sw = cx.ring;                              // workspace: ring + per-warp areas (idle now); sqrt(weight) per row first
+    double *sw = tc_smem + cx.o_ring;                  // workspace: ring + per-warp areas (idle now); sqrt(weight) per row first
+                                                       // (offset arithmetic on tc_smem compiles to LDS / STS, cx.ring would be generic)
     SUBP_BEGIN;
     if (a.do_cov) {
         const int m = a.adaptint;
@@ -1216,7 +1217,7 @@ __device__ __noinline__ int adapt(const RunArgs &a, const ChainCtx &cx, int isim
         const int warp = tid >> 5, lane = tid & 31, ar = lane >> 2, ak = lane & 3;
         const int nt4 = (npar + 3) >> 2, NT = (npar + 7) >> 3, NB = NT * (NT + 1) / 2;
         const int ldu = 8 * NT + 4;                                   // row stride of U (doubles); + 4: rows 0..3 of a k-step hit different banks
-        double *U = cx.ring + COV_CR + 8;                             // after sw[COV_CR]
+        double *U = tc_smem + cx.o_ring + COV_CR + 8;                 // after sw[COV_CR]
 #pragma unroll 1
         for (int r0 = 0; r0 < nrows; r0 += COV_CR) {
             const int rc = min(COV_CR, nrows - r0), rc4 = (rc + 3) & ~3;
@@ -1240,16 +1241,16 @@ __device__ __noinline__ int adapt(const RunArgs &a, const ChainCtx &cx, int isim
                 }
             }
             __syncthreads();
+            // blocks b and b + SPEC (upper triangle of 8x8 blocks, row-major): (block row, position in the row) advance by
+            // 2 SPEC blocks per iteration
+            int bi0 = 0, rm0 = warp, bi1 = 0, rm1 = warp + SPEC;
+            while (bi0 < NT && rm0 >= NT - bi0) { rm0 -= NT - bi0; ++bi0; }
+            while (bi1 < NT && rm1 >= NT - bi1) { rm1 -= NT - bi1; ++bi1; }
 #pragma unroll 1
             for (int b = warp; b < NB; b += 2 * SPEC) {
-                // blocks b and b + SPEC (upper triangle of 8x8 blocks, row-major)
-                int bi0 = 0, rem = b;
-                while (rem >= NT - bi0) { rem -= NT - bi0; ++bi0; }
-                const int bj0 = bi0 + rem;
+                const int bj0 = bi0 + rm0;
                 const bool two = b + SPEC < NB;
-                int bi1 = 0; rem = two ? b + SPEC : 0;
-                while (rem >= NT - bi1) { rem -= NT - bi1; ++bi1; }
-                const int bj1 = bi1 + rem;
+                const int bi1u = two ? bi1 : 0, bj1 = two ? bi1 + rm1 : 0;      // no second block: block 0 again, result dropped
                 // the old values of the two blocks: loaded first, so that their L2 latency overlaps with the MMAs
                 double2 *g0 = nullptr, *g1 = nullptr;
                 {
@@ -1258,7 +1259,7 @@ __device__ __noinline__ int adapt(const RunArgs &a, const ChainCtx &cx, int isim
                         g0 = reinterpret_cast<double2 *>(cx.gM2 + 16 * (size_t)tidx(nt4, tr, tcn) + 4 * (row & 3) + (col & 3));
                 }
                 if (two) {
-                    const int row = 8 * bi1 + ar, col = 8 * bj1 + 2 * ak, tr = row >> 2, tcn = col >> 2;
+                    const int row = 8 * bi1u + ar, col = 8 * bj1 + 2 * ak, tr = row >> 2, tcn = col >> 2;
                     if (tr <= tcn && tcn < nt4)
                         g1 = reinterpret_cast<double2 *>(cx.gM2 + 16 * (size_t)tidx(nt4, tr, tcn) + 4 * (row & 3) + (col & 3));
                 }
@@ -1267,14 +1268,17 @@ __device__ __noinline__ int adapt(const RunArgs &a, const ChainCtx &cx, int isim
                 if (g1) o1 = __ldcg(g1);
                 double d00 = 0.0, d01 = 0.0, d10 = 0.0, d11 = 0.0;
                 const double *ua0 = U + ak * ldu + 8 * bi0 + ar, *ub0 = U + ak * ldu + 8 * bj0 + ar;
-                const double *ua1 = U + ak * ldu + 8 * bi1 + ar, *ub1 = U + ak * ldu + 8 * bj1 + ar;
+                const double *ua1 = U + ak * ldu + 8 * bi1u + ar, *ub1 = U + ak * ldu + 8 * bj1 + ar;
 #pragma unroll 2
                 for (int kk = 0; kk < rc4; kk += 4) {
                     dmma_m8n8k4(d00, d01, ua0[kk * ldu], ub0[kk * ldu]);
-                    if (two) dmma_m8n8k4(d10, d11, ua1[kk * ldu], ub1[kk * ldu]);      // warp-uniform
+                    dmma_m8n8k4(d10, d11, ua1[kk * ldu], ub1[kk * ldu]);               // unconditional (no second block: block 0 again, dropped)
                 }
                 if (g0) *g0 = make_double2(o0.x + d00, o0.y + d01);
                 if (g1) *g1 = make_double2(o1.x + d10, o1.y + d11);
+                rm0 += 2 * SPEC; rm1 += 2 * SPEC;
+                while (bi0 < NT && rm0 >= NT - bi0) { rm0 -= NT - bi0; ++bi0; }
+                while (bi1 < NT && rm1 >= NT - bi1) { rm1 -= NT - bi1; ++bi1; }
             }
         }
         SUBP(8);
@@ -1317,7 +1321,7 @@ __device__ __noinline__ int adapt(const RunArgs &a, const ChainCtx &cx, int isim
             SUBP(12);
             return ok ? 1 : 2;
         }
-        double *W = cx.ring;
+        double *W = tc_smem + cx.o_ring;
         unsigned short *tab = reinterpret_cast<unsigned short *>(W + 16 * T4);
 #pragma unroll 1
         for (int t = tid; t < T4; t += DRAM_THREADS) {
