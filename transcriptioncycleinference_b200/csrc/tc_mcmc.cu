@@ -730,11 +730,13 @@ struct ChainCtx {
     double adascale, inv_dr;
     SmemCell cv;
     int o_x, o_ring, o_U;                               // offsets (doubles) into tc_smem
+    int o_lo, o_pinv, o_wmean, o_wM2, o_mb;             // hot per-parameter vectors by offset (tc_smem + offset compiles to LDS/STS, the
+                                                        // pointers below to generic accesses); o_lo < 0: bounds / prior means in HBM (big layout)
     double *ring, *x, *lo, *hi, *mu, *pinv, *wmean, *wM2, *rdiag, *mb, *dm, *U;
     double *gRb, *gM2, *gRows, *gWts, *cmean;
     __device__ __forceinline__ int slot_o(int step) const { return o_ring + (step & ring_mask) * slot_sz; }
-    __device__ __forceinline__ double *slot_d(int step) const { return ring + (size_t)(step & ring_mask) * slot_sz; }
-    __device__ __forceinline__ double *slot_sc(int step) const { return ring + (size_t)(step & ring_mask) * slot_sz + (slot_sz - 8); }
+    __device__ __forceinline__ double *slot_d(int step) const { return tc_smem + o_ring + (step & ring_mask) * slot_sz; }
+    __device__ __forceinline__ double *slot_sc(int step) const { return tc_smem + o_ring + (step & ring_mask) * slot_sz + (slot_sz - 8); }
 };
 
 // The chain rows [r0, r1) all equal the current state x (a run: the accept at row r0, then rejections).
@@ -751,13 +753,14 @@ __device__ __noinline__ void flush_run(const RunArgs &a, const ChainCtx &cx, int
     const bool cov = a.do_cov && m_c > 0;
     const double nn = wcnt + m_w, f1 = m_w > 0 ? m_w / nn : 0.0, f2 = m_w > 0 ? wcnt * m_w / nn : 0.0;
     double *grow = cov ? cx.gRows + (size_t)ndist * cx.ld : nullptr;
+    const int ox = cx.o_x, owm = cx.o_wmean, ow2 = cx.o_wM2, omb = cx.o_mb;
 #pragma unroll 1
     for (int i = tid; i < npar; i += nthr) {
-        const double xo = cx.x[i];
+        const double xo = tc_smem[ox + i];
         if (m_w > 0) {
-            const double d1 = xo - cx.wmean[i];
-            cx.wmean[i] = fma(d1, f1, cx.wmean[i]);
-            cx.wM2[i] = fma(d1 * d1, f2, cx.wM2[i]);
+            const double wm = tc_smem[owm + i], d1 = xo - wm;
+            tc_smem[owm + i] = fma(d1, f1, wm);
+            tc_smem[ow2 + i] = fma(d1 * d1, f2, tc_smem[ow2 + i]);
             if (a.store_chain && a.chain) {
                 double *dst = a.chain + ((size_t)cx.ch * cx.nstore + (rs - cx.first_row)) * cx.ld + i;
 #pragma unroll 1
@@ -766,9 +769,9 @@ __device__ __noinline__ void flush_run(const RunArgs &a, const ChainCtx &cx, int
         }
         if (cov) {
             grow[i] = xo;
-            cx.mb[i] = fma((double)m_c, xo, cx.mb[i]);
+            tc_smem[omb + i] = fma((double)m_c, xo, tc_smem[omb + i]);
         }
-        if (so >= 0) cx.x[i] = xo + tc_smem[so + 2 * i];
+        if (so >= 0) tc_smem[ox + i] = xo + tc_smem[so + 2 * i];
     }
     if (cov && tid == 0) cx.gWts[ndist] = (double)m_c;
 }
@@ -1126,9 +1129,11 @@ __device__ __forceinline__ void warp_sum2(double &p, double &q)
 // Round phase A: bounds and prior of both proposals of the candidate steps k .. k+C-1 (warp w: candidates w, w+8).
 // The proposals are never materialised: theta = x + ring increment, the very expression the forward model
 // (SumVec) and the commit phase use.                    bounds/prior: TranscriptionCycleMCMC.m:235-255
-__device__ __noinline__ void cand_bounds(const ChainCtx &cx, int k, int C, Cand *cand)
+template <bool SM>
+__device__ __forceinline__ void cand_bounds_t(const ChainCtx &cx, int k, int C, Cand *cand)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, npar = cx.npar;
+    const int ox = cx.o_x, ol = cx.o_lo, oh = ol + npar, om = oh + npar, op = cx.o_pinv;
 #pragma unroll 1
     for (int c = warp; c < C; c += SPEC) {
         const double2 *dd = reinterpret_cast<const double2 *>(tc_smem + cx.slot_o(k + c));
@@ -1137,11 +1142,12 @@ __device__ __noinline__ void cand_bounds(const ChainCtx &cx, int k, int C, Cand 
 #pragma unroll 4
         for (int j = lane; j < npar; j += 32) {
             const double2 dj = dd[j];
-            const double xj = cx.x[j], a1 = xj + dj.x, a2 = xj + dj.y;
-            const double lo = cx.lo[j], hi = cx.hi[j];
+            const double xj = tc_smem[ox + j], a1 = xj + dj.x, a2 = xj + dj.y;
+            const double lo = SM ? tc_smem[ol + j] : cx.lo[j], hi = SM ? tc_smem[oh + j] : cx.hi[j];
+            const double mu = SM ? tc_smem[om + j] : cx.mu[j], pinv = tc_smem[op + j];
             if (a1 < lo || a1 > hi) oob |= 1u;
             if (a2 < lo || a2 > hi) oob |= 2u;
-            const double e1 = (a1 - cx.mu[j]) * cx.pinv[j], e2 = (a2 - cx.mu[j]) * cx.pinv[j];
+            const double e1 = (a1 - mu) * pinv, e2 = (a2 - mu) * pinv;
             pr1 = fma(e1, e1, pr1);
             pr2 = fma(e2, e2, pr2);
         }
@@ -1149,6 +1155,11 @@ __device__ __noinline__ void cand_bounds(const ChainCtx &cx, int k, int C, Cand 
         oob = __reduce_or_sync(0xffffffffu, oob);
         if (lane == 0) { cand[c].pr1 = pr1; cand[c].pr2 = pr2; cand[c].oob = (int)oob; }
     }
+}
+__device__ __noinline__ void cand_bounds(const ChainCtx &cx, int k, int C, Cand *cand)
+{
+    if (cx.o_lo >= 0) cand_bounds_t<true>(cx, k, C, cand);
+    else cand_bounds_t<false>(cx, k, C, cand);
 }
 
 // Round phase D, part 2: the delayed-rejection arithmetic of ONE step (one lane) whose first stage rejected, from state
@@ -1475,6 +1486,7 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
                 cx.cv = cv; cx.cv.d = a.cells.dmean[cid];
                 cx.o_x = o;
                 cx.x = tc_smem + o; o += npar;
+                cx.o_lo = a.big ? -1 : o;                           // lo, hi, mu consecutive
                 if (a.big) {
                     // bounds and prior means stay in HBM/L2 (read once per candidate step by cand_bounds)
                     cx.lo = const_cast<double *>(a.low) + (size_t)ch * a.ld; cx.hi = const_cast<double *>(a.upp) + (size_t)ch * a.ld;
@@ -1482,8 +1494,8 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
                 } else {
                     cx.lo = tc_smem + o; o += npar;    cx.hi = tc_smem + o; o += npar;    cx.mu = tc_smem + o; o += npar;
                 }
-                cx.pinv = tc_smem + o; o += npar;  cx.wmean = tc_smem + o; o += npar;
-                cx.wM2 = tc_smem + o; o += npar;   cx.rdiag = tc_smem + o; o += npar; cx.mb = tc_smem + o; o += npar;
+                cx.o_pinv = o; cx.pinv = tc_smem + o; o += npar;  cx.o_wmean = o; cx.wmean = tc_smem + o; o += npar;
+                cx.o_wM2 = o; cx.wM2 = tc_smem + o; o += npar;   cx.rdiag = tc_smem + o; o += npar; cx.o_mb = o; cx.mb = tc_smem + o; o += npar;
                 cx.dm = tc_smem + o; o += npar;
                 o += o & 1;
                 cx.o_ring = o;
