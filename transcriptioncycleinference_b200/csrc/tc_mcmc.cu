@@ -150,6 +150,11 @@ __host__ __device__ inline int dram_smem_doubles(int N, int big)
     return cell_doubles(N) + (big ? 7 : 10) * (7 + N) + 4 + (big ? RING / 2 : RING) * dram_slot(N) + SPEC * dram_wsz(N, big) + 16;
 }
 
+// reciprocal pivots of the current diagonal block / failure flag of the factorisations (file scope: the out-of-line phases
+// address them as shared memory, a pointer parameter would make every access generic)
+__shared__ double tc_dinv[8];
+__shared__ int tc_cholfail;
+
 // ---- Cholesky of the proposal covariance, in shared memory, by the whole CTA
 // Storage: the upper triangle in 4x4 TILES (tile (bi, bj), bi <= bj, at index bi*nt4 - bi(bi-1)/2 + bj - bi, 16
 // doubles row-major), padded to a multiple of 4 with an identity block, so that every tile operation is
@@ -195,7 +200,7 @@ __device__ __forceinline__ bool chol8(double (&A)[8][8], double (&dinv)[8])
 // Factor the 8x8 diagonal block that starts at tile row b0 (one 4x4 tile when it is the last row of an odd nt4): every
 // lane of the calling warp factors it redundantly in registers (a chain of 8 dependent rsqrt's, no communication),
 // lanes 0-2 write the three tiles back, lane 0 the reciprocal pivots.
-__device__ __forceinline__ void chol_diag(int nt4, double *W, int b0, double *s_dinv, int *s_fail)
+__device__ __forceinline__ void chol_diag(int nt4, double *W, int b0)
 {
     const int lane = threadIdx.x & 31;
     const bool two = b0 + 1 < nt4;
@@ -238,8 +243,8 @@ __device__ __forceinline__ void chol_diag(int nt4, double *W, int b0, double *s_
             for (int c = 0; c < 4; ++c) q[4 * r + c] = c >= r ? A[r][c] : 0.0;
         st_tile(t00, q);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) s_dinv[j] = dinv[j];
-        if (bad) *s_fail = 1;
+        for (int j = 0; j < 8; ++j) tc_dinv[j] = dinv[j];
+        if (bad) tc_cholfail = 1;
     } else if (lane == 1 && two) {
         double q[16];
 #pragma unroll
@@ -287,8 +292,10 @@ __device__ __forceinline__ void chol_tile_update(int nt4, double *W, int b0, int
 // rank-8 update in registers by warps 1-7 while warp 0 updates just the NEXT diagonal block and factors it — so
 // the chain of dependent rsqrt's never sits on the critical path of the other warps.  Returns false when a
 // pivot is not positive.
-__device__ __noinline__ bool chol_tiled(int nt4, double *W, const unsigned short *tab, double *s_dinv, int *s_fail, bool prof)
+__device__ __noinline__ bool chol_tiled(int nt4, int oW, bool prof)
 {
+    double *W = tc_smem + oW;                             // (offset arithmetic on tc_smem compiles to LDS / STS)
+    const unsigned short *tab = reinterpret_cast<const unsigned short *>(W + 16 * (nt4 * (nt4 + 1) / 2));
 #ifdef TC_SUBPROF
     long long tq = clock64();
 #define CHP(i) do { if (threadIdx.x == 0 && prof) { const long long t__ = clock64(); tc_subprof[i] += t__ - tq; tq = t__; } } while (0)
@@ -297,11 +304,11 @@ __device__ __noinline__ bool chol_tiled(int nt4, double *W, const unsigned short
 #endif
     const int tid = threadIdx.x, nthr = blockDim.x, warp = tid >> 5, lane = tid & 31;
     const int T = nt4 * (nt4 + 1) / 2;
-    if (tid == 0) *s_fail = 0;
+    if (tid == 0) tc_cholfail = 0;
     __syncthreads();
-    if (warp == 0) chol_diag(nt4, W, 0, s_dinv, s_fail);
+    if (warp == 0) chol_diag(nt4, W, 0);
     __syncthreads();
-    if (*s_fail) return false;                            // uniform
+    if (tc_cholfail) return false;                        // uniform
 #pragma unroll 1
     for (int b0 = 0; b0 + 2 < nt4; b0 += 2) {
         const int bnext = b0 + 2;
@@ -316,7 +323,7 @@ __device__ __noinline__ bool chol_tiled(int nt4, double *W, const unsigned short
                     r11[p_][r] = (p_ < 4) ? (r < 4 ? t00[4 * p_ + r] : t01[4 * p_ + (r - 4)]) : t11[4 * (p_ - 4) + (r - 4)];
             double di[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) di[j] = s_dinv[j];
+            for (int j = 0; j < 8; ++j) di[j] = tc_dinv[j];
 #pragma unroll 1
             for (int cc = tid; cc < 4 * (nt4 - bnext); cc += nthr) {
                 const int bj = bnext + (cc >> 2), c = cc & 3;
@@ -364,7 +371,7 @@ __device__ __noinline__ bool chol_tiled(int nt4, double *W, const unsigned short
             }
             __syncwarp();
             CHP(6);
-            chol_diag(nt4, W, bnext, s_dinv, s_fail);
+            chol_diag(nt4, W, bnext);
             CHP(7);
         } else {
 #pragma unroll 1
@@ -376,7 +383,7 @@ __device__ __noinline__ bool chol_tiled(int nt4, double *W, const unsigned short
         CHP(15);
         __syncthreads();
         CHP(5);
-        if (*s_fail) return false;                        // uniform
+        if (tc_cholfail) return false;                    // uniform
     }
     return true;
 }
@@ -530,7 +537,7 @@ __device__ __forceinline__ void cg_accumulate(int oa, int ob, int nr, int rs, do
 #define CG_NS 8            // ring stages (a power of two)
 #define CG_RPS 8           // tile rows per stage, at most
 __device__ __noinline__ bool chol_global(int nt4, int npar, const double *gA, double invn, double qcovadj, double *gW,
-                                         int o_ws, int ws_doubles, double *s_dinv, int *s_fail)
+                                         int o_ws, int ws_doubles)
 {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, ar = lane >> 2, ak = lane & 3;
     const int ldS = 8 * ((nt4 + 1) >> 1) + 4;
@@ -543,7 +550,7 @@ __device__ __noinline__ bool chol_global(int nt4, int npar, const double *gA, do
         const int o = (8 * ldS + 1) & ~1;
         ring.init(o_ws + o, ((ws_doubles - o - 32) / CG_NS) & ~1);
     }
-    if (tid == 0) *s_fail = 0;
+    if (tid == 0) tc_cholfail = 0;
 #ifdef TC_SUBPROF
     long long tq = clock64();
 #define CGP(i) do { if (tid == 0 && blockIdx.x == 0) { const long long t__ = clock64(); tc_subprof[i] += t__ - tq; tq = t__; } } while (0)
@@ -643,13 +650,13 @@ __device__ __noinline__ bool chol_global(int nt4, int npar, const double *gA, do
 #pragma unroll
                     for (int c = r; c < 8; ++c) S[r * ldS + c] = A[r][c];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) s_dinv[j] = dinv[j];
-                if (bad) *s_fail = 1;
+                for (int j = 0; j < 8; ++j) tc_dinv[j] = dinv[j];
+                if (bad) tc_cholfail = 1;
             }
         }
         __syncthreads();
         CGP(7);
-        if (*s_fail) { ok = false; break; }                       // uniform; nothing is in flight here
+        if (tc_cholfail) { ok = false; break; }                       // uniform; nothing is in flight here
         // the first stages of the next panel that hold only final rows (< b0) start streaming now
         si = 0;
         if (tid == 0 && b0 + 2 < nt4) {
@@ -664,7 +671,7 @@ __device__ __noinline__ bool chol_global(int nt4, int npar, const double *gA, do
 #pragma unroll
                 for (int r = p_ + 1; r < 8; ++r) r11[p_][r] = S[p_ * ldS + r];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) di[j] = s_dinv[j];
+            for (int j = 0; j < 8; ++j) di[j] = tc_dinv[j];
 #pragma unroll 1
             for (int cc = 8 + tid; cc < 4 * ntc; cc += DRAM_THREADS) {
                 double xv[8];
@@ -1205,7 +1212,7 @@ __device__ __forceinline__ void scaled_copy_cg(double2 *dst, const double2 *src,
 // Chan's mean-shift term as one more weighted row, in 4x4 register tiles.  Then either burn-in scaling or
 // R = chol(cov + qcovadj I) * adascale.  Returns 0: R unchanged / scaled, 1: new full factor, 2: Cholesky failed.
 __device__ __noinline__ int adapt(const RunArgs &a, const ChainCtx &cx, int isimu, double cov_n, double rate, bool r_diag,
-                                  int ndist, double *s_dinv, int *s_flag)
+                                  int ndist)
 {
     const int tid = threadIdx.x, npar = cx.npar, ld = cx.ld;
     double *sw = tc_smem + cx.o_ring;                  // workspace: ring + per-warp areas (idle now); sqrt(weight) per row first
@@ -1322,7 +1329,7 @@ __device__ __noinline__ int adapt(const RunArgs &a, const ChainCtx &cx, int isim
         if (a.big) {
             // the factor does not fit in shared memory: factorise through HBM/L2 into this CTA's workspace
             double *gW = a.gW + (size_t)blockIdx.x * a.ldR;
-            const bool ok = chol_global(nt4, npar, cx.gM2, invn, a.qcovadj, gW, cx.o_ring, (cx.ring_mask + 1) * cx.slot_sz + SPEC * cx.wsz, s_dinv, s_flag);
+            const bool ok = chol_global(nt4, npar, cx.gM2, invn, a.qcovadj, gW, cx.o_ring, (cx.ring_mask + 1) * cx.slot_sz + SPEC * cx.wsz);
             SUBP(11);
             if (ok) {
                 scaled_copy_cg(reinterpret_cast<double2 *>(cx.gRb), reinterpret_cast<const double2 *>(gW), 8 * T4, cx.adascale);
@@ -1350,7 +1357,7 @@ __device__ __noinline__ int adapt(const RunArgs &a, const ChainCtx &cx, int isim
         }
         __syncthreads();
         SUBP(10);
-        const bool ok = chol_tiled(nt4, W, tab, s_dinv, s_flag, cx.ch == 0);
+        const bool ok = chol_tiled(nt4, cx.o_ring, cx.ch == 0);
         __syncthreads();
         SUBP(11);
         if (ok) {
@@ -1406,8 +1413,6 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
     __shared__ double s_ssv[2 * RING];
     __shared__ ChainCtx cx;
     __shared__ S2Stats s_s2;
-    __shared__ double s_dinv[8];
-    __shared__ int s_flag;
     __shared__ int s_item, s_done;
     __shared__ unsigned s_min;
     __shared__ ChainState st;
@@ -1756,7 +1761,7 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
                 const double cov_n = st.cov_n;
                 const bool rdg = st.r_diag != 0;
                 __syncthreads();
-                const int rc = adapt(a, cx, k, cov_n, rate, rdg, nd, s_dinv, &s_flag);
+                const int rc = adapt(a, cx, k, cov_n, rate, rdg, nd);
                 if (tid == 0) {
                     st.wcnt = wc0 + max(0, k - max(rr0, cx.first_row));
                     st.run_r0 = k; st.ndist = 0;
