@@ -349,28 +349,27 @@ __device__ __noinline__ bool chol_tiled(int nt4, int oW, bool prof)
         const int tA = tidx(nt4, bnext, bnext);
         const bool two = bnext + 1 < nt4;
         const int tB = two ? tA + 1 : -1, tC = two ? tidx(nt4, bnext + 1, bnext + 1) : -1;
-        if (warp == 0) {
-            // the three tiles of the next diagonal block: 48 outputs, one 8-term dot product each, spread over the lanes
-            {
-                const double *p0 = W + 16 * tidx(nt4, b0, bnext), *p1 = W + 16 * tidx(nt4, b0 + 1, bnext);   // panel rows x tile columns bnext, bnext+1:
-#pragma unroll                                                                                            // adjacent tiles, 16 doubles apart
-                for (int h = 0; h < 2; ++h) {
-                    const int e = lane + 32 * h;
-                    if (e < (two ? 48 : 16)) {
-                        const int te = e >> 4, ii = (e >> 2) & 3, jj = e & 3;
-                        const int ci = 16 * (te >> 1) + ii, cj = 16 * ((te + 1) >> 1) + jj;        // (bi, bj) - bnext = (0,0), (0,1), (1,1)
-                        double *dst = W + 16 * (te == 0 ? tA : (te == 1 ? tB : tC)) + 4 * ii + jj;
-                        double acc = *dst;
+        // the three tiles of the next diagonal block first, by three warps: 48 outputs x 2 halves of the 8-term dot product
+        // (thread pair = one output, combined with a shuffle), so that the serial factorisation below can start at once
+        if (tid < 96) {
+            const double *p0 = W + 16 * tidx(nt4, b0, bnext), *p1 = W + 16 * tidx(nt4, b0 + 1, bnext);   // panel rows x tile columns bnext, bnext+1:
+            const int e = tid >> 1, half = tid & 1;                                                        // adjacent tiles, 16 doubles apart
+            const bool on = e < (two ? 48 : 16);
+            const int te = e >> 4, ii = (e >> 2) & 3, jj = e & 3;
+            const int ci = 16 * (te >> 1) + ii, cj = 16 * ((te + 1) >> 1) + jj;        // (bi, bj) - bnext = (0,0), (0,1), (1,1)
+            double *dst = W + 16 * (te == 0 ? tA : (te == 1 ? tB : tC)) + 4 * ii + jj;
+            const double *ph = half ? p1 : p0;
+            double acc = (on && !half) ? *dst : 0.0;
+            if (on) {
 #pragma unroll
-                        for (int p_ = 0; p_ < 4; ++p_) acc = fma(-p0[4 * p_ + ci], p0[4 * p_ + cj], acc);
-#pragma unroll
-                        for (int p_ = 0; p_ < 4; ++p_) acc = fma(-p1[4 * p_ + ci], p1[4 * p_ + cj], acc);
-                        *dst = acc;
-                    }
-                }
+                for (int p_ = 0; p_ < 4; ++p_) acc = fma(-ph[4 * p_ + ci], ph[4 * p_ + cj], acc);
             }
-            __syncwarp();
-            CHP(6);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+            if (on && !half) *dst = acc;
+        }
+        __syncthreads();
+        CHP(6);
+        if (warp == 0) {
             chol_diag(nt4, W, bnext);
             CHP(7);
         } else {
