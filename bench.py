@@ -327,8 +327,9 @@ def ss_kernel_leg(cells, g, peak_dfma, torch):
         ops = float(np.sum(w_op(g["N"][cid].astype(np.float64))))
         res[name] = dict(evals_per_s=cid.size / t, ms=t * 1e3, batch=int(cid.size),
                          frac_of_fp64_peak_algorithmic_ops=ops / t / peak_dfma)
-    res["note"] = ("inputs (%.0f MB of theta) are larger than nothing in L2 terms: 333 MB > 126 MB L2; "
-                   "frac = evals/s x W_op(N) / measured DFMA rate" % (th.nbytes / 1e6))
+    res["note"] = ("device-resident inputs, %.0f MB of theta streamed from HBM per launch (> 126 MB L2); toeplitz = the O(N) "
+                   "algorithm (ss_stream_kernel: operands staged in shared memory), pairs = the O(N^2) algorithm W_op counts "
+                   "(ss_batch_kernel); frac = evals/s x W_op(N) / measured DFMA rate" % (th.nbytes / 1e6))
     return res
 
 

@@ -22,7 +22,7 @@ def marks_of(path, pats):
         for i,l in enumerate(src):
             if pat in l: out.append((name,i+1)); break
     return sorted(out,key=lambda x:x[1])
-mm=marks_of('transcriptioncycleinference_b200/csrc/tc_mcmc.cu',[('ss_batch_kernel','void __launch_bounds__(SS_THREADS'),('chol_tiled','bool chol_tiled('),('dmma','void dmma_m8n8k4'),('tma helpers','#define TMA_MAXST'),('chol_global','bool chol_global('),('cand/state structs','struct Cand'),('gen_increments_tma','void gen_increments_tma('),('flush_run','void flush_run('),('emit_s2','void emit_s2('),('generate','void generate('),('cand_bounds','void cand_bounds('),('resolve_dr','int resolve_dr('),('adapt','int adapt('),('dram_kernel(main)','dram_kernel(const __grid_constant__'),('after','RNG dump / FP64 peak')])
+mm=marks_of('transcriptioncycleinference_b200/csrc/tc_mcmc.cu',[('ss_batch_kernel','void __launch_bounds__(SS_THREADS, SS_MIN_CTAS'),('ss_stream_kernel','void __launch_bounds__(SS_THREADS, 2) ss_stream'),('chol_tiled','bool chol_tiled('),('dmma','void dmma_m8n8k4'),('tma helpers','#define TMA_MAXST'),('chol_global','bool chol_global('),('cand/state structs','struct Cand'),('gen_increments_tma','void gen_increments_tma('),('flush_run','void flush_run('),('emit_s2','void emit_s2('),('generate','void generate('),('cand_bounds','void cand_bounds('),('resolve_dr','int resolve_dr('),('adapt','int adapt('),('dram_kernel(main)','dram_kernel(const __grid_constant__'),('after','RNG dump / FP64 peak')])
 md=marks_of('transcriptioncycleinference_b200/csrc/tc_device.cuh',[('philox/draw','philox_round('),('normal_pair','void normal_pair('),('chi2_draw','double chi2_draw('),('exp/log','double tc_exp('),('warp_sum','double warp_sum('),('views','struct CellView'),('scan','void scan_counts_sequential('),('first_lag','int first_lag('),('rows_pairs','void rows_pairs('),('ss_eval','double ss_eval(')])
 agg={}
 for f,l,s,sa,ie in lines:

@@ -11,5 +11,5 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 $CMD > gpurun_out/plain2_$R.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:dram_kernel -s 3 -c 1 -o gpurun_out/prof_dram_$R $CMD > gpurun_out/ncu_dram_$R.log 2>&1
 $CMD > gpurun_out/plain3_$R.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:ss_batch_kernel -s 3 -c 1 -o gpurun_out/prof_ss_$R $CMD > gpurun_out/ncu_ss_$R.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:ss_stream_kernel -s 3 -c 1 -o gpurun_out/prof_ss_$R $CMD > gpurun_out/ncu_ss_$R.log 2>&1
 tail -n 2 gpurun_out/ncu_dram_$R.log; tail -n 2 gpurun_out/ncu_ss_$R.log

@@ -64,6 +64,7 @@ struct SsArgs {
     const int *cell_id;
     const double *theta;
     int ld, algo, raw_grid, ldo, wsz;
+    int csz, ld2;                                       // ss_stream_kernel: per-warp cell area / theta buffer (doubles, even)
     double *ss_out, *out1, *out2;
 };
 
@@ -83,6 +84,64 @@ __global__ void __launch_bounds__(SS_THREADS, SS_MIN_CTAS) ss_batch_kernel(const
         const double ss = ss_eval(a.cons, cv, GlobVec{a.theta + b * a.ld}, w, a.algo, false, o1, o2);
         if (lane == 0 && a.ss_out) a.ss_out[b] = ss;
     }
+}
+
+// The batched ssfun when only SS is wanted (tc_ss_batch, tc_ss_batch_device): every warp owns a CONTIGUOUS run of the
+// batch and keeps its operands in shared memory, the way the sampler does — the cell's series are staged once and reused
+// while consecutive items belong to the same cell (proposals for a cell arrive together), theta of item i+1 streams in
+// with cp.async while item i is evaluated (double buffer) — so an evaluation never waits on a global load: the
+// global-view kernel above spends half of its warp-cycles in long-scoreboard stalls (ncu, profiles/ncu_ss_r1w.txt).
+// Per warp: [cell | theta x 2 | forward-model scratch] = 13 KB at N = 129, two CTAs per SM.
+__global__ void __launch_bounds__(SS_THREADS, 2) ss_stream_kernel(const __grid_constant__ SsArgs a)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int o_cell = warp * (a.csz + 2 * a.ld2 + a.wsz), o_th = o_cell + a.csz, o_work = o_th + 2 * a.ld2;
+    const long long nw = (long long)gridDim.x * SS_WARPS, wi = (long long)blockIdx.x * SS_WARPS + warp;
+    const long long chunk = (a.nbatch + nw - 1) / nw, b0 = wi * chunk, b1 = min(a.nbatch, b0 + chunk);
+    const unsigned sth = (unsigned)__cvta_generic_to_shared(tc_smem + o_th);
+    int cur = -1;
+    SmemCell cv{};
+    Work w{};
+#define SS_ISSUE_THETA(bb, buf)                                                                             \
+    {                                                                                                       \
+        const double *src__ = a.theta + (bb) * a.ld;                                                        \
+        for (int i = lane; i < a.ld; i += 32)                                                               \
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sth + 8u * (unsigned)((buf) * a.ld2 + i)), "l"(src__ + i) : "memory"); \
+        asm volatile("cp.async.commit_group;" ::: "memory");                                                \
+    }
+    if (b0 < b1) SS_ISSUE_THETA(b0, 0)
+#pragma unroll 1
+    for (long long b = b0; b < b1; ++b) {
+        const int buf = (int)(b - b0) & 1;
+        const bool more = b + 1 < b1;
+        if (more) SS_ISSUE_THETA(b + 1, buf ^ 1)
+        const int cid = a.cell_id[b];
+        if (cid != cur) {                                       // warp-uniform
+            const int N = a.cells.N[cid];
+            carve_cell(o_cell, N, cv);
+            carve_work(o_work, N, w);
+            const long long o = a.cells.off[cid];
+            int *ikp = reinterpret_cast<int *>(tc_smem + cv.o_ik);
+#pragma unroll 2
+            for (int i = lane; i < N; i += 32) {
+                tc_smem[cv.o_tg + i] = a.cells.tg[o + i];
+                tc_smem[cv.o_dtg + i] = a.cells.dtg[o + i];
+                tc_smem[cv.o_ms2 + i] = a.cells.ms2[o + i];
+                tc_smem[cv.o_pp7 + i] = a.cells.pp7[o + i];
+                tc_smem[cv.o_iw + i] = a.cells.iw[o + i];
+                ikp[i] = a.cells.ik[o + i];
+            }
+            cv.d = a.cells.dmean[cid];
+            cur = cid;
+        }
+        if (more) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        const double ss = ss_eval(a.cons, cv, SmemVec{o_th + buf * a.ld2}, w, a.algo, false, nullptr, nullptr);
+        if (lane == 0) a.ss_out[b] = ss;
+        __syncwarp();                                           // the buffer is free for the copy issued two items on
+    }
+#undef SS_ISSUE_THETA
 }
 
 // ------------------------------------------------------------------------------------- sampler
@@ -2099,10 +2158,28 @@ static int launch_ss(const tc_cells *c, const DevCells *dc, long long nbatch, co
     a.cells = dc->d; a.cons = c->cons; a.nbatch = nbatch; a.cell_id = d_cell; a.theta = d_theta; a.ld = ld;
     a.algo = algo; a.raw_grid = raw; a.ldo = ldo; a.ss_out = d_ss; a.out1 = d_o1; a.out2 = d_o2;
     a.wsz = (work_doubles(c->Nmax) + 3) & ~1;
-    const size_t smem = sizeof(double) * (size_t)a.wsz * SS_WARPS;
-    CUDA_TRY(cudaFuncSetAttribute(ss_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int sms = 0;
     CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dc->device));
+    if (!raw && d_ss && !d_o1 && !d_o2 && algo == TC_ALGO_TOEPLITZ) {
+        // SS only, O(N) algorithm (latency-bound): operands staged in shared memory (ss_stream_kernel) when two CTAs per SM
+        // fit.  The pairs algorithm is FP64-pipe-bound and prefers the 32 warps/SM of the global-view kernel (measured:
+        // 52.7 M evaluations/s there, 34.2 M with 16 warps/SM here).
+        a.csz = (cell_doubles(c->Nmax) + 1) & ~1;
+        a.ld2 = (ld + 1) & ~1;
+        const size_t smem2 = sizeof(double) * (size_t)(a.csz + 2 * a.ld2 + a.wsz) * SS_WARPS;
+        int optin = 0;
+        CUDA_TRY(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dc->device));
+        if (2 * (smem2 + 1024) <= (size_t)optin + 1024) {
+            CUDA_TRY(cudaFuncSetAttribute(ss_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            const long long want2 = (nbatch + SS_WARPS - 1) / SS_WARPS;
+            const int grid2 = (int)std::min<long long>(want2, (long long)sms * 2);
+            ss_stream_kernel<<<grid2, SS_THREADS, smem2, st>>>(a);
+            CUDA_TRY(cudaGetLastError());
+            return TC_OK;
+        }
+    }
+    const size_t smem = sizeof(double) * (size_t)a.wsz * SS_WARPS;
+    CUDA_TRY(cudaFuncSetAttribute(ss_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long want = (nbatch + SS_WARPS - 1) / SS_WARPS, maxgrid = (long long)sms * 16;
     const int grid = (int)std::min<long long>(want, maxgrid);
     ss_batch_kernel<<<grid, SS_THREADS, smem, st>>>(a);
