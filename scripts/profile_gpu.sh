@@ -13,3 +13,7 @@ ncu --set full --clock-control none --import-source on -k regex:dram_kernel -s 3
 $CMD > gpurun_out/plain3_$R.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:ss_stream_kernel -s 3 -c 1 -o gpurun_out/prof_ss_$R $CMD > gpurun_out/ncu_ss_$R.log 2>&1
 tail -n 2 gpurun_out/ncu_dram_$R.log; tail -n 2 gpurun_out/ncu_ss_$R.log
+# big layout (BASELINE config 5's series length): second dram_kernel launch of the synthetic workload
+python scripts/config5.py 1184 400 400 > gpurun_out/plain_c5_$R.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:dram_kernel -s 1 -c 1 -o gpurun_out/prof_c5_$R python scripts/config5.py 1184 400 400 > gpurun_out/ncu_c5_$R.log 2>&1
+tail -n 2 gpurun_out/ncu_c5_$R.log
