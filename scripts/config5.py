@@ -17,9 +17,11 @@ t0 = time.time()
 cells, truth = synthetic.make_cells(ncells, N, devices=tuple(range(ngpus)))
 t_gen = time.time() - t0
 cc = np.arange(ncells, dtype=np.int32)
+t0 = time.time()
 inputs = setup_cell.chain_inputs(cells, cc, np.random.default_rng(5))
+print("generated %d cells in %.1f s, chain inputs in %.1f s" % (ncells, t_gen, time.time() - t0), file=sys.stderr, flush=True)
 opts = _lib.default_opts(nsimu=nsteps, burnintime=nsteps // 2, n_burn=nsteps // 2, ngpus=ngpus)
-for rep in range(2):
+for rep in range(1 if ncells >= 20000 else 2):          # (a second, warm repetition for the small runs)
     t0 = time.time()
     out = cells.mcmc_run(opts, cc, *inputs)
     wall = time.time() - t0

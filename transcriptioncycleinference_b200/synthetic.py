@@ -5,8 +5,11 @@ t = cumulative sum of dt ~ U(0.15, 0.35) min starting at 0 (irregular like the d
 of src/TranscriptionCycleMCMC.m:193-210 (v in [1,3], tau in [0,4], ton in [0,4], A in [0,1], MS2_basal, PP7_basal in [0,2],
 R = 15, dR ~ N(0,3)); signals = forward model on the raw grid (the plot call, :307-309, through tc_forward) + N(0, sigma)
 noise; NaN mask Bernoulli(0.5) on MS2 and (0.2) on PP7; numpy Philox generator, seed 20201028."""
+import re
+
 import numpy as np
 
+from . import _lib
 from .constructs import DEFAULT_CONSTRUCT
 from .engine import Cells
 
@@ -27,8 +30,19 @@ def make_cells(ncells, N=400, seed=20201028, noise=1.0, construct=DEFAULT_CONSTR
     ms2 = np.zeros((ncells, N)); pp7 = np.zeros((ncells, N))
     for b0 in range(0, ncells, batch):
         b1 = min(ncells, b0 + batch)
-        tmp = Cells(list(t[b0:b1]), list(np.zeros((b1 - b0, N))), list(np.zeros((b1 - b0, N))), construct=construct,
-                    devices=devices[:1])
+        z = list(np.zeros((b1 - b0, N)))
+        for _ in range(64):
+            # a grid whose t(1):dt:t(end) does not have N points is an error in the reference (R.*dt sizes, SumofSquares...m:30)
+            # and in tc_cells_create (TC_EDIM, "... for cell K"): redraw that cell's time grid
+            try:
+                tmp = Cells(list(t[b0:b1]), z, z, construct=construct, devices=devices[:1])
+                break
+            except _lib.TcError as e:
+                m = re.search(r"for cell (\d+)", str(e))
+                if e.code != _lib.TC_EDIM or not m:
+                    raise
+                k = b0 + int(m.group(1))
+                t[k, 1:] = np.cumsum(rng.uniform(0.15, 0.35, N - 1))
         m1, m2 = tmp.forward(np.arange(b1 - b0, dtype=np.int32), truth[b0:b1], on_raw_grid=True)
         tmp.close()
         ms2[b0:b1] = m1[:, :N]; pp7[b0:b1] = m2[:, :N]
