@@ -1,5 +1,5 @@
 """BASELINE config 5 at a single-GPU scale: synthetic cells x N = 400 time points (npar = 407: the big layout), DRAM fit
-from random starts, throughput + parameter recovery.  usage: python scripts/config5.py [ncells] [n_steps] [N] [ngpus]"""
+from random starts, throughput + parameter recovery.  usage: python scripts/config5.py [ncells] [n_steps] [N] [ngpus] [truth]   (truth: start the chains at the true parameters)"""
 import json
 import sys
 import time
@@ -13,12 +13,17 @@ ncells = int(sys.argv[1]) if len(sys.argv) > 1 else 1184
 nsteps = int(sys.argv[2]) if len(sys.argv) > 2 else 20000
 N = int(sys.argv[3]) if len(sys.argv) > 3 else 400
 ngpus = int(sys.argv[4]) if len(sys.argv) > 4 else 1
+at_truth = len(sys.argv) > 5 and sys.argv[5] == "truth"
 t0 = time.time()
 cells, truth = synthetic.make_cells(ncells, N, devices=tuple(range(ngpus)))
 t_gen = time.time() - t0
 cc = np.arange(ncells, dtype=np.int32)
 t0 = time.time()
 inputs = setup_cell.chain_inputs(cells, cc, np.random.default_rng(5))
+n_obs = np.array([np.sum(~np.isnan(cells.cell(c)[1])) + np.sum(~np.isnan(cells.cell(c)[2])) for c in range(min(ncells, 2000))])
+rms_truth = float(np.median(np.sqrt(cells.ss_batch(cc[:n_obs.size], truth[:n_obs.size]) / n_obs)))   # ~ noise sigma if the model is consistent
+if at_truth:
+    inputs = (truth.copy(),) + tuple(inputs[1:])
 print("generated %d cells in %.1f s, chain inputs in %.1f s" % (ncells, t_gen, time.time() - t0), file=sys.stderr, flush=True)
 opts = _lib.default_opts(nsimu=nsteps, burnintime=nsteps // 2, n_burn=nsteps // 2, ngpus=ngpus)
 for rep in range(1 if ncells >= 20000 else 2):          # (a second, warm repetition for the small runs)
@@ -29,7 +34,8 @@ cnt = out["counters"]
 ks = out["kernel_seconds"]
 rec = synthetic.recovery(truth, out["mean"], out["std"])
 pc = cnt[:, 8:14].sum(axis=0).astype(float)
-print(json.dumps(dict(config="config5-scale: %d cells x N=%d, n_steps=%d, %d GPU(s)" % (ncells, N, nsteps, ngpus),
+print(json.dumps(dict(config="config5-scale: %d cells x N=%d, n_steps=%d, %d GPU(s)%s" % (ncells, N, nsteps, ngpus, ", chains started AT the truth" if at_truth else ""),
+                      median_rms_residual_at_truth=rms_truth,
                       chain_steps_per_s=ncells * nsteps / ks, kernel_s=ks, wall_s=wall, gen_s=t_gen,
                       ss_evals_per_step=float(cnt[:, 0].sum()) / (ncells * nsteps),
                       accept_rate=float(cnt[:, 1:3].sum()) / (ncells * nsteps),
