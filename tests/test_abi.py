@@ -38,6 +38,7 @@ def test_version_and_defaults():
     assert (o.nsimu, o.burnintime, o.adaptint, o.ntry, o.updatesigma) == (20000, 10000, 100, 2, 1)
     assert (o.drscale, o.qcovadj, o.burnin_scale, o.N0, o.S20, o.sigma2_0) == (5.0, 1e-8, 10.0, 1.0, 1.0, 1.0)
     assert o.adascale == 0.0 and o.n_burn == 10000 and o.store_chain == 0 and o.algo == _lib.ALGO_TOEPLITZ
+    assert o.layout == 0                      # TC_LAYOUT_AUTO: the large-series layout only when the regular one does not fit
 
 
 def test_struct_layouts_match_header(tmp_path):
