@@ -32,9 +32,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 GOLDEN = os.path.join(ROOT, "tests", "golden", "cells.npz")
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE dram_kernel launch of the default workload (config 2, 200 000
-# steps), from an ncu capture of this very command (profiles/traffic_dram_r1x.csv): 14 MB read + 3.81 GB written
-# (distinct chain rows, and the part of the proposal factors / scatter matrices that L2 evicts).  Other workloads: not captured.
-MEASURED_TRAFFIC_BYTES = {("config2", 200000, 10000): 13915392 + 3810353152}
+# steps), from an ncu capture of this very command (profiles/traffic_dram_r1v.csv): 109 MB read + 8.0 GB written
+# (distinct chain rows, and the part of the proposal factors / scatter matrices that L2 evicts; 3.8 GB at r1x: the
+# write-back share moves with L2 residency, either way < 0.1 % of HBM bandwidth).  Other workloads: not captured.
+MEASURED_TRAFFIC_BYTES = {("config2", 200000, 10000): 109115648 + 8000692480}
 METRIC = "mcmc_chain_steps_per_s"
 UNIT = "chain-steps/s"
 
@@ -260,8 +261,8 @@ def run_ours(args, g):
         accept_rate=float((cnt[:, _lib.CNT_ACC_STAGE1] + cnt[:, _lib.CNT_ACC_STAGE2]).sum() / (cc.size * args.n_steps)),
         roofline=dict(bound="fp64_pipe", kernel="dram_kernel", achieved=achieved, peak=peak_tf, unit="TFLOP/s",
                       frac=achieved / peak_tf, traffic=MEASURED_TRAFFIC_BYTES.get((args.workload, args.n_steps, args.n_burn)),
-                      traffic_unit="bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/traffic_dram_r1x.csv); "
-                                   "the kernel is bound by FP64-pipe latency, not HBM: this is < 0.1 % of HBM bandwidth",
+                      traffic_unit="bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/traffic_dram_r1v.csv); "
+                                   "the kernel is bound by FP64-pipe latency, not HBM: this is 0.1 % of HBM bandwidth",
                       peak_source="measured DFMA micro-benchmark on this GPU (tc_measure_fp64_peak), SM clock %.0f MHz; "
                                   "MEASURED_PEAKS.json has no FP64 entry" % peak_clk,
                       algorithmic_flops_per_launch=flops_ss + flops_dram, flops_ss=flops_ss, flops_dram=flops_dram,
