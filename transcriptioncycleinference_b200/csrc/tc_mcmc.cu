@@ -213,6 +213,7 @@ __host__ __device__ inline int dram_smem_doubles(int N, int big)
 // address them as shared memory, a pointer parameter would make every access generic)
 __shared__ double tc_dinv[8];
 __shared__ int tc_cholfail;
+__shared__ int tc_genctr;                               // generate(): next unclaimed work item
 
 // ---- Cholesky of the proposal covariance, in shared memory, by the whole CTA
 // Storage: the upper triangle in 4x4 TILES (tile (bi, bj), bi <= bj, at index bi*nt4 - bi(bi-1)/2 + bj - bi, 16
@@ -1058,18 +1059,28 @@ __device__ __noinline__ void generate(const RunArgs &a, const ChainCtx &cx, int 
             sc[5] = tc_log(sc[0]);                                  // stage 1 is decided in the log domain
         }
         __syncwarp();
-        const int npairs = (npar + 1) >> 1;
+        const int npairs = (npar + 1) >> 1, nitems = nnew * npairs;
         const float inv_np = 1.0f / (float)npairs;                  // it / npairs without an integer division: exact here
+        // the items are handed out 32 at a time from a shared counter: warp 0 joins when its chi-square draws are done (the draws
+        // are addressed by (step, parameter pair), so who computes which does not matter)
 #pragma unroll 1                                                    // (it + 0.5 is >= 0.5/npairs away from a multiple of npairs)
-        for (int it = (tid + 32) & (DRAM_THREADS - 1); it < nnew * npairs; it += DRAM_THREADS) {
-            const int sidx = (int)(((float)it + 0.5f) * inv_np), q2 = it - sidx * npairs;
-            double *dz = ZROW(sidx);
-            const double4 z = normal_quad(a.seed, cx.uid, g0 + sidx, q2);
-            *reinterpret_cast<double2 *>(dz + 4 * q2) = make_double2(z.x, z.z);          // (z1, z2) of parameter 2q
-            if (2 * q2 + 1 < npar) *reinterpret_cast<double2 *>(dz + 4 * q2 + 2) = make_double2(z.y, z.w);
+        for (;;) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&tc_genctr, 32);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base >= nitems) break;
+            const int it = base + lane;
+            if (it < nitems) {
+                const int sidx = (int)(((float)it + 0.5f) * inv_np), q2 = it - sidx * npairs;
+                double *dz = ZROW(sidx);
+                const double4 z = normal_quad(a.seed, cx.uid, g0 + sidx, q2);
+                *reinterpret_cast<double2 *>(dz + 4 * q2) = make_double2(z.x, z.z);          // (z1, z2) of parameter 2q
+                if (2 * q2 + 1 < npar) *reinterpret_cast<double2 *>(dz + 4 * q2 + 2) = make_double2(z.y, z.w);
+            }
         }
     }
     __syncthreads();
+    if (tid == 0) tc_genctr = 0;                                    // for the next call (many barriers away)
     SUBP(0);
     // q1 = -1/2 (|(y1-y2) R^-1|^2 - |(y1-x) R^-1|^2) = -1/2 (|z1 - z2/drscale|^2 - |z1|^2)
     if (warp < nnew) {
@@ -1465,6 +1476,7 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
         const int *src = reinterpret_cast<const int *>(&ga);
         int *dst = reinterpret_cast<int *>(&a);
         for (int i = threadIdx.x; i < (int)(sizeof(RunArgs) / sizeof(int)); i += DRAM_THREADS) dst[i] = src[i];
+        if (threadIdx.x == 0) tc_genctr = 0;
     }
     __syncthreads();
     __shared__ Cand s_cand[RING];
