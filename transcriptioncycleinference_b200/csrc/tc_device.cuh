@@ -101,10 +101,14 @@ __device__ __noinline__ double4 normal_quad(uint64_t seed, uint64_t uid, uint32_
 
 // chi-square(dof) = 2*Gamma(dof/2) by Marsaglia-Tsang (dof >= 2); attempt t uses slots 2t (the normal: Box-Muller
 // in single precision like the proposal normals, words x, y) and 2t+1 (the 53-bit uniform).
-__device__ __noinline__ double chi2_draw(uint64_t seed, uint64_t uid, uint32_t step, double dof)
+// d = dof/2 - 1/3 and c = 1/sqrt(9 d) are constants of a chain: chi2_consts() once, chi2_draw_dc() per draw
+__device__ __forceinline__ void chi2_consts(double dof, double &d, double &c)
 {
-    const double a = 0.5 * dof;
-    const double d = a - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+    d = 0.5 * dof - 1.0 / 3.0;
+    c = 1.0 / sqrt(9.0 * d);
+}
+__device__ __noinline__ double chi2_draw_dc(uint64_t seed, uint64_t uid, uint32_t step, double d, double c)
+{
     for (uint32_t t = 0; t < 64; ++t) {
         const u32x4 r0 = draw(seed, uid, step, RK_CHI2, 2 * t);
         const u32x4 r1 = draw(seed, uid, step, RK_CHI2, 2 * t + 1);
@@ -119,6 +123,12 @@ __device__ __noinline__ double chi2_draw(uint64_t seed, uint64_t uid, uint32_t s
         if (tc_log(u) < 0.5 * x2 + d * (1.0 - v + tc_log(v))) return 2.0 * d * v;
     }
     return 2.0 * d;   // unreachable in practice (acceptance > 0.95 per attempt)
+}
+__device__ __forceinline__ double chi2_draw(uint64_t seed, uint64_t uid, uint32_t step, double dof)
+{
+    double d, c;
+    chi2_consts(dof, d, c);
+    return chi2_draw_dc(seed, uid, step, d, c);
 }
 
 // One out-of-line copy of the long libdevice sequences: the sampler's hot loop has to stay inside

@@ -793,7 +793,7 @@ struct ChainState {
 struct ChainCtx {
     int N, npar, npad, ld, slot_sz, wsz, ch, first_row, nstore, ring_mask;
     unsigned long long uid;
-    double adascale, inv_dr;
+    double adascale, inv_dr, chi_d, chi_c;              // chi_d, chi_c: Marsaglia-Tsang constants of chi2(N0 + 2 N)
     SmemCell cv;
     int o_x, o_ring, o_U;                               // offsets (doubles) into tc_smem
     int o_lo, o_pinv, o_wmean, o_wM2, o_mb;             // hot per-parameter vectors by offset (tc_smem + offset compiles to LDS/STS, the
@@ -1055,7 +1055,7 @@ __device__ __noinline__ void generate(const RunArgs &a, const ChainCtx &cx, int 
             const u32x4 ru = draw(a.seed, cx.uid, st, RK_U, 0);
             sc[0] = u01(ru.x, ru.y);
             sc[1] = u01(ru.z, ru.w);
-            sc[2] = a.updatesigma ? chi2_draw(a.seed, cx.uid, st, a.N0 + 2.0 * cx.N) : 1.0;
+            sc[2] = a.updatesigma ? chi2_draw_dc(a.seed, cx.uid, st, cx.chi_d, cx.chi_c) : 1.0;
             sc[5] = tc_log(sc[0]);                                  // stage 1 is decided in the log domain
         }
         __syncwarp();
@@ -1558,6 +1558,7 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
                 cx.uid = a.chain_uid ? a.chain_uid[ch] : (unsigned long long)ch;
                 cx.adascale = a.adascale > 0.0 ? a.adascale : 2.4 / sqrt((double)npar);
                 cx.inv_dr = 1.0 / a.drscale;
+                chi2_consts(a.N0 + 2.0 * N, cx.chi_d, cx.chi_c);
                 cx.cv = cv; cx.cv.d = a.cells.dmean[cid];
                 cx.o_x = o;
                 cx.x = tc_smem + o; o += npar;
