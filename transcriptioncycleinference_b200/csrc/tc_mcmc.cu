@@ -540,6 +540,57 @@ struct TmaRing {
     }
 };
 
+// The same ring filled COOPERATIVELY: every thread copies 16-byte pieces with cp.async.cg (LDGSTS) and its copies arrive on the
+// stage's full barrier (cp.async.mbarrier.arrive.noinc; 256 arrivals complete a stage).  Used where a stage is made of many
+// separate segments — chol_global's per-row pieces of a few KB: a bulk copy costs ~350-650 cycles EACH almost independently of
+// its size (scripts/stream_bench.cu), LDGSTS has no per-copy cost.  (Measured: at equal stage sizes the two fill methods give
+// the same factorisation time — what counts is the number of stage hand-overs, ~1 k cycles each; hence few, large stages.)
+template <int NS>
+struct CoopRing {
+    static_assert(NS <= TMA_MAXST && (NS & (NS - 1)) == 0, "ring size");
+    int o0, sst;
+    __device__ __forceinline__ void init(int o0_, int sst_)
+    {
+        o0 = o0_; sst = sst_;
+        __syncthreads();
+        if (threadIdx.x == 0)
+            for (int s_ = 0; s_ < NS; ++s_) { mbar_init(tc_mbar + s_, DRAM_THREADS); mbar_init(tc_mbar + TMA_MAXST + s_, SPEC); }
+        __syncthreads();
+    }
+    // every thread: wait until every warp has released the stage's previous use
+    __device__ __forceinline__ void begin(int g) const
+    {
+        if (g >= NS) mbar_wait(tc_mbar + TMA_MAXST + (g & (NS - 1)), (unsigned)((g / NS - 1) & 1));
+    }
+    // every thread: its share of one contiguous segment of `n16` 16-byte pieces -> stage offset `off` (doubles)
+    __device__ __forceinline__ void copy(int g, int off, const double *src, int n16) const
+    {
+        const unsigned dst = smem_u32(tc_smem + o0 + (g & (NS - 1)) * sst + off);
+        for (int i = threadIdx.x; i < n16; i += DRAM_THREADS)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * (unsigned)i), "l"(src + 2 * i) : "memory");
+    }
+    __device__ __forceinline__ void commit(int g) const
+    {
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(tc_mbar + (g & (NS - 1)))) : "memory");
+    }
+    __device__ __forceinline__ int acquire(int g) const  // -> offset of the stage into tc_smem (doubles)
+    {
+        const int s_ = g & (NS - 1);
+        mbar_wait(tc_mbar + s_, (unsigned)((g / NS) & 1));
+        return o0 + s_ * sst;
+    }
+    __device__ __forceinline__ void release(int g) const
+    {
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(tc_mbar + TMA_MAXST + (g & (NS - 1)));
+    }
+    __device__ __forceinline__ void fini() const         // after a __syncthreads that follows the last release
+    {
+        if (threadIdx.x == 0)
+            for (int s_ = 0; s_ < NS; ++s_) { mbar_inval(tc_mbar + s_); mbar_inval(tc_mbar + TMA_MAXST + s_); }
+    }
+};
+
 // chol_global, accumulation over `nr` staged tile rows (stride `rs` doubles) for the NM column blocks of this warp: per row one
 // A fragment and NM B fragments (constant offsets: block m sits 256 m doubles after the warp's first block) + NM MMAs.
 // Lanes whose tile column lies beyond the matrix read whatever follows the row (finite or not): those are columns / rows
@@ -593,8 +644,8 @@ __device__ __forceinline__ void cg_accumulate(int oa, int ob, int nr, int rs, do
 // false when a pivot is not positive (gW is then garbage; the caller keeps the old R).  Reads 11 MB from L2 at
 // npar = 407 (a right-looking sweep would move 34 MB).
 #define CG_MAXB 7          // column blocks per warp: npar <= 8 * 8 * 7 = 448
-#define CG_NS 8            // ring stages (a power of two)
-#define CG_RPS 8           // tile rows per stage, at most
+#define CG_NS 4            // ring stages (a power of two): few, large stages — the hand-over of a stage costs ~1 k cycles
+#define CG_RPS 32          // tile rows per stage, at most
 __device__ __noinline__ bool chol_global(int nt4, int npar, const double *gA, double invn, double qcovadj, double *gW,
                                          int o_ws, int ws_doubles)
 {
@@ -602,7 +653,7 @@ __device__ __noinline__ bool chol_global(int nt4, int npar, const double *gA, do
     const int ldS = 8 * ((nt4 + 1) >> 1) + 4;
     const int th = ar >> 2, inner = 4 * ak + (ar & 3);
     double *S = tc_smem + o_ws;                        // (offset arithmetic on tc_smem compiles to LDS / STS)
-    TmaRing<CG_NS> ring;
+    CoopRing<CG_NS> ring;
     {
         // CG_NS stages of equal capacity; a stage holds as many tile rows of the current panel as fit (<= CG_RPS); 32 doubles of
         // slack after the last one (cg_accumulate reads up to two tiles past a row)
@@ -618,13 +669,14 @@ __device__ __noinline__ bool chol_global(int nt4, int npar, const double *gA, do
 #endif
     int gi = 0, gc = 0, si = 0;        // ring uses issued (thread 0) / consumed; stages of the current panel already issued
     bool ok = true;
-    // thread 0: issue stage u of the panel at b0 (rows u rps .. of the tile rows above, each 16 ntc doubles)
+    // every thread: its share of stage u of the panel at b0 (rows u rps .. of the tile rows above, each 16 ntc doubles)
 #define CG_ISSUE(b0_, ntc_, rps_, u_)                                                                       \
     {                                                                                                       \
         const int r0__ = (u_) * (rps_), nr__ = min((rps_), (b0_) - r0__);                                     \
-        ring.begin(gi, 128u * (unsigned)((ntc_) * nr__));                                                   \
+        ring.begin(gi);                                                                                     \
         for (int q__ = 0; q__ < nr__; ++q__)                                                                \
-            ring.copy(gi, 16 * (ntc_) * q__, gW + 16 * (size_t)tidx(nt4, r0__ + q__, (b0_)), 128u * (unsigned)(ntc_)); \
+            ring.copy(gi, 16 * (ntc_) * q__, gW + 16 * (size_t)tidx(nt4, r0__ + q__, (b0_)), 8 * (ntc_));   \
+        ring.commit(gi);                                                                                    \
         ++gi;                                                                                               \
     }
 #pragma unroll 1
@@ -637,8 +689,7 @@ __device__ __noinline__ bool chol_global(int nt4, int npar, const double *gA, do
             double acc[CG_MAXB][2];
 #pragma unroll
             for (int m = 0; m < CG_MAXB; ++m) { acc[m][0] = 0.0; acc[m][1] = 0.0; }
-            if (tid == 0)
-                while (si < nst && si < CG_NS - 2) { CG_ISSUE(b0, ntc, rps, si) ++si; }
+            while (si < nst && si < CG_NS - 2) { CG_ISSUE(b0, ntc, rps, si) ++si; }
             const int nmine = nb > warp ? (nb - warp + SPEC - 1) / SPEC : 0;          // column blocks warp, warp + 8, .. < nb
             // the covariance entries of the panel are needed after the accumulation: pull them into L2 now
             if (lane < 2 * nmine) {
@@ -652,7 +703,7 @@ __device__ __noinline__ bool chol_global(int nt4, int npar, const double *gA, do
             for (int u = 0; u < nst; ++u) {
                 // issued CG_NS - 2 uses ahead: the stage being re-armed was released an iteration ago, so thread 0 does not
                 // hold the other warps in lock step
-                if (tid == 0 && si < nst) { CG_ISSUE(b0, ntc, rps, si) ++si; }
+                if (si < nst) { CG_ISSUE(b0, ntc, rps, si) ++si; }
                 const int nr = min(rps, b0 - u * rps);
                 const int pa = ring.acquire(gc) + 16 * th + inner, pb = pa + 32 * warp;
                 switch (nmine) {                                                    // warp-uniform
@@ -718,7 +769,7 @@ __device__ __noinline__ bool chol_global(int nt4, int npar, const double *gA, do
         if (tc_cholfail) { ok = false; break; }                       // uniform; nothing is in flight here
         // the first stages of the next panel that hold only final rows (< b0) start streaming now
         si = 0;
-        if (tid == 0 && b0 + 2 < nt4) {
+        if (b0 + 2 < nt4) {
             const int ntc2 = ntc - 2, rps2 = max(1, min(CG_RPS, ring.sst / (16 * ntc2)));
             while ((si + 1) * rps2 <= b0 && si < CG_NS - 2) { CG_ISSUE(b0 + 2, ntc2, rps2, si) ++si; }
         }
@@ -761,8 +812,7 @@ __device__ __noinline__ bool chol_global(int nt4, int npar, const double *gA, do
                 *reinterpret_cast<double2 *>(gW + 16 * (size_t)tidx(nt4, b0 + h, b0 + tcl) + 4 * r + 2 * c2) = make_double2(v0, v1);
             }
         }
-        fence_async_proxy();                                      // the next panels read these tiles back with bulk copies
-        __syncthreads();
+        __syncthreads();                                          // the next panels read these tiles back from L2 (cp.async.cg)
         CGP(15);
     }
 #undef CG_ISSUE
