@@ -923,6 +923,19 @@ __device__ __noinline__ void emit_s2(const RunArgs &a, const ChainCtx &cx, S2Sta
 #define GENB_MAXT 7        // column tiles per warp: npar <= 8 * 8 * 7 = 448
 #define GENB_NS 4          // ring stages
 #define GENB_RPS 8         // tile rows per stage, at most
+#ifndef GENB_COOP
+#define GENB_COOP 0        // 0: one bulk copy per stage by thread 0 (TmaRing); 1: stages filled by all threads with cp.async.cg
+                           // (CoopRing) — measured 12 % slower here: a stage of R is one contiguous 16-32 KB piece, ideal for a bulk copy
+#endif
+#if GENB_COOP
+#define GENB_RING CoopRing
+#define GENB_PRODUCER true
+#define GENB_FILL(g, src, n) { ring.begin(g); ring.copy(g, 0, src, (n) / 2); ring.commit(g); }
+#else
+#define GENB_RING TmaRing
+#define GENB_PRODUCER (tid == 0)
+#define GENB_FILL(g, src, n) ring.issue(g, src, 8u * (unsigned)(n));
+#endif
 // one k-step for the NA column tiles that still have rows: accumulator j belongs to the j-th tile from the TOP (so the live
 // ones are always a prefix and the code is straight-line: a conditional mma.sync costs a WARPSYNC each); `bt` = B fragment
 // of the top tile, tile j sits 256 j doubles before it.  EDGE: the lowest live tile (j = NA-1) is in its last k-step,
@@ -976,7 +989,7 @@ __device__ __noinline__ void gen_increments_tma(const ChainCtx &cx, int g0, int 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, npar = cx.npar;
     const int nt4 = (npar + 3) >> 2, NT = (npar + 7) >> 3;
     const int ar = lane >> 2, ak = lane & 3, th = ar >> 2, inner = 4 * ak + (ar & 3);
-    TmaRing<GENB_NS> ring;
+    GENB_RING<GENB_NS> ring;
     // the stages fill the per-warp areas (Z lives in the ring slots); one tile of room before the first stage and two after
     // the last row of a stage: the fragment reads of a half-stored tile pair fall there and are discarded
     const int sst = ((SPEC * cx.wsz - 16) / GENB_NS) & ~1, cap = sst - 32;
@@ -988,11 +1001,11 @@ __device__ __noinline__ void gen_increments_tma(const ChainCtx &cx, int g0, int 
     {                                                                                                       \
         int kend__ = pk, used__ = 0;                                                                        \
         while (kend__ < nt4 && kend__ - pk < GENB_RPS && used__ + 16 * (nt4 - kend__) <= cap) { used__ += 16 * (nt4 - kend__); ++kend__; } \
-        ring.issue(pg, src, 8u * (unsigned)used__);     /* consecutive tile rows are contiguous: ONE copy */ \
+        GENB_FILL(pg, src, used__)                      /* consecutive tile rows are contiguous: ONE segment */ \
         src += used__; pk = kend__;                                                                         \
         ++pg;                                                                                               \
     }
-    if (tid == 0)
+    if (GENB_PRODUCER)
         while (pk < nt4 && pg < GENB_NS - 2) GENB_ISSUE()
     double acc[GENB_MAXT][4];
 #pragma unroll
@@ -1009,7 +1022,7 @@ __device__ __noinline__ void gen_increments_tma(const ChainCtx &cx, int g0, int 
 #pragma unroll 1
     for (int g = 0; kk < nt4; ++g) {
         GSP_T0;
-        if (tid == 0 && pk < nt4) GENB_ISSUE()
+        if (GENB_PRODUCER && pk < nt4) GENB_ISSUE()
         GSP(28);
         int kend = kk, used = 0;                                    // the rows of stage g: the producer's packing rule
         while (kend < nt4 && kend - kk < GENB_RPS && used + 16 * (nt4 - kend) <= cap) { used += 16 * (nt4 - kend); ++kend; }
