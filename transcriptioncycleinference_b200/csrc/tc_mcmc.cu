@@ -922,7 +922,7 @@ __device__ __noinline__ void emit_s2(const RunArgs &a, const ChainCtx &cx, S2Sta
 // call and no lane issues per-element copies; the B fragment of tile column bj sits 16 (bj - kk) doubles into the row.
 #define GENB_MAXT 7        // column tiles per warp: npar <= 8 * 8 * 7 = 448
 #define GENB_NS 4          // ring stages
-#define GENB_RPS 8         // tile rows per stage, at most
+#define GENB_RPS 32        // tile rows per stage, at most (the short rows at the bottom of the triangle pack many to a stage)
 #ifndef GENB_COOP
 #define GENB_COOP 0        // 0: one bulk copy per stage by thread 0 (TmaRing); 1: stages filled by all threads with cp.async.cg
                            // (CoopRing) — measured 12 % slower here: a stage of R is one contiguous 16-32 KB piece, ideal for a bulk copy
