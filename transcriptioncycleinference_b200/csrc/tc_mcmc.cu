@@ -635,7 +635,7 @@ __device__ __forceinline__ void cg_accumulate(int oa, int ob, int nr, int rs, do
 // Panels of two tile rows (8 matrix rows).  Per panel:
 //  (1) S = A(panel rows, columns >= panel) - sum over the tile rows above of R(row, panel cols)' R(row, cols) on the FP64
 //      tensor cores: one mma.sync m8n8k4 per tile row above per 8-column block.  The tile rows above stream through
-//      the TMA ring (one bulk copy of 128 (nt4 - b0) bytes per tile row, up to 7 in flight); a warp owns the column
+//      the cooperative ring (a stage = up to CG_RPS tile rows of 128 (nt4 - b0) bytes each, two stages ahead); a warp owns the column
 //      blocks w, w+8, .. (<= CG_MAXB), its accumulators stay in registers for the whole panel; fragment reads from
 //      a stage are conflict-free (the 32 B elements of a warp are two adjacent tiles);
 //  (2) warp 0 factors the 8x8 diagonal block in registers; (3) the rest of the panel is solved one column per thread
@@ -667,7 +667,7 @@ __device__ __noinline__ bool chol_global(int nt4, int npar, const double *gA, do
 #else
 #define CGP(i)
 #endif
-    int gi = 0, gc = 0, si = 0;        // ring uses issued (thread 0) / consumed; stages of the current panel already issued
+    int gi = 0, gc = 0, si = 0;        // ring uses issued / consumed; stages of the current panel already issued (uniform)
     bool ok = true;
     // every thread: its share of stage u of the panel at b0 (rows u rps .. of the tile rows above, each 16 ntc doubles)
 #define CG_ISSUE(b0_, ntc_, rps_, u_)                                                                       \
