@@ -198,3 +198,32 @@ def test_c_dram_record_replay_and_invariants(orc, cells_npz):
     # rejected steps repeat the previous row
     rej = (r1["flags"] & 1) == 0
     assert np.all(ch[1:][rej[1:]] == ch[:-1][rej[1:]])
+
+
+def test_oracles_agree_at_config5_series_length(orc):
+    """N = 400 (BASELINE config 5; npar = 407): the literal NumPy restatement and the C restatement of ssfun agree on a synthetic
+    irregular grid with missing data, and the two DRAM restatements take the same decisions through a covariance adaptation
+    (the GPU replay tests at N = 400 lean on the C one)."""
+    co, cons = orc
+    rng = np.random.default_rng(400)
+    N = 400
+    t = np.concatenate([[0.0], np.cumsum(rng.uniform(0.15, 0.35, N - 1))])
+    ms2 = rng.uniform(0, 3, N); pp7 = rng.uniform(0, 10, N)
+    ms2[rng.random(N) < 0.5] = np.nan; pp7[rng.random(N) < 0.2] = np.nan
+    assert co.t_interp(t).size == N
+    for _ in range(3):
+        th = np.concatenate([[rng.uniform(1, 3), rng.uniform(0, 4), rng.uniform(0, 4), rng.uniform(0, 2), rng.uniform(0, 2),
+                              rng.uniform(0, 1), 15.0], rng.normal(0, 3, N)])
+        a = fl.sum_of_squares(DEFAULT_CONSTRUCT, t, np.concatenate([ms2, pp7]), th)
+        b = co.ss(cons, t, ms2, pp7, th)
+        assert abs(a - b) <= 1e-12 * abs(a)
+    x0 = osetup.initial_state(t, rng); J0 = osetup.proposal_variances(t)
+    lo, hi, mu, sg = osetup.bounds_and_priors(N, x0)
+    nsimu, burn = 150, 100
+    st = pydram.make_streams(nsimu, x0.size, 1 + 2 * N, 11)
+    rc = co.dram(cons, t, ms2, pp7, co.default_opts(nsimu, burn), x0, J0, lo, hi, mu, sg, streams=st)
+    rp = pydram.dram(lambda th: co.ss(cons, t, ms2, pp7, th), x0, J0, lo, hi, mu, sg, 2 * N, nsimu, burn,
+                     pydram.Recorded(**st))
+    assert np.array_equal(rc["flags"], rp["flags"])
+    np.testing.assert_allclose(rc["chain"], rp["chain"], rtol=0, atol=1e-7)
+    assert rc["counters"][4] == 1                       # one adaptation with a 407 x 407 factorisation (step 100)
