@@ -87,6 +87,7 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[])
     o.drscale = field_scalar(prhs[3], "drscale", o.drscale);
     o.qcovadj = field_scalar(prhs[3], "qcovadj", o.qcovadj);
     o.N0 = field_scalar(prhs[3], "N0", o.N0);
+    o.layout = (int32_t)field_scalar(prhs[3], "layout", o.layout);   // TC_LAYOUT_AUTO; 1 forces the large-series layout
     int ndev = 0;
     check(tc_device_count(&ndev));
     if (o.ngpus > ndev) o.ngpus = ndev;
