@@ -164,3 +164,19 @@ def test_synthetic_recovery_fraction():
     truth = np.zeros((4, 10)); mean = np.zeros((4, 10)); std = np.ones((4, 10))
     mean[0, 0] = 2.9; mean[1, 0] = 3.1; mean[2, 1] = -4.0
     assert synthetic.recovery(truth, mean, std) == [0.75, 0.75, 1.0]
+
+
+def test_mex_gateway_compiles_against_stub_header(tmp_path):
+    """matlab/tcmcmc_mex.cu (the MATLAB side of the boundary) is syntax-checked against tests/stubs/mex.h and the real
+    include/tcmcmc.h: every ABI call and struct field it uses exists with the types it assumes.  (MATLAB itself is
+    not in this image; the gateway is host-only C++ despite the .cu suffix mexcuda wants.)"""
+    import shutil, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("no g++")
+    src = tmp_path / "tcmcmc_mex.cpp"
+    shutil.copy(os.path.join(root, "matlab", "tcmcmc_mex.cu"), src)
+    res = subprocess.run([gxx, "-std=c++17", "-fsyntax-only", "-Wall", "-I", os.path.join(root, "tests", "stubs"),
+                          "-I", os.path.join(root, "include"), str(src)], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
