@@ -362,7 +362,7 @@ __device__ __noinline__ bool chol_tiled(int nt4, int oW, bool prof)
 #else
 #define CHP(i)
 #endif
-    const int tid = threadIdx.x, nthr = blockDim.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, nthr = blockDim.x, warp = tid >> 5;
     const int T = nt4 * (nt4 + 1) / 2;
     if (tid == 0) tc_cholfail = 0;
     __syncthreads();
