@@ -59,12 +59,13 @@ typedef struct tc_construct {
     double pp7_start[TC_MAX_SETS], pp7_end[TC_MAX_SETS], pp7_loopn[TC_MAX_SETS];
 } tc_construct;
 
-/* Forward-model algorithm selector (results agree to ~1e-14 relative; tests/test_ss_parity.py) */
+/* Forward-model algorithm selector (results agree to ~1e-14 relative; tests/test_gpu_ss.py) */
 enum {
     TC_ALGO_PAIRS = 0,     /* every (cohort i, time j) pair with position v*(t_j - t_i); any grid.
                               This is the W_op(N) = 11 N(N-1)/2 + 20 N algorithm of SURVEY.md 8(d). */
-    TC_ALGO_TOEPLITZ = 1   /* uniform t_interp grid only: per-lag response table g(v*dt*lag) +
-                              triangular convolution (2 DFMA per pair) */
+    TC_ALGO_TOEPLITZ = 1   /* uniform t_interp grid only: the response depends on the lag alone and is 0 / ramp /
+                              plateau / 0 in the lag, so each time point is O(1) from two exact prefix sums of the
+                              cohort sizes (counts K, first moments S): O(N) per evaluation */
 };
 
 /* Options of the DRAM sampler — replaces the `model`/`options` structs handed to mcmcrun at
@@ -76,8 +77,8 @@ typedef struct tc_mcmc_opts {
     int32_t adaptint;         /* options.adaptint = 100 (:268); 0 disables adaptation */
     int32_t ntry;             /* 'dram' => 2: one delayed-rejection retry; 1 => plain AM */
     int32_t updatesigma;      /* options.updatesigma = 1 (:265) */
-    int32_t burnin_cumulative;/* burn-in scaling uses 0: rejections since last adaptation,
-                                 1: cumulative rejection rate */
+    int32_t burnin_cumulative;/* burn-in scaling: 1 (default) the CUMULATIVE rejection rate, mcmcstat's
+                                 `rejected > 0.95*isimu` ([U]); 0: rejections since the last adaptation */
     int32_t n_burn;           /* summaries / stored rows start at MATLAB row n_burn: chain(n_burn:end,:)
                                  (:276-283); >= 1 */
     int32_t store_chain;      /* 0: summaries only; 1: also return rows n_burn..nsimu and s2chain */
@@ -97,7 +98,8 @@ typedef struct tc_mcmc_opts {
     int32_t layout;           /* TC_LAYOUT_AUTO (0), or TC_LAYOUT_BIG to force the large-series layout (ring of 8 proposal
                                  slots, proposal factor factorised through HBM/L2) that series with more than ~210
                                  points get automatically; same chain either way (parity tests) */
-    int32_t _pad;
+    int32_t qcovadj_always;   /* 0 (default): R = chol(cov), and chol(cov + qcovadj I) only when that fails — mcmcstat's
+                                 "try to blow it" branch [U]; 1: always factor cov + qcovadj I */
 } tc_mcmc_opts;
 enum { TC_LAYOUT_AUTO = 0, TC_LAYOUT_BIG = 1 };
 

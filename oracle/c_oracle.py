@@ -36,7 +36,7 @@ class Construct(C.Structure):
 class DramOpts(C.Structure):
     _fields_ = [
         ("nsimu", C.c_int), ("burnintime", C.c_int), ("adaptint", C.c_int), ("ntry", C.c_int),
-        ("updatesigma", C.c_int), ("burnin_cumulative", C.c_int),
+        ("updatesigma", C.c_int), ("burnin_cumulative", C.c_int), ("qcovadj_always", C.c_int),
         ("drscale", C.c_double), ("adascale", C.c_double), ("qcovadj", C.c_double),
         ("burnin_scale", C.c_double), ("N0", C.c_double), ("S20", C.c_double),
         ("sigma2_0", C.c_double), ("Nobs", C.c_double),
@@ -45,7 +45,7 @@ class DramOpts(C.Structure):
 
 def default_opts(nsimu, burnintime, Nobs=0.0, **kw):
     o = DramOpts(nsimu=nsimu, burnintime=burnintime, adaptint=100, ntry=2, updatesigma=1,
-                 burnin_cumulative=0, drscale=5.0, adascale=0.0, qcovadj=1e-8, burnin_scale=10.0,
+                 burnin_cumulative=1, qcovadj_always=0, drscale=5.0, adascale=0.0, qcovadj=1e-8, burnin_scale=10.0,
                  N0=1.0, S20=1.0, sigma2_0=1.0, Nobs=Nobs)
     for k, v in kw.items():
         setattr(o, k, v)

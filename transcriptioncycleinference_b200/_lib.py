@@ -49,7 +49,7 @@ class McmcOpts(C.Structure):
         ("devices", C.c_int32 * MAX_GPUS),
         ("drscale", C.c_double), ("adascale", C.c_double), ("qcovadj", C.c_double),
         ("burnin_scale", C.c_double), ("N0", C.c_double), ("S20", C.c_double), ("sigma2_0", C.c_double),
-        ("seed", C.c_uint64), ("layout", C.c_int32), ("_pad", C.c_int32),
+        ("seed", C.c_uint64), ("layout", C.c_int32), ("qcovadj_always", C.c_int32),
     ]
 
 

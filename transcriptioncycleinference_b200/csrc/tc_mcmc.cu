@@ -14,6 +14,7 @@
 #include <cstring>
 #include <limits>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "tc_device.cuh"
@@ -35,6 +36,14 @@ static int fail(int code, const std::string &msg)
         if (e__ != cudaSuccess)                                                               \
             return fail(TC_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));       \
     } while (0)
+
+// The library is loaded into host applications (MATLAB through MEX, a PyTorch process) that have their own notion of the
+// current device: every entry point that calls cudaSetDevice restores the caller's device on return.
+struct DeviceGuard {
+    int prev = -1;
+    DeviceGuard() { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
 
 #define DRAM_THREADS 256   // 8 warps per chain
 #define SPEC 8             // forward-model evaluations per speculative round (= warps per CTA)
@@ -150,7 +159,7 @@ struct RunArgs {
     tc_construct cons;
     // options
     int nsimu, burnintime, adaptint, ntry, updatesigma, burnin_cumulative, n_burn, store_chain, replay,
-        algo;
+        algo, qcovadj_always;
     double drscale, adascale, qcovadj, burnin_scale, N0, S20, sigma2_0;
     unsigned long long seed;
     // chains
@@ -494,6 +503,12 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
 }
 // generic-proxy writes (st.global / st.shared) that a later bulk copy reads or overwrites: order them before the async proxy
 __device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// after mbarrier.init by one thread: make the initialised barriers visible to the async proxy (TMA complete_tx, cp.async arrive)
+__device__ __forceinline__ void fence_mbar_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async;" ::: "memory");
+}
 // ring bookkeeping: use number g of the ring -> stage g % NS (NS a power of two); producer side (thread 0) and consumer
 // side (everyone)
 template <int NS>
@@ -506,7 +521,10 @@ struct TmaRing {
         fence_async_proxy();                             // the stages were last written by ordinary stores
         __syncthreads();
         if (threadIdx.x == 0)
+        {
             for (int s_ = 0; s_ < NS; ++s_) { mbar_init(tc_mbar + s_, 1); mbar_init(tc_mbar + TMA_MAXST + s_, SPEC); }
+            fence_mbar_init();                           // the generic-proxy inits, before the async proxy's complete_tx
+        }
         __syncthreads();
     }
     // thread 0: arm use g for `total` bytes (waits until every warp has released the stage's previous use), then copy pieces
@@ -554,7 +572,10 @@ struct CoopRing {
         o0 = o0_; sst = sst_;
         __syncthreads();
         if (threadIdx.x == 0)
+        {
             for (int s_ = 0; s_ < NS; ++s_) { mbar_init(tc_mbar + s_, DRAM_THREADS); mbar_init(tc_mbar + TMA_MAXST + s_, SPEC); }
+            fence_mbar_init();
+        }
         __syncthreads();
     }
     // every thread: wait until every warp has released the stage's previous use
@@ -1161,6 +1182,9 @@ __device__ __noinline__ void generate(const RunArgs &a, const ChainCtx &cx, int 
     }
     SUBP(1);
     if (r_diag) {
+        // big layout: Z lives in the ring slots and is scaled IN PLACE below, while the warps above may still be reading it
+        // for the norms (the regular layout keeps Z apart, and gen_increments_tma starts with a barrier of its own)
+        if (big || TC_TMA_ALL) __syncthreads();
 #pragma unroll 1
         for (int sidx = 0; sidx < nnew; ++sidx) {
             const double2 *dz = reinterpret_cast<const double2 *>(ZROW(sidx));
@@ -1458,10 +1482,14 @@ __device__ __noinline__ int adapt(const RunArgs &a, const ChainCtx &cx, int isim
         // R = chol(cov + qcovadj I) * adascale, factorised in shared memory (tiled layout), kept in HBM/L2
         const double invn = 1.0 / (cov_n - 1.0);
         const int nt4 = (npar + 3) >> 2, T4 = nt4 * (nt4 + 1) / 2;
+        // mcmcstat: [Ra,is] = chol(cov); only when that fails ("try to blow it") chol(cov + qcovadj I)  [U]; qcovadj_always = 1
+        // factors cov + qcovadj I at once
         if (a.big) {
             // the factor does not fit in shared memory: factorise through HBM/L2 into this CTA's workspace
             double *gW = a.gW + (size_t)blockIdx.x * a.ldR;
-            const bool ok = chol_global(nt4, npar, cx.gM2, invn, a.qcovadj, gW, cx.o_ring, (cx.ring_mask + 1) * cx.slot_sz + SPEC * cx.wsz);
+            const int o_ws = cx.o_ring, ws_d = (cx.ring_mask + 1) * cx.slot_sz + SPEC * cx.wsz;
+            bool ok = chol_global(nt4, npar, cx.gM2, invn, a.qcovadj_always ? a.qcovadj : 0.0, gW, o_ws, ws_d);
+            if (!ok && !a.qcovadj_always) ok = chol_global(nt4, npar, cx.gM2, invn, a.qcovadj, gW, o_ws, ws_d);
             SUBP(11);
             if (ok) {
                 scaled_copy_cg(reinterpret_cast<double2 *>(cx.gRb), reinterpret_cast<const double2 *>(gW), 8 * T4, cx.adascale);
@@ -1473,25 +1501,31 @@ __device__ __noinline__ int adapt(const RunArgs &a, const ChainCtx &cx, int isim
         }
         double *W = tc_smem + cx.o_ring;
         unsigned short *tab = reinterpret_cast<unsigned short *>(W + 16 * T4);
+        bool ok = false;
 #pragma unroll 1
-        for (int t = tid; t < T4; t += DRAM_THREADS) {
-            int rem = t, b = 0;
-            while (rem >= nt4 - b) { rem -= nt4 - b; ++b; }
-            tab[t] = (unsigned short)((b << 8) | (b + rem));
-        }
-        scaled_copy_cg(reinterpret_cast<double2 *>(W), reinterpret_cast<const double2 *>(cx.gM2), 8 * T4, invn);
-        __syncthreads();
-        // + qcovadj I; identity on the padding rows (the rest of the padding is zero: it only ever accumulated zeros)
+        for (int attempt = a.qcovadj_always ? 1 : 0; attempt < 2 && !ok; ++attempt) {
+            const double adj = attempt ? a.qcovadj : 0.0;
+            __syncthreads();
 #pragma unroll 1
-        for (int i = tid; i < 4 * nt4; i += DRAM_THREADS) {
-            double *d = W + 16 * tidx(nt4, i >> 2, i >> 2) + 5 * (i & 3);
-            *d = i < npar ? *d + a.qcovadj : 1.0;
+            for (int t = tid; t < T4; t += DRAM_THREADS) {
+                int rem = t, b = 0;
+                while (rem >= nt4 - b) { rem -= nt4 - b; ++b; }
+                tab[t] = (unsigned short)((b << 8) | (b + rem));
+            }
+            scaled_copy_cg(reinterpret_cast<double2 *>(W), reinterpret_cast<const double2 *>(cx.gM2), 8 * T4, invn);
+            __syncthreads();
+            // + adj I; identity on the padding rows (the rest of the padding is zero: it only ever accumulated zeros)
+#pragma unroll 1
+            for (int i = tid; i < 4 * nt4; i += DRAM_THREADS) {
+                double *d = W + 16 * tidx(nt4, i >> 2, i >> 2) + 5 * (i & 3);
+                *d = i < npar ? *d + adj : 1.0;
+            }
+            __syncthreads();
+            SUBP(10);
+            ok = chol_tiled(nt4, cx.o_ring, cx.ch == 0);
+            __syncthreads();
+            SUBP(11);
         }
-        __syncthreads();
-        SUBP(10);
-        const bool ok = chol_tiled(nt4, cx.o_ring, cx.ch == 0);
-        __syncthreads();
-        SUBP(11);
         if (ok) {
             {
                 const double2 *src = reinterpret_cast<const double2 *>(W);
@@ -2013,6 +2047,10 @@ struct DevCells {
     int device = -1;
     CellsDev d{};
     std::vector<void *> allocs;
+    // Scratch of the fits comes from a PRIVATE stream-ordered pool owned by the dataset (created on first use, destroyed
+    // with it): consecutive fits recycle their tens of MB without cudaMalloc/cudaFree, and the host application's default
+    // pool is never touched.
+    mutable cudaMemPool_t pool = nullptr;
 };
 
 struct tc_cells {
@@ -2109,7 +2147,7 @@ void tc_opts_default(tc_mcmc_opts *o)
 {
     std::memset(o, 0, sizeof(*o));
     o->nsimu = 20000; o->burnintime = 10000; o->adaptint = 100; o->ntry = 2; o->updatesigma = 1;
-    o->burnin_cumulative = 0; o->n_burn = 10000; o->store_chain = 0; o->replay = 0; o->algo = TC_ALGO_TOEPLITZ;
+    o->burnin_cumulative = 1; o->qcovadj_always = 0; o->n_burn = 10000; o->store_chain = 0; o->replay = 0; o->algo = TC_ALGO_TOEPLITZ;
     o->ngpus = 1;
     for (int i = 0; i < TC_MAX_GPUS; ++i) o->devices[i] = -1;
     o->drscale = 5.0; o->adascale = 0.0; o->qcovadj = 1e-8; o->burnin_scale = 10.0; o->N0 = 1.0; o->S20 = 1.0;
@@ -2128,6 +2166,7 @@ int tc_cells_create(const tc_construct *construct, int ncells, const int32_t *N,
     int ndevs = 0;
     if (cudaGetDeviceCount(&ndevs) != cudaSuccess || ndevs < 1) return fail(TC_ENODEV, "no CUDA device available (libtcmcmc has no CPU fallback)");
     if (ndev < 1) ndev = 1;
+    DeviceGuard guard;
     tc_cells *c = new tc_cells();
     c->cons = *construct;
     c->ncells = ncells;
@@ -2201,9 +2240,11 @@ int tc_cells_create(const tc_construct *construct, int ncells, const int32_t *N,
 void tc_cells_destroy(tc_cells *c)
 {
     if (!c) return;
+    DeviceGuard guard;
     for (auto &dc : c->dev) {
         if (dc.device >= 0) cudaSetDevice(dc.device);
         for (void *p : dc.allocs) cudaFree(p);
+        if (dc.pool) { cudaDeviceSynchronize(); cudaMemPoolDestroy(dc.pool); dc.pool = nullptr; }
     }
     delete c;
 }
@@ -2269,6 +2310,7 @@ int tc_ss_batch_device(const tc_cells *c, int device, int64_t nbatch, const int3
     if (!c) return fail(TC_EINVAL, "cells is NULL");
     const DevCells *dc = find_dev(c, device);
     if (!dc) return fail(TC_EINVAL, "cells not resident on that device");
+    DeviceGuard guard;
     CUDA_TRY(cudaSetDevice(device));
     return launch_ss(c, dc, nbatch, d_cell_id, d_theta, ld, algo, 0, d_ss_out, nullptr, nullptr, 0, (cudaStream_t)stream);
 }
@@ -2276,11 +2318,11 @@ int tc_ss_batch_device(const tc_cells *c, int device, int64_t nbatch, const int3
 }  // extern "C"
 
 struct DevBuf {                      // RAII for device scratch
-    // With a stream: stream-ordered allocation from the device's default memory pool, whose release threshold
-    // tc_mcmc_run raises, so that the scratch of one fit (tens of MB) is recycled by the next instead of going
-    // through cudaMalloc/cudaFree every call.
+    // With a pool: stream-ordered allocation from the dataset's private memory pool (DevCells::pool), so that the
+    // scratch of one fit (tens of MB) is recycled by the next instead of going through cudaMalloc/cudaFree every call.
     std::vector<void *> ptrs;
     cudaStream_t st = nullptr;
+    cudaMemPool_t pool = nullptr;
     bool pooled = false;
     void release()
     {
@@ -2292,7 +2334,7 @@ struct DevBuf {                      // RAII for device scratch
     {
         void *q = nullptr;
         const size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
-        cudaError_t e = pooled ? cudaMallocAsync(&q, bytes, st) : cudaMalloc(&q, bytes);
+        cudaError_t e = pooled ? cudaMallocFromPoolAsync(&q, bytes, pool, st) : cudaMalloc(&q, bytes);
         if (e == cudaSuccess) { ptrs.push_back(q); p = static_cast<T *>(q); }
         return e;
     }
@@ -2308,6 +2350,7 @@ static int ss_host(const tc_cells *c, int64_t nbatch, const int32_t *cell_id, co
         if (cell_id[b] < 0 || cell_id[b] >= c->ncells) return fail(TC_EINVAL, "cell_id out of range");
     if ((o1 || o2) && ldo < c->Nmax) return fail(TC_EINVAL, "ldo < max(N)");
     const DevCells *dc = &c->dev[0];
+    DeviceGuard guard;
     CUDA_TRY(cudaSetDevice(dc->device));
     DevBuf buf;
     int *d_cell = nullptr; double *d_theta = nullptr, *d_ss = nullptr, *d_o1 = nullptr, *d_o2 = nullptr;
@@ -2393,9 +2436,20 @@ int tc_mcmc_run(const tc_cells *c, const tc_mcmc_opts *o, int nchains, const int
     if (o->store_chain && (!chain || !s2chain)) return fail(TC_EINVAL, "store_chain set but chain/s2chain is NULL");
     for (int i = 0; i < nchains; ++i)
         if (chain_cell[i] < 0 || chain_cell[i] >= c->ncells) return fail(TC_EINVAL, "chain_cell out of range");
+    // params{i} = {name, init, lo, hi, mu, sig} (TranscriptionCycleMCMC.m:242-255): mcmcstat refuses an initial value outside
+    // its bounds; a prior width that is zero, negative or NaN would make the prior sum NaN and the chain would never accept
     for (size_t i = 0; i < (size_t)nchains; ++i)
-        for (int p = 0; p < 7 + c->N[chain_cell[i]]; ++p)
-            if (!(qcov_diag[i * ld + p] > 0)) return fail(TC_EINVAL, "qcov_diag must be > 0");
+        for (int p = 0; p < 7 + c->N[chain_cell[i]]; ++p) {
+            const size_t e = i * ld + p;
+            const char *what = nullptr;
+            if (!(qcov_diag[e] > 0)) what = "qcov_diag must be > 0";
+            else if (!(low[e] <= upp[e])) what = "low must be <= upp";
+            else if (!(theta0[e] >= low[e] && theta0[e] <= upp[e])) what = "theta0 must lie inside [low, upp]";
+            else if (!(prior_sig[e] > 0)) what = "prior_sig must be > 0 (Inf = flat)";
+            else if (std::isnan(prior_mu[e])) what = "prior_mu is NaN";
+            if (what) return fail(TC_EINVAL, std::string(what) + " (chain " + std::to_string(i) + ", parameter " + std::to_string(p) + ")");
+        }
+    DeviceGuard guard;                                    // declared before `runs`: restores the caller's device last
 
     // devices: 'numParPools' => GPU count
     int ngpus = std::max(1, o->ngpus);
@@ -2436,14 +2490,24 @@ int tc_mcmc_run(const tc_cells *c, const tc_mcmc_opts *o, int nchains, const int
         CUDA_TRY(cudaSetDevice(r.device));
         CUDA_TRY(cudaStreamCreateWithFlags(&r.st, cudaStreamNonBlocking));
         {
-            cudaMemPool_t pool = nullptr;
+            const DevCells *dcp = find_dev(c, r.device);
             int pools = 0;
-            if (cudaDeviceGetAttribute(&pools, cudaDevAttrMemoryPoolsSupported, r.device) == cudaSuccess && pools &&
-                cudaDeviceGetDefaultMemPool(&pool, r.device) == cudaSuccess) {
-                unsigned long long keep = ~0ULL;
-                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-                r.buf.st = r.st; r.buf.pooled = true;
+            if (!dcp->pool && cudaDeviceGetAttribute(&pools, cudaDevAttrMemoryPoolsSupported, r.device) == cudaSuccess && pools) {
+                cudaMemPoolProps props{};
+                props.allocType = cudaMemAllocationTypePinned;
+                props.handleTypes = cudaMemHandleTypeNone;
+                props.location.type = cudaMemLocationTypeDevice;
+                props.location.id = r.device;
+                cudaMemPool_t pool = nullptr;
+                if (cudaMemPoolCreate(&pool, &props) == cudaSuccess) {
+                    unsigned long long keep = ~0ULL;                  // our own pool: keep the scratch between fits
+                    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+                    dcp->pool = pool;
+                } else {
+                    (void)cudaGetLastError();
+                }
             }
+            if (dcp->pool) { r.buf.st = r.st; r.buf.pool = dcp->pool; r.buf.pooled = true; }
         }
         CUDA_TRY(cudaEventCreate(&r.e0));
         CUDA_TRY(cudaEventCreate(&r.e1));
@@ -2451,7 +2515,7 @@ int tc_mcmc_run(const tc_cells *c, const tc_mcmc_opts *o, int nchains, const int
         a.cells = find_dev(c, r.device)->d; a.cons = c->cons;
         a.nsimu = o->nsimu; a.burnintime = o->burnintime; a.adaptint = o->adaptint; a.ntry = o->ntry;
         a.updatesigma = o->updatesigma; a.burnin_cumulative = o->burnin_cumulative; a.n_burn = o->n_burn;
-        a.store_chain = o->store_chain; a.replay = o->replay; a.algo = o->algo;
+        a.store_chain = o->store_chain; a.replay = o->replay; a.algo = o->algo; a.qcovadj_always = o->qcovadj_always;
         a.drscale = o->drscale; a.adascale = o->adascale; a.qcovadj = o->qcovadj; a.burnin_scale = o->burnin_scale;
         a.N0 = o->N0; a.S20 = o->S20; a.sigma2_0 = o->sigma2_0; a.seed = o->seed;
         a.nchains = nc; a.ld = ld; a.ldR = ldR; a.do_cov = do_cov ? 1 : 0;
@@ -2529,32 +2593,52 @@ int tc_mcmc_run(const tc_cells *c, const tc_mcmc_opts *o, int nchains, const int
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaEventRecord(r.e1, r.st));
     }
-    double kmax = 0.0;
-    for (auto &r : runs) {
+    // Drain: every device's outputs go back on its own stream; with several devices one host thread per device, so the
+    // device -> host copies (raw chains: GBs) of the 8 GPUs overlap instead of queueing behind each other.
+    std::vector<int64_t> cnt_tmp;
+    if (!counters) { cnt_tmp.assign((size_t)nchains * TC_NCOUNTERS, 0); counters = cnt_tmp.data(); }   // TC_CNT_STATUS is always checked
+    std::vector<double> ksec(runs.size(), 0.0);
+    std::vector<int> rcs(runs.size(), TC_OK);
+    std::vector<std::string> errs(runs.size());
+    auto drain = [&](size_t g) -> int {
+        DevRun &r = runs[g];
         const int nc = r.c1 - r.c0;
         const size_t o0 = (size_t)r.c0;
         CUDA_TRY(cudaSetDevice(r.device));
-        CUDA_TRY(cudaStreamSynchronize(r.st));
+        RunArgs &a = r.a;
+        cudaStream_t st = r.st;
+        if (mean) CUDA_TRY(cudaMemcpyAsync(mean + o0 * ld, a.mean, (size_t)nc * ld * 8, cudaMemcpyDeviceToHost, st));
+        if (std) CUDA_TRY(cudaMemcpyAsync(std + o0 * ld, a.std, (size_t)nc * ld * 8, cudaMemcpyDeviceToHost, st));
+        if (sig) CUDA_TRY(cudaMemcpyAsync(sig + o0 * 2, a.sig, (size_t)nc * 2 * 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(counters + o0 * TC_NCOUNTERS, a.counters, (size_t)nc * TC_NCOUNTERS * 8, cudaMemcpyDeviceToHost, st));
+        if (o->store_chain) {
+            CUDA_TRY(cudaMemcpyAsync(chain + o0 * nstore * ld, a.chain, (size_t)nc * nstore * ld * 8, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync(s2chain + o0 * o->nsimu, a.s2chain, (size_t)nc * o->nsimu * 8, cudaMemcpyDeviceToHost, st));
+        }
+        if (rp && rp->flags) CUDA_TRY(cudaMemcpyAsync(rp->flags + o0 * o->nsimu, a.flags, (size_t)nc * o->nsimu * 4, cudaMemcpyDeviceToHost, st));
+        if (rp && rp->sschain) CUDA_TRY(cudaMemcpyAsync(rp->sschain + o0 * o->nsimu, a.sschain, (size_t)nc * o->nsimu * 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
         float ms = 0;
         CUDA_TRY(cudaEventElapsedTime(&ms, r.e0, r.e1));
-        kmax = std::max(kmax, (double)ms * 1e-3);
-        RunArgs &a = r.a;
-        if (mean) CUDA_TRY(cudaMemcpy(mean + o0 * ld, a.mean, (size_t)nc * ld * 8, cudaMemcpyDeviceToHost));
-        if (std) CUDA_TRY(cudaMemcpy(std + o0 * ld, a.std, (size_t)nc * ld * 8, cudaMemcpyDeviceToHost));
-        if (sig) CUDA_TRY(cudaMemcpy(sig + o0 * 2, a.sig, (size_t)nc * 2 * 8, cudaMemcpyDeviceToHost));
-        if (counters) CUDA_TRY(cudaMemcpy(counters + o0 * TC_NCOUNTERS, a.counters, (size_t)nc * TC_NCOUNTERS * 8, cudaMemcpyDeviceToHost));
-        if (o->store_chain) {
-            CUDA_TRY(cudaMemcpy(chain + o0 * nstore * ld, a.chain, (size_t)nc * nstore * ld * 8, cudaMemcpyDeviceToHost));
-            CUDA_TRY(cudaMemcpy(s2chain + o0 * o->nsimu, a.s2chain, (size_t)nc * o->nsimu * 8, cudaMemcpyDeviceToHost));
-        }
-        if (rp && rp->flags) CUDA_TRY(cudaMemcpy(rp->flags + o0 * o->nsimu, a.flags, (size_t)nc * o->nsimu * 4, cudaMemcpyDeviceToHost));
-        if (rp && rp->sschain) CUDA_TRY(cudaMemcpy(rp->sschain + o0 * o->nsimu, a.sschain, (size_t)nc * o->nsimu * 8, cudaMemcpyDeviceToHost));
+        ksec[g] = (double)ms * 1e-3;
+        return TC_OK;
+    };
+    if (runs.size() == 1) {
+        rcs[0] = drain(0);
+        if (rcs[0]) return rcs[0];
+    } else {
+        std::vector<std::thread> th;
+        for (size_t g = 0; g < runs.size(); ++g)
+            th.emplace_back([&, g]() { rcs[g] = drain(g); if (rcs[g]) errs[g] = g_err; });
+        for (auto &t : th) t.join();
+        for (size_t g = 0; g < runs.size(); ++g) if (rcs[g]) return fail(rcs[g], errs[g]);
     }
+    double kmax = 0.0;
+    for (double k : ksec) kmax = std::max(kmax, k);
     g_last_kernel_s = kmax;
-    if (counters)
-        for (int i = 0; i < nchains; ++i)
-            if (counters[(size_t)i * TC_NCOUNTERS + TC_CNT_STATUS] != 0)
-                return fail(TC_ESTATE, "ss(theta0) is not finite for chain " + std::to_string(i));
+    for (int i = 0; i < nchains; ++i)
+        if (counters[(size_t)i * TC_NCOUNTERS + TC_CNT_STATUS] != 0)
+            return fail(TC_ESTATE, "ss(theta0) is not finite for chain " + std::to_string(i));
     return TC_OK;
 }
 
@@ -2564,6 +2648,7 @@ int tc_rng_dump(uint64_t seed, uint64_t chain_uid, int npar, double chi2_dof, in
     if (npar < 1 || nsimu < 1 || !z1 || !u1 || !z2 || !u2 || !chi2) return fail(TC_EINVAL, "bad argument");
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) return fail(TC_ENODEV, "no such CUDA device");
+    DeviceGuard guard;
     CUDA_TRY(cudaSetDevice(device));
     DevBuf b;
     double *dz1, *dz2, *du1, *du2, *dc2;
@@ -2599,6 +2684,7 @@ int tc_measure_fp64_peak(int device, double *dfma_per_s, double *sm_clock_mhz)
 {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) return fail(TC_ENODEV, "no such CUDA device");
+    DeviceGuard guard;
     CUDA_TRY(cudaSetDevice(device));
     int sms = 0;
     CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
