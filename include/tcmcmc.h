@@ -95,13 +95,15 @@ typedef struct tc_mcmc_opts {
     double sigma2_0;          /* model.sigma2 = 1 (:212,259) */
     uint64_t seed;            /* Philox key; draws are addressed by (seed, chain_uid, step, slot) so
                                  results do not depend on the GPU count */
-    int32_t layout;           /* TC_LAYOUT_AUTO (0), or TC_LAYOUT_BIG to force the large-series layout (ring of 8 proposal
-                                 slots, proposal factor factorised through HBM/L2) that series with more than ~210
-                                 points get automatically; same chain either way (parity tests) */
+    int32_t layout;           /* TC_LAYOUT_AUTO (0): one CTA per chain (speculative rounds) for up to a few chains per SM, one
+                                 WARP per chain beyond that (thousands of chains: BASELINE config 3), the large-series
+                                 layout for series with more than ~210 points.  TC_LAYOUT_BIG forces the large-series layout
+                                 (ring of 8 proposal slots, proposal factor factorised through HBM/L2), TC_LAYOUT_WARP the
+                                 chain-per-warp kernel.  Same chain whichever runs (parity tests) */
     int32_t qcovadj_always;   /* 0 (default): R = chol(cov), and chol(cov + qcovadj I) only when that fails — mcmcstat's
                                  "try to blow it" branch [U]; 1: always factor cov + qcovadj I */
 } tc_mcmc_opts;
-enum { TC_LAYOUT_AUTO = 0, TC_LAYOUT_BIG = 1 };
+enum { TC_LAYOUT_AUTO = 0, TC_LAYOUT_BIG = 1, TC_LAYOUT_WARP = 2 };
 
 /* Per-chain counters returned by tc_mcmc_run (int64 each) */
 enum {

@@ -46,16 +46,17 @@ def _oracle_chain(orc, cells_npz, c, opts_kw, inputs, i, streams=None):
     return co.dram(cons, t, ms2, pp7, opts, th0, q, lo, hi, mu, sg, streams=st)
 
 
-@pytest.mark.parametrize("algo", [1, 0])
-def test_replay_accept_reject_identical(gpu_cells, cells_npz, orc, algo):
+@pytest.mark.parametrize("algo,layout", [(1, 0), (0, 0), (1, 2), (0, 2)])
+def test_replay_accept_reject_identical(gpu_cells, cells_npz, orc, algo, layout):
     """600 steps with burn-in 300: covers burn-in, the first covariance adaptation (Cholesky of
-    the 300-row covariance) and three later ones."""
+    the 300-row covariance) and three later ones.  layout 0: one CTA per chain (dram_kernel), 2: one warp per chain
+    (dram_warp_kernel)."""
     from transcriptioncycleinference_b200 import _lib
     chain_cell = np.array([0, 5, 77, 150, 298, 42], dtype=np.int32)
     nsimu, burn = 600, 300
     inputs = _setup(gpu_cells, chain_cell, 11)
     st = _streams(len(chain_cell), nsimu, gpu_cells.ld, cells_npz["N"][chain_cell], 12)
-    opts = _lib.default_opts(nsimu=nsimu, burnintime=burn, n_burn=1, store_chain=1, replay=1, algo=algo, **SHORT)
+    opts = _lib.default_opts(nsimu=nsimu, burnintime=burn, n_burn=1, store_chain=1, replay=1, algo=algo, layout=layout, **SHORT)
     out = gpu_cells.mcmc_run(opts, chain_cell, *inputs, replay=st, want_flags=True)
     for i, c in enumerate(chain_cell):
         ref = _oracle_chain(orc, cells_npz, int(c), dict(nsimu=nsimu, burnintime=burn), inputs, i, st)
@@ -252,7 +253,7 @@ def test_replay_long_default_path(gpu_cells, cells_npz, orc):
     all 20 000 steps, chain equal to 1e-6 (150 factorisations in a different summation order), counters equal."""
     from transcriptioncycleinference_b200 import _lib
     nsimu, burn = 20000, 5000
-    for c, layout in ((17, 0), (211, 1)):
+    for c, layout in ((17, 0), (211, 1), (250, 2)):
         chain_cell = np.array([c], dtype=np.int32)
         inputs = _setup(gpu_cells, chain_cell, 81 + layout)
         st = _streams(1, nsimu, gpu_cells.ld, cells_npz["N"][chain_cell], 82 + layout)
@@ -297,7 +298,7 @@ def test_singular_covariance_falls_back(gpu_cells, cells_npz, orc):
     lo, hi = th0.copy(), th0.copy()
     nsimu, burn = 400, 200
     st = _streams(1, nsimu, gpu_cells.ld, cells_npz["N"][chain_cell], 96)
-    for layout in (0, 1):
+    for layout in (0, 1, 2):
         opts = _lib.default_opts(nsimu=nsimu, burnintime=burn, n_burn=1, store_chain=1, replay=1, layout=layout)
         out = gpu_cells.mcmc_run(opts, chain_cell, th0, q, lo, hi, mu, sg, replay=st, want_flags=True)
         ref = _oracle_chain(orc, cells_npz, 5, dict(nsimu=nsimu, burnintime=burn, extra={}), (th0, q, lo, hi, mu, sg), 0, st)
@@ -338,3 +339,42 @@ def test_input_validation_and_device_restored(gpu_cells):
             assert torch.cuda.current_device() == 0
     except ImportError:
         pass
+
+
+def test_warp_kernel_production_path(gpu_cells, cells_npz, orc):
+    """dram_warp_kernel (one warp per chain: what thousands of chains get, BASELINE config 3) on its production path:
+    (1) Philox streams: the chain is the oracle's on the device's dumped randomness, through 16 park/resume slices and with
+    more chains than one CTA holds (two groups of 16 + a ragged one); (2) the same chains through dram_kernel: identical
+    accept/reject sequence and counters, means equal to rounding (the two kernels factor the covariance in different orders);
+    (3) option variants the warp kernel implements separately: ntry = 1, updatesigma = 0, a bounds vector without the
+    reference's head + block structure (generic path)."""
+    from transcriptioncycleinference_b200 import _lib
+    cc = np.arange(0, 296, 8, dtype=np.int32)                     # 37 chains of different cells
+    uid = cc.astype(np.uint64) * np.uint64(1 << 20) + np.uint64(3)
+    nsimu, burn, seed = 3300, 1000, 20201028
+    inputs = _setup(gpu_cells, cc, 101)
+    res = {}
+    for layout in (2, 0):
+        # 1 000-row covariances of ~130 parameters are nearly singular: chol(cov) without the regulariser amplifies the
+        # rounding differences between the kernels' factorisations to 1e-3 in the chain (measured), so: SHORT
+        opts = _lib.default_opts(nsimu=nsimu, burnintime=burn, n_burn=1, store_chain=1, seed=seed, layout=layout, **SHORT)
+        res[layout] = gpu_cells.mcmc_run(opts, cc, *inputs, chain_uid=uid, want_flags=True)
+    assert np.array_equal(res[2]["flags"], res[0]["flags"])
+    assert np.array_equal(res[2]["counters"][:, :8], res[0]["counters"][:, :8])
+    np.testing.assert_allclose(res[2]["mean"], res[0]["mean"], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(res[2]["sig"], res[0]["sig"], rtol=1e-9)
+    for i in (0, 17, 36):
+        c = int(cc[i]); N = int(cells_npz["N"][c]); npar = 7 + N
+        d = _lib.rng_dump(seed, int(uid[i]), npar, 1 + 2 * N, nsimu)
+        st = {k: v[None] for k, v in d.items()}
+        ref = _oracle_chain(orc, cells_npz, c, dict(nsimu=nsimu, burnintime=burn), [x[i:i + 1] for x in inputs], 0, st)
+        assert np.array_equal(res[2]["flags"][i], ref["flags"])
+        np.testing.assert_allclose(res[2]["chain"][i][:, :npar], ref["chain"], rtol=0, atol=1e-7)
+        np.testing.assert_allclose(res[2]["s2chain"][i], ref["s2chain"], rtol=1e-9)
+    th0, q, lo, hi, mu, sg = [x[:3].copy() for x in inputs]
+    lo[:, 40] = -25.0; sg[:, 55] = 10.0                          # breaks the head + block structure
+    for variant in (dict(ntry=1), dict(updatesigma=0), dict()):
+        a = gpu_cells.mcmc_run(_lib.default_opts(nsimu=700, burnintime=300, n_burn=1, seed=5, layout=2, **SHORT, **variant), cc[:3], th0, q, lo, hi, mu, sg, want_flags=True)
+        b = gpu_cells.mcmc_run(_lib.default_opts(nsimu=700, burnintime=300, n_burn=1, seed=5, layout=0, **SHORT, **variant), cc[:3], th0, q, lo, hi, mu, sg, want_flags=True)
+        assert np.array_equal(a["flags"], b["flags"]), variant
+        np.testing.assert_allclose(a["mean"], b["mean"], rtol=0, atol=1e-6)

@@ -8,7 +8,7 @@ CSRC = os.path.join(HERE, "csrc")
 # TC_LIBTCMCMC / TC_NVCC_EXTRA: development builds only (e.g. a -DTC_SUBPROF profiling variant beside the product library)
 LIB = os.environ.get("TC_LIBTCMCMC") or os.path.join(HERE, "libtcmcmc.so")
 SOURCES = ["tc_mcmc.cu"]
-HEADERS = ["tc_device.cuh", os.path.join("..", "..", "include", "tcmcmc.h")]
+HEADERS = ["tc_device.cuh", "tc_warp.cuh", os.path.join("..", "..", "include", "tcmcmc.h")]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

@@ -87,7 +87,7 @@ __device__ __noinline__ void normal_pair(const u32x4 &r, double &z0, double &z1)
 // Box-Muller in single precision (32-bit radius uniform => |z| <= 6.76, 24-bit angle) and widened to FP64;
 // everything downstream (proposal, forward model, SS, acceptance) is FP64.  tc_rng_dump calls this very
 // function, so the parity harness sees bit-identical draws.
-__device__ __noinline__ double4 normal_quad(uint64_t seed, uint64_t uid, uint32_t step, uint32_t q)
+__device__ __forceinline__ double4 normal_quad_inl(uint64_t seed, uint64_t uid, uint32_t step, uint32_t q)
 {
     const u32x4 r = philox4x32_10(q, step, (uint32_t)uid, ((uint32_t)(uid >> 32) << 8) | RK_Z1, (uint32_t)seed, (uint32_t)(seed >> 32));
     const float ua1 = ((float)r.x + 0.5f) * 2.3283064365386963e-10f, ua2 = ((float)r.z + 0.5f) * 2.3283064365386963e-10f;   // (0, 1]
@@ -98,6 +98,8 @@ __device__ __noinline__ double4 normal_quad(uint64_t seed, uint64_t uid, uint32_
     sincospif(ub2, &s2, &c2);
     return make_double4((double)(rad1 * c1), (double)(rad1 * s1), (double)(rad2 * c2), (double)(rad2 * s2));
 }
+// one out-of-line copy for the callers that draw a block at a time (normal_quad_inl: callers that interleave several blocks)
+__device__ __noinline__ double4 normal_quad(uint64_t seed, uint64_t uid, uint32_t step, uint32_t q) { return normal_quad_inl(seed, uid, step, q); }
 
 // chi-square(dof) = 2*Gamma(dof/2) by Marsaglia-Tsang (dof >= 2); attempt t uses slots 2t (the normal: Box-Muller
 // in single precision like the proposal normals, words x, y) and 2t+1 (the 53-bit uniform).

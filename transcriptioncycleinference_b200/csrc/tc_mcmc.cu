@@ -53,6 +53,9 @@ struct DeviceGuard {
 #ifndef SS_MIN_CTAS
 #define SS_MIN_CTAS 4          // 64 registers: 32 warps per SM hide the latency of streaming theta (measured +12 % over 2)
 #endif
+#ifndef TC_WARP_MIN_CHAINS_PER_SM
+#define TC_WARP_MIN_CHAINS_PER_SM 6   // chain-per-warp kernel from this many chains per SM on (tc_mcmc_run)
+#endif
 #define COV_CR 32          // weighted rows of the covariance block staged per pass of the scatter update
 
 // development aid: cycle counts of sub-phases, chain 0 only (build with -DTC_SUBPROF; see scripts/subprof.py)
@@ -175,7 +178,11 @@ struct RunArgs {
     double *sschain;
     // scratch (global)
     double *gR, *gM2, *gRows, *gWts, *gCmean, *gState;
-    double *gW;                                         // big layout: one Cholesky workspace (ldR doubles) per CTA
+    double *gW;                                         // big layout: one Cholesky workspace (ldR doubles) per CTA; warp kernel: per warp
+    // chain-per-warp kernel (tc_warp.cuh): reciprocal prior widths and block-mean accumulators per chain; per warp slot the
+    // increments / scalars of the current batch of steps; the work-item counter
+    double *gPinv, *gMb, *gInc, *gSc;
+    unsigned long long *wq;
     // time slicing
     int seglen;
     int *cstate;
@@ -2007,6 +2014,23 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
     }
 }
 
+// delayed-rejection decision from values (the chain-per-warp kernel keeps the step's scalars in L2)
+__device__ __noinline__ int resolve_dr_v(double q1, double u2, bool o1, double x12, double pr1, double pr2, double ss1, double ss2,
+                                         double ss, double pri, double s2p)
+{
+    double e12, e32, e13;
+    tc_exp3(x12, -0.5 * ((ss1 - ss2) / s2p + pr1 - pr2), -0.5 * ((ss2 - ss) / s2p + pr2 - pri) + q1, e12, e32, e13);
+    const double a12 = o1 ? 0.0 : e12;
+    double a32 = e32;
+    a32 = a32 > 1.0 ? 1.0 : a32;
+    if (!(a32 >= 0.0)) a32 = 0.0;
+    double a13 = e13 * (1.0 - a32) / (1.0 - a12);
+    a13 = a13 > 1.0 ? 1.0 : a13;
+    return ((a13 >= 1.0) || (a13 > u2)) ? 1 : 0;
+}
+
+#include "tc_warp.cuh"
+
 // -------------------------------------------------------------------------- RNG dump / FP64 peak
 __global__ void rng_dump_kernel(unsigned long long seed, unsigned long long uid, int npar, double dof,
                                 int nsimu, double *z1, double *u1, double *z2, double *u2, double *chi2)
@@ -2558,33 +2582,69 @@ int tc_mcmc_run(const tc_cells *c, const tc_mcmc_opts *o, int nchains, const int
             CUDA_TRY(r.buf.alloc(a.gWts, (size_t)nc * o->adaptint));
             CUDA_TRY(r.buf.alloc(a.gCmean, (size_t)nc * ld));
         }
-        int optin = 0;
+        int optin = 0, sms = 0;
         CUDA_TRY(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, r.device));
+        CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, r.device));
         cudaFuncAttributes fa;
         CUDA_TRY(cudaFuncGetAttributes(&fa, dram_kernel));
         const size_t avail = (size_t)optin > fa.sharedSizeBytes ? (size_t)optin - fa.sharedSizeBytes : 0;
         // regular layout when the Cholesky workspace fits in one SM's shared memory, else the big one
         a.big = (sizeof(double) * (size_t)dram_smem_doubles(Nmax, 0) > avail || o->layout == TC_LAYOUT_BIG) ? 1 : 0;
+        // Many chains per SM: one warp per chain (dram_warp_kernel, tc_warp.cuh) instead of one CTA per chain.  The CTA kernel
+        // buys latency with speculation and wins while there are about as many chains as CTA slots (measured crossover on
+        // B200: ~4 chains per SM); beyond that the warp kernel does no wasted evaluations and no CTA barriers.
+        cudaFuncAttributes faw;
+        CUDA_TRY(cudaFuncGetAttributes(&faw, dram_warp_kernel));
+        const size_t smem_w = sizeof(double) * (size_t)wk_region(Nmax) * WK_WARPS;
+        const bool warp_fits = smem_w + faw.sharedSizeBytes <= (size_t)optin && npmax <= 32 * WK_PIT;
+        if (o->layout == TC_LAYOUT_WARP && !warp_fits)
+            return fail(TC_EINVAL, "max(N) = " + std::to_string(Nmax) + " is too large for the chain-per-warp layout");
+        const bool use_warp = o->layout == TC_LAYOUT_WARP || (o->layout == TC_LAYOUT_AUTO && warp_fits && !a.big && nc >= TC_WARP_MIN_CHAINS_PER_SM * sms);
+        // time slices: a multiple of adaptint, ~32 per chain
+        const int unit = o->adaptint > 0 ? o->adaptint : 1;
+        long long sl = ((long long)o->nsimu + 31) / 32;
+        CUDA_TRY(r.buf.alloc(a.gState, (size_t)nc * state_doubles(ld)));
+        CUDA_TRY(r.buf.alloc(a.cstate, nc));
+        CUDA_TRY(cudaMemsetAsync(a.cstate, 0, sizeof(int) * nc, r.st));
+        if (use_warp) {
+            a.big = 0;
+            sl = ((sl + unit - 1) / unit) * unit;
+            a.seglen = (int)std::max<long long>(sl, unit);
+            CUDA_TRY(cudaFuncSetAttribute(dram_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
+            int per_sm = 0;
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dram_warp_kernel, WK_THREADS, smem_w));
+            if (per_sm < 1) return fail(TC_EINVAL, "chain-per-warp kernel does not fit on this device");
+            // persistent grid, one item = WK_WARPS consecutive chains
+            const int grid = std::max(1, std::min(per_sm * sms, (nc + WK_WARPS - 1) / WK_WARPS));
+            const size_t nslots = (size_t)grid * WK_WARPS;
+            const int ldp = wk_ldp(Nmax);
+            CUDA_TRY(r.buf.alloc(a.gPinv, (size_t)nc * ld));
+            CUDA_TRY(r.buf.alloc(a.gInc, nslots * 2 * WK_GEN * ldp));
+            CUDA_TRY(r.buf.alloc(a.gSc, nslots * 8 * WK_GEN));
+            CUDA_TRY(r.buf.alloc(a.wq, 1));
+            CUDA_TRY(cudaMemsetAsync(a.wq, 0, sizeof(unsigned long long), r.st));
+            if (do_cov) {
+                CUDA_TRY(r.buf.alloc(a.gMb, (size_t)nc * ld));
+                CUDA_TRY(r.buf.alloc(a.gW, nslots * ldR));
+            }
+            CUDA_TRY(cudaEventRecord(r.e0, r.st));
+            dram_warp_kernel<<<grid, WK_THREADS, smem_w, r.st>>>(a);
+            CUDA_TRY(cudaGetLastError());
+            CUDA_TRY(cudaEventRecord(r.e1, r.st));
+            continue;
+        }
         a.wsz = dram_wsz(Nmax, a.big);
         const size_t smem = sizeof(double) * (size_t)dram_smem_doubles(Nmax, a.big);
         if (smem > avail || (npmax + 3) / 4 > 255)
             return fail(TC_EINVAL, "max(N) = " + std::to_string(Nmax) + " is too large for the shared-memory layout of this build "
                                    "(one CTA per chain: the cell, the chain state, 8 proposal slots and 8 forward-model scratch areas must fit in one SM)");
         CUDA_TRY(cudaFuncSetAttribute(dram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        // time slices: a multiple of adaptint, ~32 per chain; persistent grid = resident CTA slots
-        {
-            const int unit = o->adaptint > 0 ? o->adaptint : 1;
-            long long sl = ((long long)o->nsimu + 31) / 32;
-            if (nc >= 4 * 296) sl = o->nsimu;                 // many chains per CTA slot: imbalance averages out, no slicing
-            sl = ((sl + unit - 1) / unit) * unit;
-            a.seglen = (int)std::max<long long>(sl, unit);
-            CUDA_TRY(r.buf.alloc(a.gState, (size_t)nc * state_doubles(ld)));
-            CUDA_TRY(r.buf.alloc(a.cstate, nc));
-            CUDA_TRY(cudaMemsetAsync(a.cstate, 0, sizeof(int) * nc, r.st));
-        }
-        int per_sm = 0, sms = 0;
+        // persistent grid = resident CTA slots
+        if (nc >= 4 * 296) sl = o->nsimu;                 // many chains per CTA slot: imbalance averages out, no slicing
+        sl = ((sl + unit - 1) / unit) * unit;
+        a.seglen = (int)std::max<long long>(sl, unit);
+        int per_sm = 0;
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dram_kernel, DRAM_THREADS, smem));
-        CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, r.device));
         if (per_sm < 1) return fail(TC_EINVAL, "sampler kernel does not fit on this device");
         const int grid = std::min(nc, per_sm * sms);           // every CTA resident: slices may wait on each other
         if (a.big && do_cov) CUDA_TRY(r.buf.alloc(a.gW, (size_t)grid * ldR));
