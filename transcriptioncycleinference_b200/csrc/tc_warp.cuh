@@ -118,6 +118,20 @@ __device__ __forceinline__ double wk_ld_keep(const double *p, unsigned long long
     return v;
 }
 
+// FP32 -> FP64 (exact).  WK_INTWIDEN: with integer instructions instead of the conversion unit (normal or zero values only:
+// radius * cos/sin of Box-Muller is never denormal) — a development switch
+__device__ __forceinline__ double wk_widen(float f)
+{
+#ifndef WK_INTWIDEN                                                  // measured: no faster than F2F on B200 (generate 28.2 k vs 27.0 k cycles/step)
+    return (double)f;
+#else
+    const unsigned b = __float_as_uint(f);
+    const unsigned hi = (b & 0x7f800000u) ? ((b & 0x80000000u) | (((b >> 3) & 0x0fffffffu) + 0x38000000u)) : (b & 0x80000000u);
+    return __hiloint2double((int)hi, (int)(b << 29));
+#endif
+}
+__device__ __forceinline__ double wk_widen(double f) { return f; }
+
 template <typename ZT>
 __device__ __forceinline__ void wk_increments(const WkCtx &c, int nnew)
 {
@@ -146,6 +160,7 @@ __device__ __forceinline__ void wk_increments(const WkCtx &c, int nnew)
 #define WK_LOAD_GROUP()                                                                                     \
     {                                                                                                       \
         _Pragma("unroll") for (int u = 0; u < 8; ++u) {                                                     \
+            /* (unconditional loads with a select were measured slower: the padded k-steps become real L2 transactions) */ \
             bvn[u] = (kk_n + u < ks_n && kk_n + u <= bj_n) ? wk_ld_stream(pl_n, pol_r) : 0.0;               \
             pl_n += dpl_n; dpl_n -= 16;                                                                     \
         }                                                                                                   \
@@ -172,7 +187,7 @@ __device__ __forceinline__ void wk_increments(const WkCtx &c, int nnew)
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const int kc = min(4 * (kk + u), ldz - 4);
-                const double a1 = (double)za1p[kc], a2 = (double)za2p[kc];
+                const double a1 = wk_widen(za1p[kc]), a2 = wk_widen(za2p[kc]);
                 dmma_m8n8k4(acc[u & 3][0], acc[u & 3][1], a1, bv[u]);
                 dmma_m8n8k4(acc[u & 3][2], acc[u & 3][3], a2, bv[u]);
             }
