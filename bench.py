@@ -1,24 +1,33 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the transcription-cycle MCMC hot path on B200.
 
-Metric (BASELINE.json): MCMC chain-steps/s (and SS-likelihood evaluations/s) on the 299 cells of
-TestData.mat.  One bench "step" = one complete DRAM fit of the workload (all chains, n_steps MCMC
-steps each) by ONE launch of the device-resident sampler kernel.
+Metric (BASELINE.json): MCMC chain-steps/s (and SS-likelihood evaluations/s) on the 299 cells of TestData.mat.
+One bench "step" = one complete DRAM fit of the workload (all chains, n_steps MCMC steps each): ONE launch of the
+device-resident sampler kernel per GPU.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                  [--workload config2|config3] [--n-steps S] [--n-burn B]
+                  [--workload auto|config2|config3] [--scaling strong|weak] [--n-steps S] [--n-burn B]
 
-  config2 (default, BASELINE configs[1]): 299 cells x 1 chain, n_burn=10000, n_steps=200000.
-  config3: 299 cells x 64 chains (19 136 chains), same steps.
-With N > 1 (torchrun, one rank per GPU) every rank fits its own replica set of chains (weak
-scaling: the path has no data-path collective; Philox streams are keyed by chain identity, never by
-rank).  `value` = chain-steps of all ranks / max-over-ranks time.
+  --gpus 1 (default)  BASELINE configs[1] = "config 2": 299 cells x 1 chain, n_burn=10000, n_steps=200000 (dram_kernel: one
+                      CTA per chain).  Secondary legs in the same line: config 3 on one GPU (the N > 1 workload, and one fit
+                      at n_steps=200000), the raw-chain write-back leg, the batched ssfun kernel, N = 400, CPU baselines.
+  --gpus N > 1        BASELINE configs[2] = "config 3": 299 cells x 64 chains = 19 136 chains, PARTITIONED over the ranks by
+                      cumulative work (transcriptioncycleinference_b200.distributed.fit_sharded around Cells.mcmc_run: the
+                      reference's `parfor (cellNum = 1:N, numParPools)`), summaries all-gathered over NCCL inside the e2e
+                      region: strong scaling.  n_burn=10000, n_steps=20000 (the reference's code defaults,
+                      src/TranscriptionCycleMCMC.m:38-40).  The one-GPU point of this series is `config3` in the --gpus 1
+                      line (or: --gpus 1 --workload config3).  --scaling weak: every rank fits its own replica set instead.
 
---impl reference times the CPU restatement of the reference algorithm (oracle/, a C port: the
-reference is MATLAB + un-vendored mcmcstat and cannot run here) on the box's host cores on a bounded
-sample of the same workload.
+The path has no data-path collective; Philox streams are keyed by chain identity, never by rank or GPU.
+`value` = chain-steps of all ranks / max-over-ranks sampler-kernel time (CUDA events on the launching stream, inside
+libtcmcmc); `e2e` = the same through the public call with HOST buffers, max-over-ranks host time around it.
+
+--impl reference times the CPU restatement of the reference algorithm (oracle/, a C port: the reference is MATLAB +
+un-vendored mcmcstat and cannot run here) on the box's host cores on a bounded sample of the same workload.
 """
 import argparse
+import glob
+import hashlib
 import json
 import os
 import subprocess
@@ -31,11 +40,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 GOLDEN = os.path.join(ROOT, "tests", "golden", "cells.npz")
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE dram_kernel launch of the default workload (config 2, 200 000
-# steps), from an ncu capture of this very command (profiles/traffic_dram_r1v.csv): 109 MB read + 8.0 GB written
-# (distinct chain rows, and the part of the proposal factors / scatter matrices that L2 evicts; 3.8 GB at r1x: the
-# write-back share moves with L2 residency, either way < 0.1 % of HBM bandwidth).  Other workloads: not captured.
-MEASURED_TRAFFIC_BYTES = {("config2", 200000, 10000): 109115648 + 8000692480}
+CSRC = [os.path.join(ROOT, "transcriptioncycleinference_b200", "csrc", f) for f in ("tc_mcmc.cu", "tc_device.cuh", "tc_warp.cuh")]
 METRIC = "mcmc_chain_steps_per_s"
 UNIT = "chain-steps/s"
 
@@ -56,13 +61,50 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="config2", choices=["config2", "config3"])
-    ap.add_argument("--n-steps", type=int, default=200000)
+    ap.add_argument("--workload", default="auto", choices=["auto", "config2", "config3"])
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--n-steps", type=int, default=0, help="0: 200000 for config2, 20000 for config3")
     ap.add_argument("--n-burn", type=int, default=10000)
-    ap.add_argument("--cpu-sample-seconds", type=float, default=15.0)
+    ap.add_argument("--cpu-sample-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-config5", action="store_true", help="skip the secondary N = 400 leg")
-    return ap.parse_args()
+    ap.add_argument("--no-config3", action="store_true", help="skip the secondary config-3 legs of the one-GPU line")
+    ap.add_argument("--no-writeback", action="store_true", help="skip the raw-chain write-back leg")
+    a = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if a.workload == "auto":
+        a.workload = "config2" if world == 1 else "config3"
+    if a.n_steps == 0:
+        a.n_steps = 200000 if a.workload == "config2" else 20000
+    return a
+
+
+def source_hash():
+    h = hashlib.sha256()
+    for f in CSRC:
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def measured_traffic(kernel, workload, n_steps, n_burn):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of `kernel` on this workload, from the newest ncu capture
+    that scripts/profile_gpu.sh committed under profiles/ (traffic_<kernel>_<tag>.json).  A capture made from other kernel
+    sources than the ones benched is not quoted: -> (None, why)."""
+    best = None
+    for f in glob.glob(os.path.join(ROOT, "profiles", "traffic_%s_*.json" % kernel)):
+        try:
+            d = json.load(open(f))
+        except Exception:
+            continue
+        if d.get("workload") == workload and d.get("n_steps") == n_steps and d.get("n_burn") == n_burn:
+            if best is None or d.get("when", "") > best.get("when", ""):
+                best = dict(d, file=os.path.relpath(f, ROOT))
+    if best is None:
+        return None, "no ncu capture of %s for %s (n_steps %d) under profiles/" % (kernel, workload, n_steps)
+    if best.get("source_hash") != source_hash():
+        return None, "%s was captured from other kernel sources (%s) than the ones benched (%s)" % (best["file"], best.get("source_hash"), source_hash())
+    return best, None
 
 
 # ------------------------------------------------------------------------------------- clocks
@@ -105,32 +147,37 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------- CPU baseline
-def cpu_baseline(g, workload, n_burn, target_seconds, rank_offset=0):
-    """Oracle (C port of the reference algorithm, literal m x n forward model + DRAM) on the host
-    cores, OpenMP over chains (the parfor analogue).  Bounded sample: all 299 cells, one chain each,
-    a reduced number of MCMC steps chosen to cost ~target_seconds of CPU time."""
+def host_cores():
+    """all the host cores this process may use (torchrun exports OMP_NUM_THREADS=1: ask the OS, not OpenMP)"""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+class _HostCells:                             # the bits of engine.Cells that setup_cell.chain_inputs needs
+    def __init__(self, g):
+        self.g = g
+        self.ld = 7 + int(g["N"].max())
+
+    def cell(self, c):
+        o = int(self.g["off"][c]); n = int(self.g["N"][c])
+        return self.g["t"][o:o + n], self.g["ms2"][o:o + n], self.g["pp7"][o:o + n]
+
+
+def cpu_baseline(g, target_seconds, with_config1=False):
+    """Oracle (C port of the reference algorithm: literal m x n forward model + DRAM) on the host cores, OpenMP over chains
+    (the parfor analogue).  Bounded sample: all 299 cells, one chain each, a reduced number of MCMC steps chosen to cost
+    ~target_seconds on all cores.  with_config1: also BASELINE configs[0] in full (cell 1, n_burn 10000, n_steps 20000,
+    ONE thread) and the one-thread rate of the 299-cell slice."""
     from oracle import c_oracle, forward_literal
     from transcriptioncycleinference_b200 import setup_cell
 
     cons = c_oracle.Construct.from_dict(forward_literal.CONSTRUCTS["P2P-MS2v5-LacZ-PP7v4"])
-    # all the host cores this process may use (torchrun exports OMP_NUM_THREADS=1: ask the OS, not OpenMP)
-    try:
-        cores = len(os.sched_getaffinity(0))
-    except AttributeError:
-        cores = os.cpu_count() or 1
-
-    class HostCells:                      # the bits of engine.Cells that chain_inputs needs
-        def __init__(s):
-            s.ld = 7 + int(g["N"].max())
-
-        def cell(s, c):
-            o = int(g["off"][c]); n = int(g["N"][c])
-            return g["t"][o:o + n], g["ms2"][o:o + n], g["pp7"][o:o + n]
-
+    cores = host_cores()
     cc = np.arange(299, dtype=np.int32)
-    inputs = setup_cell.chain_inputs(HostCells(), cc, np.random.default_rng(1))
-    # calibrate: 40 steps
-    opts = c_oracle.default_opts(40, 20)
+    inputs = setup_cell.chain_inputs(_HostCells(g), cc, np.random.default_rng(1))
+    opts = c_oracle.default_opts(40, 20)                                 # calibrate: 40 steps
     t0 = time.time()
     c_oracle.run_chains(cons, g, opts, 20, cc, *inputs, seed=1, nthreads=cores)
     per_step = (time.time() - t0) / (299 * 40)
@@ -141,10 +188,27 @@ def cpu_baseline(g, workload, n_burn, target_seconds, rank_offset=0):
     t0 = time.time()
     _, _, _, cnt = c_oracle.run_chains(cons, g, opts, burn, cc, *inputs, seed=2, nthreads=cores)
     dt = time.time() - t0
-    return dict(value=299 * nsimu / dt, unit=UNIT, cores=cores, kind="port",
-                sample="299 cells x 1 chain x %d MCMC steps (burnintime %d), literal m x n forward model, "
-                       "C port of the reference algorithm (oracle/tc_oracle.c), OpenMP over chains" % (nsimu, burn),
-                seconds=dt, ss_evals_per_s=float(cnt[:, 0].sum()) / dt)
+    out = dict(value=299 * nsimu / dt, unit=UNIT, cores=cores, kind="port",
+               sample="299 cells x 1 chain x %d MCMC steps (burnintime %d), literal m x n forward model, "
+                      "C port of the reference algorithm (oracle/tc_oracle.c), OpenMP over chains, %d threads" % (nsimu, burn, cores),
+               seconds=dt, ss_evals_per_s=float(cnt[:, 0].sum()) / dt)
+    if with_config1:
+        o1 = c_oracle.default_opts(20000, 10000)
+        one = [x[:1] for x in inputs]
+        t0 = time.time()
+        _, _, _, c1 = c_oracle.run_chains(cons, g, o1, 10000, cc[:1], *one, seed=3, nthreads=1)
+        d1 = time.time() - t0
+        out["config1"] = dict(value=20000 / d1, unit=UNIT, cores=1, seconds=d1, ss_evals_per_s=float(c1[:, 0].sum()) / d1,
+                              sample="BASELINE configs[0] in full: TestData cell 1 (N = %d), n_burn 10000, n_steps 20000, one chain, one thread" % int(g["N"][0]))
+        ns1 = max(100, (int(nsimu / max(cores, 1) * 1.5) // 100) * 100)
+        o2 = c_oracle.default_opts(ns1, ns1 // 2)
+        sub = np.arange(0, 299, 13, dtype=np.int32)                      # 23 cells spread over the six movies
+        t0 = time.time()
+        c_oracle.run_chains(cons, g, o2, ns1 // 2, sub, *[x[sub] for x in inputs], seed=4, nthreads=1)
+        d2 = time.time() - t0
+        out["one_thread"] = dict(value=sub.size * ns1 / d2, unit=UNIT, cores=1, seconds=d2,
+                                 sample="%d of the 299 cells x %d MCMC steps (burnintime %d), one thread" % (sub.size, ns1, ns1 // 2))
+    return out
 
 
 def run_reference(args, g):
@@ -154,15 +218,17 @@ def run_reference(args, g):
     vals = []
     last = None
     for i in range(args.warmup + args.steps):
-        last = cpu_baseline(g, args.workload, args.n_burn, max(2.0, args.cpu_sample_seconds / 3))
+        last = cpu_baseline(g, max(2.0, args.cpu_sample_seconds / 3))
         if i >= args.warmup:
             vals.append(last)
     v = float(np.mean([x["value"] for x in vals]))
     line = dict(metric=METRIC, value=v, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=float(np.mean([x["seconds"] for x in vals]) * 1e3), higher_is_better=True,
-                scaling="weak", vs_baseline=None, dtype="f64", data="TestData.mat cells (tests/golden/cells.npz), synthetic x0",
+                scaling="strong" if (args.gpus > 1 and args.scaling == "strong") else "weak", vs_baseline=None, dtype="f64",
+                data="TestData.mat cells (tests/golden/cells.npz), synthetic x0",
                 impl="reference",
-                config=dict(workload=args.workload + " (bounded sample)", cells=299, chains_per_cell=1),
+                config=dict(workload=args.workload + " (bounded sample: one chain per cell, reduced n_steps; chain-steps/s does not depend on the chain count on a CPU)",
+                            cells=299, chains_per_cell=1),
                 cpu_baseline=dict(value=v, unit=UNIT, cores=last["cores"], kind=last["kind"], sample=last["sample"]),
                 e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 ss_evals_per_s=float(np.mean([x["ss_evals_per_s"] for x in vals])), gpu_launches=0)
@@ -170,10 +236,23 @@ def run_reference(args, g):
 
 
 # ----------------------------------------------------------------------------------- GPU arm
+def algorithmic_flops(g, cc, cnt, n_steps, n_burn, _lib):
+    """SS evaluations x W_flop(N) + full-R proposal mat-vecs after burn-in (2 proposals: 2 npar^2/2 FMA) +
+    covariance block updates (npar^2/2 FMA per row) + Cholesky (npar^3/6 FMA) per adaptation."""
+    Ns = g["N"][cc].astype(np.float64)
+    npar = Ns + 7
+    ss_evals = cnt[:, _lib.CNT_SS_EVALS].astype(np.float64)
+    post = max(0, n_steps - n_burn)
+    flops_ss = float(np.sum(ss_evals * w_flop(Ns)))
+    flops_dram = float(np.sum(2.0 * post * npar ** 2 * 2 / 2 + n_steps * npar ** 2 + cnt[:, _lib.CNT_ADAPTATIONS] * npar ** 3 / 3))
+    ops_ss = float(np.sum(ss_evals * w_op(Ns)))
+    return flops_ss, flops_dram, ops_ss
+
+
 def run_ours(args, g):
     import torch
     import torch.distributed as dist
-    from transcriptioncycleinference_b200 import _lib, setup_cell
+    from transcriptioncycleinference_b200 import _lib, distributed, setup_cell
     from transcriptioncycleinference_b200.engine import Cells
 
     rank = int(os.environ.get("RANK", "0"))
@@ -184,7 +263,6 @@ def run_ours(args, g):
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = "WARN"            # keep NCCL's version banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
@@ -193,97 +271,192 @@ def run_ours(args, g):
         torch.cuda.synchronize()
 
     cells = Cells.from_packed(g["N"], g["off"], g["t"], g["ms2"], g["pp7"], devices=(local,))
+    ld = cells.ld
     per_cell = 1 if args.workload == "config2" else 64
+    strong = world > 1 and args.scaling == "strong"
     cc = np.repeat(np.arange(299, dtype=np.int32), per_cell)
-    # chain identity: (cell, chain replica) — rank r owns replicas [r*per_cell, (r+1)*per_cell)
-    rep = np.tile(np.arange(per_cell, dtype=np.uint64), 299) + np.uint64(rank * per_cell)
+    # chain identity = (cell, chain replica); weak scaling: rank r owns replicas [r per_cell, (r+1) per_cell)
+    rep = np.tile(np.arange(per_cell, dtype=np.uint64), 299) + np.uint64(0 if strong else rank * per_cell)
     uid = cc.astype(np.uint64) * np.uint64(1 << 20) + rep
-    inputs = setup_cell.chain_inputs(cells, cc, np.random.default_rng(1000 + rank))
+    inputs = setup_cell.chain_inputs(cells, cc, np.random.default_rng(1000 + (0 if strong else rank)))
     opts = _lib.default_opts(nsimu=args.n_steps, burnintime=args.n_burn, n_burn=args.n_burn, store_chain=0,
                              seed=20201028, ngpus=1)
     opts.devices[0] = local
-    h2d = sum(x.nbytes for x in inputs) + cc.nbytes + uid.nbytes
-    ld = cells.ld
-    d2h = cc.size * (2 * ld + 2) * 8 + cc.size * _lib.NCOUNTERS * 8
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
-
     peak_dfma, peak_clk = _lib.measure_fp64_peak(local)
+    schema = distributed.summary_schema(ld, _lib.NCOUNTERS)
+
+    def run_local(c, arrs, u):
+        return cells.mcmc_run(opts, c, *arrs, chain_uid=u)               # host buffers in, summaries out
 
     def one_fit():
         flush.zero_()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        out = cells.mcmc_run(opts, cc, *inputs, chain_uid=uid)          # host buffers in, summaries out
-        return time.perf_counter() - t0, out
+        if strong:
+            out = distributed.fit_sharded(run_local, cc, g["N"], list(inputs), uid, rank, world, schema=schema)
+            ks = out["local"].get("kernel_seconds", 0.0)
+        else:
+            out = run_local(cc, inputs, uid)
+            ks = out["kernel_seconds"]
+        return time.perf_counter() - t0, ks, out
 
     for _ in range(args.warmup):
         one_fit()
     barrier()
-    kernel_s, e2e_s, outs = [], [], []
+    kernel_s, e2e_s, out = [], [], None
     sampler = ClockSampler(local)
     with sampler:
         for _ in range(args.steps):
-            dt, out = one_fit()
-            e2e_s.append(dt); kernel_s.append(out["kernel_seconds"]); outs.append(out)
+            dt, ks, out = one_fit()
+            e2e_s.append(dt); kernel_s.append(ks)
     barrier()
     tk, te = float(np.sum(kernel_s)), float(np.sum(e2e_s))
     if world > 1:
         tt = torch.tensor([tk, te], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         tk, te = float(tt[0]), float(tt[1])
-    nsteps_total = world * cc.size * args.n_steps * args.steps
-    cnt = outs[-1]["counters"]
-    Ns = g["N"][cc].astype(np.float64)
-    npar = Ns + 7
+    cnt = out["counters"]                                               # strong: gathered (all chains); else this rank's
+    chains_total = cc.size if strong else world * cc.size
+    nsteps_total = chains_total * args.n_steps * args.steps
+    flops_ss, flops_dram, ops_ss = algorithmic_flops(g, cc, cnt, args.n_steps, args.n_burn, _lib)
+    if not strong:
+        flops_ss, flops_dram, ops_ss = world * flops_ss, world * flops_dram, world * ops_ss
     ss_evals = cnt[:, _lib.CNT_SS_EVALS].astype(np.float64)
-    # algorithmic flops of one fit: SS evaluations + full-R proposal mat-vecs after the first
-    # adaptation (2 proposals share one pass: 2 * npar^2/2 FMA) + covariance block updates
-    # (npar^2/2 FMA per row) + Cholesky (npar^3/6 FMA) per adaptation     [SURVEY.md 8d]
-    post = max(0, args.n_steps - args.n_burn)
-    flops_ss = float(np.sum(ss_evals * w_flop(Ns)))
-    flops_dram = float(np.sum(2.0 * post * npar ** 2 * 2 / 2 + args.n_steps * npar ** 2 + cnt[:, _lib.CNT_ADAPTATIONS] * npar ** 3 / 3))
-    ops_ss = float(np.sum(ss_evals * w_op(Ns)))
     t_fit = tk / args.steps
     achieved = (flops_ss + flops_dram) / t_fit / 1e12
-    peak_tf = 2 * peak_dfma / 1e12
+    peak_tf = 2 * peak_dfma / 1e12 * world
+    if strong:
+        parts = out["partition"]
+        n_loc = [b - a for a, b in parts]
+        h2d = int(sum(x.nbytes for x in inputs) / cc.size * max(n_loc) + max(n_loc) * 12)
+        d2h = int(max(n_loc) * ((2 * ld + 2) * 8 + _lib.NCOUNTERS * 8))
+        gather = int(cc.size * ((2 * ld + 2) * 8 + _lib.NCOUNTERS * 8))
+    else:
+        h2d = sum(x.nbytes for x in inputs) + cc.nbytes + uid.nbytes
+        d2h = cc.size * (2 * ld + 2) * 8 + cc.size * _lib.NCOUNTERS * 8
+        gather = 0
+    chains_per_gpu = int(np.ceil(cc.size / world)) if strong else int(cc.size)
+    sms = _lib.device_info(local)["sm_count"]
+    kernel = "dram_warp_kernel" if chains_per_gpu >= 6 * sms else "dram_kernel"
+    traffic, why = measured_traffic(kernel, args.workload, args.n_steps, args.n_burn) if world == 1 else (None, "captured on one GPU only")
     line = dict(
         metric=METRIC, value=nsteps_total / tk, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
-        ms_per_step=tk / args.steps * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
+        ms_per_step=tk / args.steps * 1e3, higher_is_better=True, scaling="strong" if strong else "weak", vs_baseline=None,
+        dtype="f64",
         data="TestData.mat cells (tests/golden/cells.npz: the reference's 299-cell dataset), synthetic x0",
-        config=dict(workload="%s: 299 cells x %d chain(s)/cell per GPU, n_burn=%d, n_steps=%d, adaptint=100, DRAM, "
-                             "construct P2P-MS2v5-LacZ-PP7v4" % (args.workload, per_cell, args.n_burn, args.n_steps),
-                    chains_per_gpu=int(cc.size), l2="flushed between timed fits (256 MiB write)",
-                    sharding="chains replicated per rank, no collective in the data path"),
-        e2e=dict(value=nsteps_total / te, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h)),
-        gpu_launches=args.steps,
-        ss_evals_per_s=float(world * ss_evals.sum() * args.steps / tk),
+        config=dict(workload="%s: 299 cells x %d chain(s)/cell = %d chains %s, n_burn=%d, n_steps=%d, adaptint=100, DRAM, "
+                             "construct P2P-MS2v5-LacZ-PP7v4" % (args.workload, per_cell, cc.size,
+                                                                 "partitioned over %d GPU(s)" % world if strong else "per GPU",
+                                                                 args.n_burn, args.n_steps),
+                    chains_per_gpu=chains_per_gpu, kernel=kernel, l2="flushed between timed fits (256 MiB write)",
+                    sharding=("chains partitioned over the ranks by cumulative N^2 + npar^2 (distributed.fit_sharded around "
+                              "Cells.mcmc_run); no collective in the data path; summaries + counters all-gathered over NCCL "
+                              "(%d bytes per fit) inside the e2e region" % gather) if strong else
+                             "chains replicated per rank, no collective in the data path",
+                    one_gpu_point="python bench.py --gpus 1: key config3.value (same workload, one GPU)" if strong else None),
+        e2e=dict(value=nsteps_total / te, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
+                 gather_bytes_per_step=gather),
+        gpu_launches=args.steps * world,
+        ss_evals_per_s=float((1 if strong else world) * ss_evals.sum() * args.steps / tk),
         ss_evals_per_chain_step=float(ss_evals.sum() / (cc.size * args.n_steps)),
         accept_rate=float((cnt[:, _lib.CNT_ACC_STAGE1] + cnt[:, _lib.CNT_ACC_STAGE2]).sum() / (cc.size * args.n_steps)),
-        roofline=dict(bound="fp64_pipe", kernel="dram_kernel", achieved=achieved, peak=peak_tf, unit="TFLOP/s",
-                      frac=achieved / peak_tf, traffic=MEASURED_TRAFFIC_BYTES.get((args.workload, args.n_steps, args.n_burn)),
-                      traffic_unit="bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/traffic_dram_r1v.csv); "
-                                   "the kernel is bound by FP64-pipe latency, not HBM: this is 0.1 % of HBM bandwidth",
-                      peak_source="measured DFMA micro-benchmark on this GPU (tc_measure_fp64_peak), SM clock %.0f MHz; "
-                                  "MEASURED_PEAKS.json has no FP64 entry" % peak_clk,
-                      algorithmic_flops_per_launch=flops_ss + flops_dram, flops_ss=flops_ss, flops_dram=flops_dram,
-                      frac_ops_ss_only=ops_ss / t_fit / peak_dfma,
-                      hbm_row_writeback_gbs=float(np.sum(npar) * args.n_steps * 8 / t_fit / 1e9)),
+        roofline=dict(bound="fp64_pipe", kernel=kernel, achieved=achieved, peak=peak_tf, unit="TFLOP/s",
+                      frac=achieved / peak_tf,
+                      traffic=(traffic["bytes_read"] + traffic["bytes_write"]) if traffic else None,
+                      traffic_source=(dict(file=traffic["file"], bytes_read=traffic["bytes_read"], bytes_write=traffic["bytes_write"],
+                                           when=traffic.get("when"), source_hash=traffic.get("source_hash"))
+                                      if traffic else why),
+                      traffic_unit="bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum); the kernel is bound by "
+                                   "FP64-pipe latency, not HBM",
+                      peak_source="measured DFMA micro-benchmark on this GPU (tc_measure_fp64_peak) x %d GPU(s), SM clock %.0f MHz; "
+                                  "MEASURED_PEAKS.json has no FP64 entry" % (world, peak_clk),
+                      algorithmic_flops_per_launch=(flops_ss + flops_dram) / world, flops_ss=flops_ss, flops_dram=flops_dram,
+                      frac_ops_ss_only=ops_ss / t_fit / (peak_dfma * world)),
         clocks=sampler.summary(),
     )
-    # secondary: the batched SS kernel alone (device-resident inputs), the compute-bound leg
-    if rank == 0:
-        line["ss_kernel"] = ss_kernel_leg(cells, g, peak_dfma, torch)
-        if not args.no_config5:
+    if rank == 0 and world == 1:
+        # secondary legs of the one-GPU line (each guarded: a secondary leg must not cost the headline)
+        def leg(name, fn):
             try:
-                line["config5_scale"] = config5_leg(local)
-            except Exception as e:                       # a secondary leg must not cost the headline line
-                line["config5_scale"] = dict(error=repr(e))
+                line[name] = fn()
+            except Exception as e:
+                line[name] = dict(error=repr(e))
+        leg("ss_kernel", lambda: ss_kernel_leg(cells, g, peak_dfma, torch))
+        if args.workload == "config2" and not args.no_config3:
+            leg("config3", lambda: config3_leg(cells, g, local, peak_dfma, flush, torch, 20000, args.n_burn, fits=2))
+            leg("config3_n200000", lambda: config3_leg(cells, g, local, peak_dfma, flush, torch, 200000, args.n_burn, fits=1))
+        if not args.no_writeback:
+            leg("chain_writeback", lambda: writeback_leg(cells, g, local, flush, torch))
+        if not args.no_config5:
+            leg("config5_scale", lambda: config5_leg(local))
         if not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(g, args.workload, args.n_burn, args.cpu_sample_seconds)
+            leg("cpu_baseline", lambda: cpu_baseline(g, args.cpu_sample_seconds, with_config1=True))
+    if rank == 0:
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def config3_leg(cells, g, device, peak_dfma, flush, torch, n_steps, n_burn, fits):
+    """BASELINE config 3 on ONE GPU: 299 cells x 64 chains = 19 136 chains (dram_warp_kernel: one warp per chain) — the
+    one-GPU point of the partitioned --gpus N series (n_steps 20 000), and one fit at n_steps 200 000."""
+    from transcriptioncycleinference_b200 import _lib, setup_cell
+    cc = np.repeat(np.arange(299, dtype=np.int32), 64)
+    uid = cc.astype(np.uint64) * np.uint64(1 << 20) + np.tile(np.arange(64, dtype=np.uint64), 299)
+    inputs = setup_cell.chain_inputs(cells, cc, np.random.default_rng(1000))
+    opts = _lib.default_opts(nsimu=n_steps, burnintime=n_burn, n_burn=n_burn, store_chain=0, seed=20201028, ngpus=1)
+    opts.devices[0] = device
+    warm = _lib.default_opts(nsimu=min(n_steps, 2000), burnintime=1000, n_burn=1000, store_chain=0, seed=1, ngpus=1)
+    warm.devices[0] = device
+    cells.mcmc_run(warm, cc, *inputs, chain_uid=uid)                     # pools, code, clocks
+    ks, es, out = [], [], None
+    for _ in range(fits):
+        flush.zero_(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = cells.mcmc_run(opts, cc, *inputs, chain_uid=uid)
+        es.append(time.perf_counter() - t0); ks.append(out["kernel_seconds"])
+    t, te = float(np.mean(ks)), float(np.mean(es))
+    flops_ss, flops_dram, ops_ss = algorithmic_flops(g, cc, out["counters"], n_steps, n_burn, _lib)
+    return dict(workload="config3: 299 cells x 64 chains = 19136 chains on one GPU, n_burn=%d, n_steps=%d" % (n_burn, n_steps),
+                kernel="dram_warp_kernel", value=cc.size * n_steps / t, unit=UNIT, e2e_value=cc.size * n_steps / te, ms_per_fit=t * 1e3, fits=fits,
+                ss_evals_per_s=float(out["counters"][:, _lib.CNT_SS_EVALS].sum()) / t,
+                roofline_frac=(flops_ss + flops_dram) / t / (2 * peak_dfma), frac_ops_ss_only=ops_ss / t / peak_dfma)
+
+
+def writeback_leg(cells, g, device, flush, torch, n_steps=20000, n_burn=10000):
+    """The reference's default product is the raw chain (src/TranscriptionCycleMCMC.m:276-283,315-323,377-378): config 2 at the
+    reference's code defaults (n_burn 10000, n_steps 20000) with store_chain = 1 — 299 x 10 001 rows x ld doubles + s2chain —
+    against the same fit with summaries only.  Destinations are page-locked host buffers allocated once (tc_host_alloc)."""
+    from transcriptioncycleinference_b200 import _lib, setup_cell
+    cc = np.arange(299, dtype=np.int32)
+    uid = cc.astype(np.uint64) * np.uint64(1 << 20)
+    inputs = setup_cell.chain_inputs(cells, cc, np.random.default_rng(1000))
+    ld = cells.ld
+    res = {}
+    nstore = n_steps - n_burn + 1
+    chain = _lib.pinned_empty((cc.size, nstore, ld)); s2 = _lib.pinned_empty((cc.size, n_steps))
+    for store in (0, 1):
+        opts = _lib.default_opts(nsimu=n_steps, burnintime=n_burn, n_burn=n_burn, store_chain=store, seed=20201028, ngpus=1)
+        opts.devices[0] = device
+        ks, es, ds = [], [], []
+        for it in range(4):
+            flush.zero_(); torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            out = cells.mcmc_run(opts, cc, *inputs, chain_uid=uid, chain_out=chain if store else None, s2chain_out=s2 if store else None)
+            if it >= 1:
+                es.append(time.perf_counter() - t0); ks.append(out["kernel_seconds"]); ds.append(out["drain_seconds"])
+        res[store] = (float(np.mean(ks)), float(np.mean(es)), float(np.mean(ds)))
+    nbytes = chain.nbytes + s2.nbytes
+    rows_bytes = float(np.sum((g["N"][cc] + 7 + 1) * 8.0) * nstore)     # algorithmic: (npar + 1) doubles per stored row
+    (k0, e0, d0), (k1, e1, d1) = res[0], res[1]
+    return dict(workload="config2, n_burn=%d, n_steps=%d, store_chain=1: %d rows x %d chains" % (n_burn, n_steps, nstore, cc.size),
+                chain_bytes=int(nbytes), kernel_ms_summaries_only=k0 * 1e3, kernel_ms_with_chains=k1 * 1e3, kernel_slowdown=k1 / k0,
+                hbm_row_write_gbs=rows_bytes / k1 / 1e9,
+                hbm_note="algorithmic bytes of the stored rows / kernel time; ncu's dram__bytes_write.sum.per_second for this launch is in profiles/ (writeback capture)",
+                d2h_seconds=d1, d2h_gbs=nbytes / d1 / 1e9, e2e_ms_summaries_only=e0 * 1e3, e2e_ms_with_chains=e1 * 1e3,
+                e2e_slowdown=e1 / e0, chain_steps_per_s_e2e_with_chains=cc.size * n_steps / e1)
 
 
 def config5_leg(device, ncells=1184, N=400, nsteps=2000):

@@ -194,6 +194,15 @@ int tc_mcmc_run(const tc_cells *cells, const tc_mcmc_opts *opts, int nchains,
 /* Seconds spent in the sampler kernel(s) of the last tc_mcmc_run on this thread, measured with CUDA
  * events on the launching stream (max over devices). */
 double tc_last_kernel_seconds(void);
+/* Host seconds the last tc_mcmc_run on this thread spent draining its outputs (device -> host copies of summaries, counters
+ * and, with store_chain, the raw chains) after the kernels had finished. */
+double tc_last_drain_seconds(void);
+
+/* Page-locked host memory for large outputs (the raw chains of src/TranscriptionCycleMCMC.m:276-283,315-323 are GBs): a
+ * chain / s2chain buffer allocated here goes device -> host by DMA at PCIe speed and, with several GPUs, in parallel;
+ * ordinary (pageable) buffers are accepted everywhere too, only slower.  Free with tc_host_free. */
+int tc_host_alloc(size_t bytes, void **out);
+void tc_host_free(void *p);
 
 /* The randomness tc_mcmc_run would draw for (seed, chain_uid) at steps [0, nsimu): lets the CPU
  * oracle consume the device's Philox streams.  z1,z2 [nsimu x npar]; u1,u2,chi2 [nsimu]. */

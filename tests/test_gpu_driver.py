@@ -118,3 +118,25 @@ def test_multiple_chains_per_cell_pool_and_diagnose(tmp_path, cells_npz):
         W = v.var(axis=1, ddof=1).mean(); B = 401 * v.mean(axis=1).var(ddof=1)
         assert abs(dg["Rhat"][0, 0] - np.sqrt((400 / 401 * W + B / 401) / W)) < 1e-8
         assert _f(dg["Rhat_max"]) >= 1.0 - 1e-12
+
+
+def test_two_gpus_same_result_as_one(cells_npz):
+    """numParPools = 2 -> two GPUs inside one process (tc_mcmc_opts.ngpus = 2: chains partitioned by cumulative N^2, one
+    stream and one drain thread per device): bit-identical to the one-GPU fit, raw chains included (Philox is keyed by chain
+    identity, never by device).  Skipped on a box with fewer than two devices."""
+    from transcriptioncycleinference_b200 import _lib, setup_cell
+    from transcriptioncycleinference_b200.engine import Cells
+    if _lib.device_count() < 2:
+        pytest.skip("needs 2 CUDA devices")
+    g = cells_npz
+    cc = np.arange(0, 299, 7, dtype=np.int32)
+    res = []
+    for devs in ((0,), (0, 1)):
+        cells = Cells.from_packed(g["N"], g["off"], g["t"], g["ms2"], g["pp7"], devices=devs)
+        inputs = setup_cell.chain_inputs(cells, cc, np.random.default_rng(3))
+        opts = _lib.default_opts(nsimu=1200, burnintime=400, n_burn=400, store_chain=1, ngpus=len(devs), seed=11)
+        res.append(cells.mcmc_run(opts, cc, *inputs, chain_uid=cc.astype(np.uint64)))
+        cells.close()
+    for k in ("mean", "std", "sig", "chain", "s2chain"):
+        assert np.array_equal(res[0][k], res[1][k]), k
+    assert np.array_equal(res[0]["counters"][:, :8], res[1]["counters"][:, :8])

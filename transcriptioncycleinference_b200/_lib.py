@@ -23,7 +23,7 @@ EXPORTS = [
     "tc_version", "tc_last_error", "tc_device_count", "tc_device_info_get", "tc_opts_default",
     "tc_cells_create", "tc_cells_destroy", "tc_cells_t_interp", "tc_ss_batch", "tc_ss_batch_device",
     "tc_forward", "tc_mcmc_run", "tc_last_kernel_seconds", "tc_rng_dump", "tc_measure_fp64_peak",
-    "tc_debug_subprof",
+    "tc_debug_subprof", "tc_last_drain_seconds", "tc_host_alloc", "tc_host_free",
 ]
 
 
@@ -88,6 +88,10 @@ def load():
     L.tc_version.restype = C.c_int
     L.tc_last_error.restype = C.c_char_p
     L.tc_last_kernel_seconds.restype = C.c_double
+    L.tc_last_drain_seconds.restype = C.c_double
+    L.tc_host_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
+    L.tc_host_free.argtypes = [C.c_void_p]
+    L.tc_host_free.restype = None
     L.tc_device_count.argtypes = [C.POINTER(C.c_int)]
     L.tc_device_info_get.argtypes = [C.c_int, C.POINTER(DeviceInfo)]
     L.tc_opts_default.argtypes = [C.POINTER(McmcOpts)]
@@ -126,6 +130,33 @@ def f64(a):
 
 def i32(a):
     return np.ascontiguousarray(a, dtype=np.int32)
+
+
+class _Pinned:
+    """Owner of one tc_host_alloc block (freed when the last array viewing it goes away)."""
+
+    def __init__(self, nbytes):
+        self.ptr = C.c_void_p(None)
+        check(load().tc_host_alloc(nbytes, C.byref(self.ptr)))
+        self.nbytes = nbytes
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                load().tc_host_free(self.ptr)
+                self.ptr = C.c_void_p(None)
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype=np.float64):
+    """ndarray in page-locked host memory (tc_host_alloc): the destination of large device -> host copies (raw chains)."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    own = _Pinned(max(n, 1))
+    buf = (C.c_char * max(n, 1)).from_address(own.ptr.value)
+    buf._owner = own                                            # keeps the block alive as long as the buffer is referenced
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
 
 
 def device_count():

@@ -9,6 +9,7 @@
 //   rng_dump_kernel   the Philox streams of a chain, for the parity harness
 //   dfma_peak_kernel  FP64 pipe micro-benchmark (roofline denominator)
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -24,6 +25,7 @@ using namespace tc;
 // ------------------------------------------------------------------------------------ utilities
 static thread_local std::string g_err;
 static thread_local double g_last_kernel_s = 0.0;
+static thread_local double g_last_drain_s = 0.0;
 
 static int fail(int code, const std::string &msg)
 {
@@ -2144,6 +2146,22 @@ extern "C" {
 int tc_version(void) { return TC_VERSION; }
 const char *tc_last_error(void) { return g_err.c_str(); }
 double tc_last_kernel_seconds(void) { return g_last_kernel_s; }
+double tc_last_drain_seconds(void) { return g_last_drain_s; }
+
+int tc_host_alloc(size_t bytes, void **out)
+{
+    if (!out) return fail(TC_EINVAL, "out is NULL");
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n < 1) return fail(TC_ENODEV, "no CUDA device available (libtcmcmc has no CPU fallback)");
+    CUDA_TRY(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
+    return TC_OK;
+}
+
+void tc_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
 
 int tc_device_count(int *count)
 {
@@ -2563,6 +2581,7 @@ int tc_mcmc_run(const tc_cells *c, const tc_mcmc_opts *o, int nchains, const int
             CUDA_TRY(r.buf.alloc(a.chain, (size_t)nc * nstore * ld));
             CUDA_TRY(cudaMemsetAsync(a.chain, 0, (size_t)nc * nstore * ld * 8, r.st));
             CUDA_TRY(r.buf.alloc(a.s2chain, (size_t)nc * o->nsimu));
+            CUDA_TRY(cudaMemsetAsync(a.s2chain, 0, (size_t)nc * o->nsimu * 8, r.st));
         }
         if (o->replay) {
             const size_t nz = (size_t)nc * o->nsimu * ld, nu = (size_t)nc * o->nsimu;
@@ -2655,6 +2674,7 @@ int tc_mcmc_run(const tc_cells *c, const tc_mcmc_opts *o, int nchains, const int
     }
     // Drain: every device's outputs go back on its own stream; with several devices one host thread per device, so the
     // device -> host copies (raw chains: GBs) of the 8 GPUs overlap instead of queueing behind each other.
+    const auto t_drain0 = std::chrono::steady_clock::now();
     std::vector<int64_t> cnt_tmp;
     if (!counters) { cnt_tmp.assign((size_t)nchains * TC_NCOUNTERS, 0); counters = cnt_tmp.data(); }   // TC_CNT_STATUS is always checked
     std::vector<double> ksec(runs.size(), 0.0);
@@ -2696,6 +2716,8 @@ int tc_mcmc_run(const tc_cells *c, const tc_mcmc_opts *o, int nchains, const int
     double kmax = 0.0;
     for (double k : ksec) kmax = std::max(kmax, k);
     g_last_kernel_s = kmax;
+    // host time from the last launch to the last byte on the host, minus the kernel: the device -> host copies
+    g_last_drain_s = std::max(0.0, std::chrono::duration<double>(std::chrono::steady_clock::now() - t_drain0).count() - kmax);
     for (int i = 0; i < nchains; ++i)
         if (counters[(size_t)i * TC_NCOUNTERS + TC_CNT_STATUS] != 0)
             return fail(TC_ESTATE, "ss(theta0) is not finite for chain " + std::to_string(i));

@@ -29,20 +29,57 @@ def chain_work(N_of_chain):
     return N * N + (N + 7) ** 2
 
 
-def fit_sharded(run_local, chain_cell, N_of_cell, arrays, chain_uid, rank, world, group=None):
-    """Run `run_local(chain_cell_slice, arrays_slice, uid_slice) -> dict of per-chain arrays` on this
-    rank's contiguous slice and all-gather the per-chain outputs (small: summaries and counters) so
-    that every rank ends up with the full result in the original chain order."""
-    import torch.distributed as dist
+SUMMARY_SCHEMA = None   # filled by summary_schema(ld)
+
+
+def summary_schema(ld, ncounters=16):
+    """Per-chain outputs of Cells.mcmc_run that the gather assembles: name -> (trailing shape, dtype)."""
+    return {"mean": ((ld,), np.float64), "std": ((ld,), np.float64), "sig": ((2,), np.float64),
+            "counters": ((ncounters,), np.int64)}
+
+
+def fit_sharded(run_local, chain_cell, N_of_cell, arrays, chain_uid, rank, world, group=None, schema=None):
+    """Run `run_local(chain_cell_slice, arrays_slice, uid_slice) -> dict of per-chain arrays` on this rank's contiguous
+    slice of the chains (partition by cumulative work, `parfor` over `numParPools` workers) and gather the per-chain
+    outputs so that every rank ends up with the full result in the original chain order.
+
+    The gather is the path's only communication: ONE all_gather per dtype of the packed summaries (float64: mean | std |
+    sig, int64: counters), padded to the largest slice — tensors on the GPU over NCCL (NVLink/NVSwitch), on the host over
+    gloo.  `schema` (name -> (trailing shape, dtype), e.g. summary_schema(ld)) names the arrays to gather; by default every
+    array of the local result whose first dimension is the slice length.  Other entries of the local dict stay local
+    (returned under "local")."""
     parts = partition(chain_work(np.asarray(N_of_cell)[chain_cell]), world)
     s, e = parts[rank]
-    local = run_local(chain_cell[s:e], [a[s:e] for a in arrays], chain_uid[s:e]) if e > s else {}
+    n_loc = e - s
+    local = run_local(chain_cell[s:e], [a[s:e] for a in arrays], chain_uid[s:e]) if n_loc > 0 else {}
     if world == 1:
         return local
-    gathered = [None] * world
-    dist.all_gather_object(gathered, {k: np.asarray(v) for k, v in local.items()}, group=group)
-    keys = [k for g in gathered for k in g.keys()]
+    import torch
+    import torch.distributed as dist
+    if schema is None:
+        schema = {k: (tuple(np.asarray(v).shape[1:]), np.asarray(v).dtype) for k, v in local.items()
+                  if isinstance(v, np.ndarray) and v.ndim >= 1 and v.shape[0] == n_loc}
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    n_max = max(b - a for a, b in parts)
     out = {}
-    for k in dict.fromkeys(keys):
-        out[k] = np.concatenate([g[k] for g in gathered if k in g], axis=0)
+    for dt in sorted({np.dtype(d).str for _, d in schema.values()}):
+        keys = [k for k, (_, d) in schema.items() if np.dtype(d).str == dt]
+        widths = [int(np.prod(schema[k][0])) if schema[k][0] else 1 for k in keys]
+        pack = np.zeros((n_max, sum(widths)), dtype=np.dtype(dt))
+        o = 0
+        for k, w in zip(keys, widths):
+            if n_loc > 0:
+                pack[:n_loc, o:o + w] = np.asarray(local[k]).reshape(n_loc, w)
+            o += w
+        send = torch.from_numpy(pack).to(dev)
+        recv = torch.empty((world * n_max, send.shape[1]), dtype=send.dtype, device=dev)
+        dist.all_gather_into_tensor(recv, send, group=group)
+        full = recv.cpu().numpy().reshape(world, n_max, send.shape[1])
+        o = 0
+        for k, w in zip(keys, widths):
+            out[k] = np.concatenate([full[r, :b - a, o:o + w] for r, (a, b) in enumerate(parts)], axis=0).reshape(
+                (len(chain_cell),) + tuple(schema[k][0]))
+            o += w
+    out["local"] = {k: v for k, v in local.items() if k not in schema}
+    out["partition"] = parts
     return out
