@@ -180,3 +180,42 @@ def test_mex_gateway_compiles_against_stub_header(tmp_path):
     res = subprocess.run([gxx, "-std=c++17", "-fsyntax-only", "-Wall", "-I", os.path.join(root, "tests", "stubs"),
                           "-I", os.path.join(root, "include"), str(src)], capture_output=True, text=True)
     assert res.returncode == 0, res.stderr
+
+
+def test_raw_chains_beyond_the_mat5_limit_are_split_into_matlab_readable_parts(tmp_path):
+    """Plain `save` (MAT v5) cannot hold a variable of 2 GiB and the reference's own defaults on TestData give a 3.1 GB
+    MCMCchain: below the limit the writer produces the reference's single file, above it parts of whole
+    cells + an index, all of them MAT v5 files that scipy (and MATLAB) read back — never a non-MATLAB format."""
+    import scipy.io as sio
+    from transcriptioncycleinference_b200 import mcmc
+    rng = np.random.default_rng(0)
+    chain = []
+    for c in range(7):
+        N = 5 + c
+        rec = {f: rng.standard_normal((11, 1)) for f in mcmc.CHAIN_FIELDS}
+        rec["dR_chain"] = rng.standard_normal((11, N)); rec["s2chain"] = rng.random((20, 1))
+        chain.append(rec)
+    one = mcmc.save_raw_chains(str(tmp_path), "a", chain)                       # fits: the reference's file
+    assert [os.path.basename(f) for f in one] == ["a_RawChain.mat"]
+    m = sio.loadmat(one[0])["MCMCchain"]
+    assert m.shape == (1, 7) and m.dtype.names == mcmc.CHAIN_FIELDS
+    size = [sum(v.nbytes for v in c.values()) for c in chain]
+    files = mcmc.save_raw_chains(str(tmp_path), "b", chain, limit=size[0] + size[1] + size[2] + 8)   # forces a split
+    assert os.path.basename(files[0]) == "b_RawChain.mat" and len(files) >= 3
+    idx = sio.loadmat(files[0])
+    assert int(idx["nParts"].squeeze()) == len(files) - 1
+    names = [str(x[0]) if isinstance(x, np.ndarray) else str(x) for x in idx["MCMCchainParts"].reshape(-1)]
+    back = [None] * 7
+    for k, nm in enumerate(names, start=1):
+        with open(os.path.join(tmp_path, nm.strip()), "rb") as fh:
+            assert fh.read(19) == b"MATLAB 5.0 MAT-file"
+        p = sio.loadmat(os.path.join(tmp_path, nm.strip()))
+        a, b = int(p["firstCell"].squeeze()), int(p["lastCell"].squeeze())
+        assert np.all(idx["MCMCchainPartOfCell"][0, a - 1:b] == k) and p["MCMCchain"].shape == (1, b - a + 1)
+        for j in range(a, b + 1):
+            back[j - 1] = p["MCMCchain"][0, j - a]
+    for c in range(7):
+        for f in mcmc.CHAIN_FIELDS:
+            np.testing.assert_array_equal(back[c][f], chain[c][f])
+    with pytest.raises(ValueError):
+        mcmc.save_raw_chains(str(tmp_path), "c", chain, limit=size[0] - 8)       # one cell alone is too large

@@ -15,6 +15,8 @@ Differences that are deliberate and documented:
     results are read from 'previousResults' (a results .mat in this same layout) or from the newest
     results file in fileDir whose DatasetName matches; cells are matched on cell_index, unmatched
     cells are skipped and removed, ApprovedFits is carried over.
+  * raw chains beyond MAT v5's 2 GiB per variable (the reference's own defaults on TestData are 3.1 GB) are written as
+    MATLAB-readable parts `<date>-<name>_RawChain_part<K>.mat` + an index (save_raw_chains, matlab/LoadRawChains.m).
   * new optional arguments: 'files', 'previousResults', 'numChains' (default 1), 'seed',
     'saveChains' (default True), 'verbose', 'returnResults'.  With numChains > 1 the chains of a cell are
     pooled in MCMCresults and an extra variable MCMCdiagnostics (Rhat, n_eff per parameter) is saved.
@@ -123,6 +125,42 @@ def _struct_array(fields, records):
         for f in fields:
             arr[0, i][f] = r[f]
     return arr
+
+
+MAT5_LIMIT = 2 ** 31 - 2 ** 24          # bytes per MAT v5 variable (2 GiB), with room for the struct headers
+
+
+def save_raw_chains(save_loc, base, chain, limit=MAT5_LIMIT):
+    """`save([saveLoc,'\',filename,'_RawChain.mat'],'MCMCchain')` (:377-378).  Plain `save` writes MAT v5, whose variables
+    are limited to 2 GiB — the reference's own defaults on TestData (299 cells x 10 001 rows x ~128 doubles = 3.1 GB) already
+    exceed that.  Up to the limit: the reference's single file.  Beyond it: MATLAB-readable PARTS
+    `<base>_RawChain_part<K>.mat`, each a v5 file below the limit holding `MCMCchain` for a run of whole cells
+    (plus `firstCell`, `lastCell`: positions in the full 1 x Ncells array), and the index `<base>_RawChain.mat` with
+    `MCMCchainParts` (file names), `MCMCchainPartOfCell` (1 x Ncells) and `nParts`; matlab/LoadRawChains.m puts them back
+    together.  Returns the list of files written."""
+    import scipy.io as sio
+    sizes = [sum(np.asarray(v).nbytes for v in c.values()) for c in chain]
+    if any(b > limit for b in sizes):
+        raise ValueError("the raw chain of one cell (%d bytes) exceeds the MAT v5 variable limit: thin it or lower n_steps" % max(sizes))
+    path = os.path.join(save_loc, base + "_RawChain.mat")
+    if sum(sizes) <= limit:
+        sio.savemat(path, dict(MCMCchain=_struct_array(CHAIN_FIELDS, chain)))
+        return [path]
+    groups, cur, cur_b = [], [], 0
+    for i, b in enumerate(sizes):
+        if cur and cur_b + b > limit:
+            groups.append(cur); cur, cur_b = [], 0
+        cur.append(i); cur_b += b
+    groups.append(cur)
+    files, part_of = [], np.zeros((1, len(chain)))
+    for k, idx in enumerate(groups, start=1):
+        fn = "%s_RawChain_part%d.mat" % (base, k)
+        sio.savemat(os.path.join(save_loc, fn), dict(MCMCchain=_struct_array(CHAIN_FIELDS, [chain[i] for i in idx]),
+                                                     firstCell=float(idx[0] + 1), lastCell=float(idx[-1] + 1), part=float(k)))
+        files.append(fn); part_of[0, idx] = k
+    sio.savemat(path, dict(MCMCchainParts=np.array(files, dtype=object).reshape(-1, 1), MCMCchainPartOfCell=part_of,
+                           nParts=float(len(groups))))
+    return [path] + [os.path.join(save_loc, f) for f in files]
 
 
 def fit_dataset(cells_in, o, devices):
@@ -252,14 +290,7 @@ def TranscriptionCycleMCMC(*varargin):
             mat["MCMCdiagnostics"] = _struct_array(DIAG_FIELDS, diags)
         sio.savemat(os.path.join(save_loc, base + ".mat"), mat)
         if o["saveChains"]:
-            nbytes = sum(sum(np.asarray(v).nbytes for v in c.values()) for c in chain)
-            if nbytes >= 2 ** 31:
-                # plain MAT v5 (what the reference's `save` writes) cannot hold it
-                np.savez(os.path.join(save_loc, base + "_RawChain.npz"),
-                         **{"%s_%d" % (fld, i): c[fld] for i, c in enumerate(chain) for fld in CHAIN_FIELDS})
-            else:
-                sio.savemat(os.path.join(save_loc, base + "_RawChain.mat"),
-                            dict(MCMCchain=_struct_array(CHAIN_FIELDS, chain)))
+            save_raw_chains(save_loc, base, chain)
         ret.append(dict(DatasetName=name, MCMCresults=results, MCMCplot=plot, MCMCchain=chain, MCMCdiagnostics=diags))
     print("MCMC analysis complete. Information stored in: %s" % save_loc)
     return ret if o["returnResults"] else None
