@@ -378,3 +378,37 @@ def test_warp_kernel_production_path(gpu_cells, cells_npz, orc):
         b = gpu_cells.mcmc_run(_lib.default_opts(nsimu=700, burnintime=300, n_burn=1, seed=5, layout=0, **SHORT, **variant), cc[:3], th0, q, lo, hi, mu, sg, want_flags=True)
         assert np.array_equal(a["flags"], b["flags"]), variant
         np.testing.assert_allclose(a["mean"], b["mean"], rtol=0, atol=1e-6)
+
+
+def test_philox_variates_pass_ks(gpu_cells):
+    """The sampling variates are the one place single precision enters: the proposal normals and the normal
+    inside Marsaglia-Tsang's chi-square are Box-Muller in FP32 (32-bit radius uniform => |z| <= 6.76, 24-bit angle) widened
+    to FP64; u1, u2 are 53-bit uniforms.  Stated tolerance: indistinguishable from N(0,1) / U(0,1) / chi2(nu) by
+    Kolmogorov-Smirnov at 2.5e5 - 5e6 draws (p > 1e-3), moments within 4 standard errors, tails present up to 4.5 sigma,
+    and no correlation between the two stages or consecutive steps."""
+    from scipy import stats
+    from transcriptioncycleinference_b200 import _lib
+    npar, nsimu, nu = 127, 20000, 241.0
+    d = _lib.rng_dump(20201028, 123456789, npar, nu, nsimu)
+    for k in ("z1", "z2"):
+        z = d[k][1:].reshape(-1)
+        assert stats.kstest(z[:500000], "norm").pvalue > 1e-3
+        se = 1.0 / np.sqrt(z.size)
+        assert abs(z.mean()) < 4 * se and abs(z.var() - 1) < 4 * np.sqrt(2.0) * se
+        assert abs(stats.skew(z)) < 4 * np.sqrt(6.0) * se and abs(stats.kurtosis(z)) < 4 * np.sqrt(24.0) * se
+        # tail mass against the exact normal: P(|z| > 4.5) = 6.8e-6 -> ~17 of 2.5e6
+        n45 = int((np.abs(z) > 4.5).sum())
+        assert 2 <= n45 <= 45 and np.abs(z).max() <= 6.77
+    z1, z2 = d["z1"][1:], d["z2"][1:]
+    assert abs(np.corrcoef(z1.reshape(-1), z2.reshape(-1))[0, 1]) < 4 / np.sqrt(z1.size)
+    assert abs(np.corrcoef(z1[:-1].reshape(-1), z1[1:].reshape(-1))[0, 1]) < 4 / np.sqrt(z1.size)
+    assert abs(np.corrcoef(z1[:, :-1].reshape(-1), z1[:, 1:].reshape(-1))[0, 1]) < 4 / np.sqrt(z1.size)
+    for k in ("u1", "u2"):
+        assert stats.kstest(d[k][1:], "uniform").pvalue > 1e-3
+    c2 = d["chi2"][1:]
+    assert stats.kstest(c2, "chi2", args=(nu,)).pvalue > 1e-3
+    assert abs(c2.mean() / nu - 1) < 4 * np.sqrt(2.0 / nu / c2.size) and abs(c2.var() / (2 * nu) - 1) < 0.06
+    # a second degrees-of-freedom value (N = 400: nu = 801) and an independent chain identity
+    d2 = _lib.rng_dump(7, 42, 16, 801.0, 50000)
+    assert stats.kstest(d2["chi2"][1:], "chi2", args=(801.0,)).pvalue > 1e-3
+    assert stats.kstest(d2["z1"][1:].reshape(-1), "norm").pvalue > 1e-3

@@ -124,3 +124,30 @@ def test_empty_batch_and_errors(gpu_cells):
         gpu_cells.ss_batch(np.array([299], dtype=np.int32), np.zeros((1, gpu_cells.ld)))
     with pytest.raises(_lib.TcError):
         gpu_cells.ss_batch(np.array([0], dtype=np.int32), np.zeros((1, 20)))
+
+
+def test_ss_one_million_random_theta(gpu_cells, cells_npz, orc):
+    """SURVEY.md 8(d)'s SS-parity volume: 10^6 theta drawn uniformly inside the bounds of TranscriptionCycleMCMC.m:242-254
+    (seed 0) across all 299 cells, both algorithms, against the literal m x n oracle (all host cores), 1e-10 relative.
+    A polymerase within an ulp of the discontinuity at L = L0 + tau v may flip: counted, reported, and
+    bounded at 5 per million."""
+    co, cons = orc
+    rng = np.random.default_rng(0)
+    n = 1_000_000
+    cid = np.sort(rng.integers(0, 299, n)).astype(np.int32)           # proposals for a cell arrive together
+    ld = gpu_cells.ld
+    lo = np.concatenate([[0, 0, 0, 0, 0, 0, 0], -30 * np.ones(ld - 7)])
+    hi = np.concatenate([[10, 20, 10, 50, 50, 1, 40], 30 * np.ones(ld - 7)])
+    th = np.zeros((n, ld))
+    for s in range(0, n, 100_000):                                   # (in slabs: 1.1 GB of theta in all)
+        th[s:s + 100_000] = lo + (hi - lo) * rng.random((min(100_000, n - s), ld))
+    npar = 7 + cells_npz["N"][cid]
+    th[np.arange(ld)[None, :] >= npar[:, None]] = 0.0                # zero padding beyond each cell's npar
+    ref = co.ss_batch(cons, cells_npz, cid, th)
+    for algo in (1, 0):
+        got = gpu_cells.ss_batch(cid, th, algo=algo)
+        rel = np.abs(got - ref) / np.maximum(np.abs(ref), 1e-300)
+        flips = int((rel >= TOL).sum())
+        print("algo %d: 10^6 evaluations, max rel %.3g, median %.3g, rows beyond 1e-10: %d" % (algo, rel.max(), np.median(rel), flips))
+        assert flips <= 5, (algo, flips, rel.max())
+        assert np.median(rel) < 1e-13
