@@ -871,7 +871,8 @@ struct ChainState {
 // Immutable per-chain context, built once in shared memory so that the out-of-line phases below
 // (kept out of line to keep the hot loop inside the instruction cache) can share it.
 struct ChainCtx {
-    int N, npar, npad, ld, slot_sz, wsz, ch, first_row, nstore, ring_mask;
+    int N, npar, npad, ld, slot_sz, wsz, ch, first_row, nstore, ring_mask, uni;
+    double blk[4];                                      // uni: common lo, hi, mu, 1/sig of the parameters >= 7 (the dR block)
     unsigned long long uid;
     double adascale, inv_dr, chi_d, chi_c;              // chi_d, chi_c: Marsaglia-Tsang constants of chi2(N0 + 2 N)
     SmemCell cv;
@@ -1301,11 +1302,15 @@ __device__ __forceinline__ void warp_sum2(double &p, double &q)
 // Round phase A: bounds and prior of both proposals of the candidate steps k .. k+C-1 (warp w: candidates w, w+8).
 // The proposals are never materialised: theta = x + ring increment, the very expression the forward model
 // (SumVec) and the commit phase use.                    bounds/prior: TranscriptionCycleMCMC.m:235-255
-template <bool SM>
+// UNI: this chain's bounds / prior have the reference's structure (TranscriptionCycleMCMC.m:242-255) — seven head parameters with
+// their own bounds, then one block (dR) with common bounds and prior (cx.blk) — so only the first pass (j < 32) reads the
+// per-parameter vectors; SM: the vectors are in shared memory (regular layout) or in HBM/L2 (big layout).
+template <bool SM, bool UNI>
 __device__ __forceinline__ void cand_bounds_t(const ChainCtx &cx, int k, int C, Cand *cand)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, npar = cx.npar;
     const int ox = cx.o_x, ol = cx.o_lo, oh = ol + npar, om = oh + npar, op = cx.o_pinv;
+    const double blo = cx.blk[0], bhi = cx.blk[1], bmu = cx.blk[2], bpinv = cx.blk[3];
 #pragma unroll 1
     for (int c = warp; c < C; c += SPEC) {
         const double2 *dd = reinterpret_cast<const double2 *>(tc_smem + cx.slot_o(k + c));
@@ -1315,8 +1320,12 @@ __device__ __forceinline__ void cand_bounds_t(const ChainCtx &cx, int k, int C, 
         for (int j = lane; j < npar; j += 32) {
             const double2 dj = dd[j];
             const double xj = tc_smem[ox + j], a1 = xj + dj.x, a2 = xj + dj.y;
-            const double lo = SM ? tc_smem[ol + j] : cx.lo[j], hi = SM ? tc_smem[oh + j] : cx.hi[j];
-            const double mu = SM ? tc_smem[om + j] : cx.mu[j], pinv = tc_smem[op + j];
+            double lo, hi, mu, pinv;
+            if (UNI && j >= 8) { lo = blo; hi = bhi; mu = bmu; pinv = bpinv; }
+            else {
+                lo = SM ? tc_smem[ol + j] : cx.lo[j]; hi = SM ? tc_smem[oh + j] : cx.hi[j];
+                mu = SM ? tc_smem[om + j] : cx.mu[j]; pinv = tc_smem[op + j];
+            }
             if (a1 < lo || a1 > hi) oob |= 1u;
             if (a2 < lo || a2 > hi) oob |= 2u;
             const double e1 = (a1 - mu) * pinv, e2 = (a2 - mu) * pinv;
@@ -1330,8 +1339,8 @@ __device__ __forceinline__ void cand_bounds_t(const ChainCtx &cx, int k, int C, 
 }
 __device__ __noinline__ void cand_bounds(const ChainCtx &cx, int k, int C, Cand *cand)
 {
-    if (cx.o_lo >= 0) cand_bounds_t<true>(cx, k, C, cand);
-    else cand_bounds_t<false>(cx, k, C, cand);
+    if (cx.o_lo >= 0) { if (cx.uni) cand_bounds_t<true, true>(cx, k, C, cand); else cand_bounds_t<true, false>(cx, k, C, cand); }
+    else { if (cx.uni) cand_bounds_t<false, true>(cx, k, C, cand); else cand_bounds_t<false, false>(cx, k, C, cand); }
 }
 
 // Round phase D, part 2: the delayed-rejection arithmetic of ONE step (one lane) whose first stage rejected, from state
@@ -1340,11 +1349,11 @@ __device__ __noinline__ void cand_bounds(const ChainCtx &cx, int k, int C, Cand 
 //   a12 = exp(-1/2 ((ss1-ss)/s2 + pr1-pri)), a32 = exp(-1/2 ((ss1-ss2)/s2 + pr1-pr2)), exp(l2 + q1)
 //                                                                             mcmcstat DRAM: SURVEY.md 3.2
 __device__ __noinline__ int resolve_dr(const double *sc, bool o1, double x12, double pr1, double pr2, double ss1, double ss2,
-                                       double ss, double pri, double s2p)
+                                       double ss, double pri, double is2p)            // is2p = 1 / sigma2 of the step
 {
     const double q1 = -0.5 * (sc[3] - sc[4]);
     double e12, e32, e13;
-    tc_exp3(x12, -0.5 * ((ss1 - ss2) / s2p + pr1 - pr2), -0.5 * ((ss2 - ss) / s2p + pr2 - pri) + q1, e12, e32, e13);
+    tc_exp3(x12, -0.5 * ((ss1 - ss2) * is2p + pr1 - pr2), -0.5 * ((ss2 - ss) * is2p + pr2 - pri) + q1, e12, e32, e13);
     const double a12 = o1 ? 0.0 : e12;
     double a32 = e32;
     a32 = a32 > 1.0 ? 1.0 : a32;
@@ -1731,6 +1740,23 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
             for (int i = tid; i < cx.slot_sz; i += DRAM_THREADS) cx.ring[i] = 0.0;
         }
 
+        {
+            // bounds / prior in the reference's head + block structure?  (four vectors read once per slice)
+            int diff = 0;
+#pragma unroll 1
+            for (int i = 8 + tid; i < npar; i += DRAM_THREADS) {
+                const size_t g = (size_t)ch * a.ld;
+                const double s7 = a.psig[g + 7], si = a.psig[g + i];
+                diff |= !(a.low[g + i] == a.low[g + 7] && a.upp[g + i] == a.upp[g + 7] && a.pmu[g + i] == a.pmu[g + 7] && si == s7);
+            }
+            diff = __syncthreads_or(diff);
+            if (tid == 0) {
+                const size_t g = (size_t)ch * a.ld + 7;
+                const double s7 = a.psig[g];
+                cx.uni = diff ? 0 : 1;
+                cx.blk[0] = a.low[g]; cx.blk[1] = a.upp[g]; cx.blk[2] = a.pmu[g]; cx.blk[3] = isinf(s7) ? 0.0 : 1.0 / s7;
+            }
+        }
         if (tid == 0) {
             if (seg == 0) {
                 st.ss = 0.0; st.pri = 0.0; st.sigma2 = a.sigma2_0; st.cov_n = 0.0; st.wcnt = 0.0; st.r_diag = 1; st.bad0 = 0;
@@ -1783,6 +1809,11 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
             // chain state of this round (thread 0 rewrites st only in the commit phase, after two barriers)
             const double ss = st.ss, pri = st.pri, sig2 = st.sigma2, wcnt = st.wcnt;
             const int run_r0 = st.run_r0, ndist = st.ndist;
+            // 1 / sigma2 of the candidate steps, started here so that the divisions are off the critical path of phase D:
+            // step k sees sig2, step k + w sees (N0 S20 + ss) / chi2_{k+w-1}, i.e. 1/sigma2 = chi2_{k+w-1} * rden.  (A product
+            // with a rounded reciprocal instead of a quotient: the acceptance exponent moves by an ulp, like the log-domain
+            // decision of stage 1.)
+            const double rden = 1.0 / (a.N0 * a.S20 + ss), rsig = 1.0 / sig2;
 
             if (gen_upto < bound && gen_upto - k < (a.big ? 1 : SPEC)) {
                 // fewer than SPEC steps ready => at least GEN_M of the RING slots are free (big layout: ring of GEN_M
@@ -1839,15 +1870,15 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
             so_.acc = 0; so_.fl = 0; so_.nev = 0; so_.noob = 0; so_.ssn = 0.0; so_.prin = 0.0;
             const bool act = lane < nsteps;
             const bool o1 = (c_oob & 1) != 0, o2 = (c_oob & 2) != 0;
-            double s2p = sig2, x12 = 0.0, pr1 = 0.0, pr2 = 0.0, ss1 = INFINITY, ss2 = 0.0;
+            double is2p = rsig, x12 = 0.0, pr1 = 0.0, pr2 = 0.0, ss1 = INFINITY, ss2 = 0.0;
             const double *scp = cx.slot_sc(k + (act ? lane : 0));
             bool acc1 = false;
             if (act) {
-                if (lane > 0 && a.updatesigma) s2p = (a.N0 * a.S20 + ss) / cx.slot_sc(k + lane - 1)[2];
+                if (lane > 0 && a.updatesigma) is2p = cx.slot_sc(k + lane - 1)[2] * rden;
                 pr2 = s_cand[lane].pr2; ss2 = s_ssv[2 * lane + 1];
                 if (!o1) {
                     pr1 = s_cand[lane].pr1; ss1 = s_ssv[2 * lane];
-                    x12 = -0.5 * ((ss1 - ss) / s2p + pr1 - pri);
+                    x12 = -0.5 * ((ss1 - ss) * is2p + pr1 - pri);
                     acc1 = x12 >= 0.0 || x12 > scp[5];
                 }
             }
@@ -1864,7 +1895,7 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
                     if (o2) { so_.fl |= TC_FL_OOB2; ++so_.noob; }
                     else {
                         ++so_.nev;
-                        if (resolve_dr(scp, o1, x12, pr1, pr2, ss1, ss2, ss, pri, s2p)) { so_.acc = 2; so_.fl |= TC_FL_STAGE2; so_.ssn = ss2; so_.prin = pr2; }
+                        if (resolve_dr(scp, o1, x12, pr1, pr2, ss1, ss2, ss, pri, is2p)) { so_.acc = 2; so_.fl |= TC_FL_STAGE2; so_.ssn = ss2; so_.prin = pr2; }
                     }
                 }
             }
@@ -1884,8 +1915,21 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
             }
             SUBP(21);
             if (warp == 0) {
-                // per-row scalars of the committed rows (lane = row): sigma2 of the row (rows before the accept keep ss),
-                // s2chain statistics, optional per-step outputs; then the chain state for the next round
+                // the chain state of the next round: only what the next round needs, one division (lane 0).  The sigma2 the
+                // next step sees is the draw of the last committed row, made from that row's ss
+                if (lane == 0) {
+                    const double ss_new = accd ? ssn_a : ss;
+                    if (accd) {
+                        st.ss = ss_new; st.pri = prin_a;
+                        st.wcnt = wcnt + max(0, r_acc - max(run_r0, cx.first_row));
+                        if (a.do_cov && r_acc > run_r0) st.ndist = ndist + 1;
+                        st.run_r0 = r_acc;
+                    }
+                    if (a.updatesigma) st.sigma2 = (a.N0 * a.S20 + ss_new) / cx.slot_sc(k + ncommit - 1)[2];
+                }
+            } else if (warp == SPEC - 1) {
+                // meanwhile: per-row scalars of the committed rows (lane = row) — sigma2 of the row (rows before the accept
+                // keep ss), s2chain statistics, optional per-step outputs — and the counters
                 const double ss_new = accd ? ssn_a : ss;
                 double s2 = 0.0, sq = 0.0;
                 if (lane < ncommit) {
@@ -1897,7 +1941,6 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
                     if (a.flags) a.flags[(size_t)cx.ch * a.nsimu + r] = so_.fl;
                     if (a.sschain) a.sschain[(size_t)cx.ch * a.nsimu + r] = ssr;
                 }
-                const double s2_last = __shfl_sync(0xffffffffu, s2, ncommit - 1);   // the sigma2 the next step sees
 #pragma unroll
                 for (int o = RING / 2; o > 0; o >>= 1) { s2 += __shfl_xor_sync(0xffffffffu, s2, o); sq += __shfl_xor_sync(0xffffffffu, sq, o); }
                 const int d_ss = __reduce_add_sync(0xffffffffu, lane < ncommit ? so_.nev : 0);
@@ -1909,14 +1952,7 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
                     const int nrej = accd ? first : nsteps;
                     st.n_ss += d_ss; st.n_oob += d_oob; st.n_dr += d_dr; st.n_spec += d_spec;
                     st.rej += nrej; st.reju += nrej;
-                    if (accd) {
-                        st.ss = ss_new; st.pri = prin_a;
-                        if (acc_t == 1) ++st.n_acc1; else ++st.n_acc2;
-                        st.wcnt = wcnt + max(0, r_acc - max(run_r0, cx.first_row));
-                        if (a.do_cov && r_acc > run_r0) st.ndist = ndist + 1;
-                        st.run_r0 = r_acc;
-                    }
-                    if (a.updatesigma) st.sigma2 = s2_last;
+                    if (accd) { if (acc_t == 1) ++st.n_acc1; else ++st.n_acc2; }
                 }
             }
             SUBP(22);
