@@ -99,11 +99,12 @@ typedef struct tc_mcmc_opts {
                                  WARP per chain beyond that (thousands of chains: BASELINE config 3), the large-series
                                  layout for series with more than ~210 points.  TC_LAYOUT_BIG forces the large-series layout
                                  (ring of 8 proposal slots, proposal factor factorised through HBM/L2), TC_LAYOUT_WARP the
-                                 chain-per-warp kernel.  Same chain whichever runs (parity tests) */
+                                 chain-per-warp kernel, TC_LAYOUT_CTA the CTA-per-chain kernel whatever the chain count.  Same
+                                 chain whichever runs (parity tests) */
     int32_t qcovadj_always;   /* 0 (default): R = chol(cov), and chol(cov + qcovadj I) only when that fails — mcmcstat's
                                  "try to blow it" branch [U]; 1: always factor cov + qcovadj I */
 } tc_mcmc_opts;
-enum { TC_LAYOUT_AUTO = 0, TC_LAYOUT_BIG = 1, TC_LAYOUT_WARP = 2 };
+enum { TC_LAYOUT_AUTO = 0, TC_LAYOUT_BIG = 1, TC_LAYOUT_WARP = 2, TC_LAYOUT_CTA = 3 };
 
 /* Per-chain counters returned by tc_mcmc_run (int64 each) */
 enum {

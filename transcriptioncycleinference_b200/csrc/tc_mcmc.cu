@@ -56,7 +56,7 @@ struct DeviceGuard {
 #define SS_MIN_CTAS 4          // 64 registers: 32 warps per SM hide the latency of streaming theta (measured +12 % over 2)
 #endif
 #ifndef TC_WARP_MIN_CHAINS_PER_SM
-#define TC_WARP_MIN_CHAINS_PER_SM 6   // chain-per-warp kernel from this many chains per SM on (tc_mcmc_run)
+#define TC_WARP_MIN_CHAINS_PER_SM 13  // chain-per-warp kernel from this many chains per SM on (measured crossover on B200: ~1 900 chains)
 #endif
 #define COV_CR 32          // weighted rows of the covariance block staged per pass of the scatter update
 
@@ -2647,14 +2647,14 @@ int tc_mcmc_run(const tc_cells *c, const tc_mcmc_opts *o, int nchains, const int
         a.big = (sizeof(double) * (size_t)dram_smem_doubles(Nmax, 0) > avail || o->layout == TC_LAYOUT_BIG) ? 1 : 0;
         // Many chains per SM: one warp per chain (dram_warp_kernel, tc_warp.cuh) instead of one CTA per chain.  The CTA kernel
         // buys latency with speculation and wins while there are about as many chains as CTA slots (measured crossover on
-        // B200: ~4 chains per SM); beyond that the warp kernel does no wasted evaluations and no CTA barriers.
+        // B200: ~13 chains per SM); beyond that the warp kernel does no wasted evaluations and no CTA barriers.
         cudaFuncAttributes faw;
         CUDA_TRY(cudaFuncGetAttributes(&faw, dram_warp_kernel));
         const size_t smem_w = sizeof(double) * (size_t)wk_region(Nmax) * WK_WARPS;
         const bool warp_fits = smem_w + faw.sharedSizeBytes <= (size_t)optin && npmax <= 32 * WK_PIT;
         if (o->layout == TC_LAYOUT_WARP && !warp_fits)
             return fail(TC_EINVAL, "max(N) = " + std::to_string(Nmax) + " is too large for the chain-per-warp layout");
-        const bool use_warp = o->layout == TC_LAYOUT_WARP || (o->layout == TC_LAYOUT_AUTO && warp_fits && !a.big && nc >= TC_WARP_MIN_CHAINS_PER_SM * sms);
+        const bool use_warp = o->layout == TC_LAYOUT_WARP || (o->layout == TC_LAYOUT_AUTO && warp_fits && !a.big && nc >= TC_WARP_MIN_CHAINS_PER_SM * sms);   // TC_LAYOUT_CTA / _BIG: never
         // time slices: a multiple of adaptint, ~32 per chain
         const int unit = o->adaptint > 0 ? o->adaptint : 1;
         long long sl = ((long long)o->nsimu + 31) / 32;

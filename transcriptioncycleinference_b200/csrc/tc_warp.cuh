@@ -789,6 +789,13 @@ __global__ void __launch_bounds__(WK_THREADS, 1) dram_warp_kernel(const __grid_c
             uni = c.uni != 0;
         }
         const bool active = valid && !bad0;
+#ifdef WK_SUBPROF
+#define WK_T0 const long long t0__ = clock64()
+#define WK_T1(i) do { if (lane == 0) st.pc[i] += clock64() - t0__; } while (0)
+#else
+#define WK_T0
+#define WK_T1(i)
+#endif
 #define WK_PHASE(i) do { if (lane == 0) { const long long tn__ = clock64(); st.pc[i] += tn__ - st.tprev; st.tprev = tn__; } } while (0)
 
         int k = seg == 0 ? 1 : seg * a.seglen;
@@ -820,7 +827,9 @@ __global__ void __launch_bounds__(WK_THREADS, 1) dram_warp_kernel(const __grid_c
                 const bool o1 = uni ? wk_propose1<true>(c, ox, ob, row, pr1, inc2) : wk_propose1<false>(c, ox, ob, row, pr1, inc2);
                 if (o1) { fl |= TC_FL_OOB1; noob = 1; pr1 = 0.0; }
                 else {
+                    WK_T0;
                     ss1 = ss_eval(a.cons, cv, SmemVec{ob}, w, a.algo, false, nullptr, nullptr);
+                    WK_T1(7);
                     nev = 1;
                     x12 = -0.5 * ((ss1 - ss) / sig2 + pr1 - pri);
                     if (x12 >= 0.0 || x12 > s_logu) acc = 1;
@@ -833,7 +842,9 @@ __global__ void __launch_bounds__(WK_THREADS, 1) dram_warp_kernel(const __grid_c
                     const bool o2 = uni ? wk_propose2<true>(c, ox, ob, pr2, inc2) : wk_propose2<false>(c, ox, ob, pr2, inc2);
                     if (o2) { fl |= TC_FL_OOB2; ++noob; }
                     else {
+                        WK_T0;
                         const double ss2 = ss_eval(a.cons, cv, SmemVec{ob}, w, a.algo, false, nullptr, nullptr);
+                        WK_T1(7);
                         ++nev;
                         if (resolve_dr_v(-0.5 * (s_n1 - s_n0), s_u2, o1, x12, pr1, pr2, ss1, ss2, ss, pri, sig2)) { acc = 2; fl |= TC_FL_STAGE2; ssn = ss2; prin = pr2; }
                     }
@@ -936,7 +947,12 @@ __global__ void __launch_bounds__(WK_THREADS, 1) dram_warp_kernel(const __grid_c
                 cn[TC_CNT_CHOL_FAIL] = st.n_cholfail; cn[TC_CNT_DR_TRIES] = st.n_dr; cn[TC_CNT_STATUS] = bad0 ? 1 : 0;
                 cn[TC_CNT_CYCLES0 + 0] = st.pc[0]; cn[TC_CNT_CYCLES0 + 1] = st.pc[1]; cn[TC_CNT_CYCLES0 + 2] = st.pc[3]; cn[TC_CNT_CYCLES0 + 3] = st.pc[4];
                 cn[TC_CNT_CYCLES0 + 4] = st.pc[5]; cn[TC_CNT_CYCLES0 + 5] = st.pc[2]; cn[TC_CNT_CYCLES0 + 6] = st.pc[6];
+#ifdef WK_SUBPROF
+                cn[TC_CNT_CYCLES0 + 7] = st.pc[7];
+#endif
+#ifndef WK_SUBPROF
                 cn[TC_CNT_CYCLES0 + 7] = st.n_ss;                       // no speculation: every evaluation is committed
+#endif
             }
             __threadfence();
             atomicExch(a.cstate + ch, nseg);
