@@ -13,7 +13,7 @@ def raw(rep):
     txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
     return rows[0], rows[1], rows[2]
-for name in ("dram", "ss", "c5"):
+for name in ("dram", "ss", "c5", "warp"):
     rep = "gpurun_out/prof_%s_%s.ncu-rep" % (name, R)
     if not os.path.exists(rep):
         continue
@@ -24,7 +24,7 @@ for name in ("dram", "ss", "c5"):
             if a in ("Kernel Name", "Block Size", "Grid Size") or any(k.strip() in a for k in KEYS):
                 f.write("%-90s %-14s %s\n" % (a, b, c))
         f.write("\n# by source function (warp instructions executed, stall samples)\n")
-        f.write(subprocess.run([sys.executable, "scripts/ncu_funcs.py", rep], capture_output=True, text=True).stdout)
+        f.write(subprocess.run([sys.executable, "scripts/ncu_wk_funcs.py" if name == "warp" else "scripts/ncu_funcs.py", rep], capture_output=True, text=True).stdout)
         f.write("\n# top source lines by stall samples\n")
         f.write(subprocess.run([sys.executable, "scripts/ncu_lines.py", rep, "25"], capture_output=True, text=True).stdout)
 lst = "gpurun_out/launches_%s.csv" % R
@@ -47,6 +47,9 @@ if os.path.exists(lst):
         f.write("# (cold-cache, serialised: compare SHARES)\n%-60s %8s %12s %7s\n" % ("kernel", "launches", "total ms", "share"))
         for k, (n, ms) in sorted(agg.items(), key=lambda x: -x[1][1]):
             f.write("%-60s %8d %12.3f %6.1f%%\n" % (k[:60], n, ms, 100 * ms / tot))
+import glob, shutil
+for f in glob.glob("gpurun_out/traffic_*_%s.json" % R) + glob.glob("gpurun_out/traffic_writeback_%s.csv" % R) + glob.glob("gpurun_out/bench_%s_n*.json" % R) + glob.glob("gpurun_out/bench_ref_%s_n*.json" % R):
+    shutil.copy(f, "profiles/")
 for fn in ("bench_%s.json" % R, "bench_ref_%s.json" % R):
     p = os.path.join("gpurun_out", fn)
     if os.path.exists(p):

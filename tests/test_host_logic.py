@@ -219,3 +219,27 @@ def test_raw_chains_beyond_the_mat5_limit_are_split_into_matlab_readable_parts(t
             np.testing.assert_array_equal(back[c][f], chain[c][f])
     with pytest.raises(ValueError):
         mcmc.save_raw_chains(str(tmp_path), "c", chain, limit=size[0] - 8)       # one cell alone is too large
+
+
+def test_split_rhat_and_ess_from_raw_chains():
+    """split-Rhat and the autocorrelation-based ESS (diagnostics.split_rhat / ess): AR(1) chains with known
+    integrated autocorrelation time (1 + phi) / (1 - phi); a drifting single chain is caught by split-Rhat although plain
+    Rhat cannot see it."""
+    from transcriptioncycleinference_b200 import diagnostics
+    rng = np.random.default_rng(11)
+    m, n = 4, 20000
+    phis = np.array([0.0, 0.5, 0.9, 0.98])
+    x = np.zeros((m, n, phis.size))
+    e = rng.standard_normal((m, n, phis.size))
+    for t in range(1, n):
+        x[:, t] = phis * x[:, t - 1] + np.sqrt(1 - phis ** 2) * e[:, t]
+    es = diagnostics.ess(x)
+    expect = m * n * (1 - phis) / (1 + phis)
+    assert np.all(np.abs(es / expect - 1) < 0.25), (es, expect)
+    sr = diagnostics.split_rhat(x)
+    assert np.all(sr < 1.05)
+    _, ne = diagnostics.rhat_from_summaries(x.mean(axis=1), x.std(axis=1), n)
+    assert np.all(np.isfinite(ne)) and np.all(ne <= m * n)      # the summaries-only estimate: right order of magnitude, m - 1 degrees of freedom
+    assert np.all(ne / expect < 20) and np.all(ne / expect > 0.05)
+    drift = x[:1, :, :1] + np.linspace(0, 3, n)[None, :, None]
+    assert diagnostics.split_rhat(drift)[0] > 1.3 and diagnostics.ess(drift)[0] < 0.05 * n

@@ -35,7 +35,9 @@ RESULT_FIELDS = ("mean_v", "sigma_v", "mean_ton", "sigma_ton", "mean_A", "sigma_
                  "mean_MS2_basal", "sigma_MS2_basal", "mean_PP7_basal", "sigma_PP7_basal", "mean_R", "sigma_R",
                  "mean_dR", "sigma_dR", "mean_sigma", "sigma_sigma", "cell_index", "ApprovedFits")  # :151-155
 PLOT_FIELDS = ("t_plot", "MS2_plot", "PP7_plot", "simMS2", "simPP7")                                 # :156-157
-DIAG_FIELDS = ("cell_index", "numChains", "Rhat", "n_eff", "Rhat_max")   # extension, only with numChains > 1
+DIAG_FIELDS = ("cell_index", "numChains", "Rhat", "n_eff", "Rhat_max", "split_Rhat", "ESS")   # extension, only with numChains > 1
+# (Rhat, n_eff: from the device summaries, n_eff = the between-chain estimate; split_Rhat, ESS: from the raw chains — split
+# halves, autocorrelation — empty unless saveChains)
 CHAIN_FIELDS = ("v_chain", "ton_chain", "A_chain", "tau_chain", "MS2_basal_chain", "PP7_basal_chain", "R_chain",
                 "dR_chain", "s2chain")                                                              # :149-150
 _IDX = dict(v=0, tau=1, ton=2, MS2_basal=3, PP7_basal=4, A=5, R=6)
@@ -221,8 +223,13 @@ def fit_dataset(cells_in, o, devices):
             if nchains > 1:
                 # order of theta: [v, tau, ton, MS2_basal, PP7_basal, A, R, dR_1..dR_N]
                 rh, ne = diagnostics.rhat_from_summaries(mu_c, sd_c, n_steps - n_burn + 1)
-                diags.append(dict(cell_index=float(ci + 1), numChains=float(nchains), Rhat=rh.reshape(1, -1),
-                                  n_eff=ne.reshape(1, -1), Rhat_max=float(np.nanmax(rh[:7]))))
+                d = dict(cell_index=float(ci + 1), numChains=float(nchains), Rhat=rh.reshape(1, -1),
+                         n_eff=ne.reshape(1, -1), Rhat_max=float(np.nanmax(rh[:7])), split_Rhat=np.zeros((0, 0)), ESS=np.zeros((0, 0)))
+                if o["saveChains"]:
+                    raw = out["chain"][sl, :, :npar]
+                    d["split_Rhat"] = diagnostics.split_rhat(raw).reshape(1, -1)
+                    d["ESS"] = diagnostics.ess(raw).reshape(1, -1)
+                diags.append(d)
             r = dict(mean_v=mean[0], sigma_v=std[0], mean_tau=mean[1], sigma_tau=std[1], mean_ton=mean[2],
                      sigma_ton=std[2], mean_MS2_basal=mean[3], sigma_MS2_basal=std[3], mean_PP7_basal=mean[4],
                      sigma_PP7_basal=std[4], mean_A=mean[5], sigma_A=std[5], mean_R=mean[6], sigma_R=std[6],
