@@ -232,7 +232,7 @@ def run_reference(args, g):
                 cpu_baseline=dict(value=v, unit=UNIT, cores=last["cores"], kind=last["kind"], sample=last["sample"]),
                 e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 ss_evals_per_s=float(np.mean([x["ss_evals_per_s"] for x in vals])), gpu_launches=0)
-    print(json.dumps(line))
+    return line
 
 
 # ----------------------------------------------------------------------------------- GPU arm
@@ -392,11 +392,10 @@ def run_ours(args, g):
             leg("config5_scale", lambda: config5_leg(local))
         if not args.no_cpu_baseline:
             leg("cpu_baseline", lambda: cpu_baseline(g, args.cpu_sample_seconds, with_config1=True))
-    if rank == 0:
-        print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    return line if rank == 0 else None
 
 
 def config3_leg(cells, g, device, peak_dfma, flush, torch, n_steps, n_burn, fits):
@@ -512,11 +511,17 @@ def ss_kernel_leg(cells, g, peak_dfma, torch):
 
 def main():
     args = parse()
+    # ONE JSON line on stdout: whatever a library prints to file descriptor 1 while the bench runs (NCCL's version banner and
+    # NCCL_DEBUG lines, torchrun notices) goes to stderr, where the driver can still read it
+    sys.stdout.flush()
+    out_fd = os.dup(1)
+    os.dup2(2, 1)
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     g = dict(np.load(GOLDEN))
-    if args.impl == "reference":
-        run_reference(args, g)
-    else:
-        run_ours(args, g)
+    line = run_reference(args, g) if args.impl == "reference" else run_ours(args, g)
+    sys.stdout.flush()
+    if line is not None:
+        os.write(out_fd, (json.dumps(line) + "\n").encode())
 
 
 if __name__ == "__main__":
