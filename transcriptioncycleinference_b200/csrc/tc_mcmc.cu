@@ -2664,14 +2664,9 @@ int tc_mcmc_run(const tc_cells *c, const tc_mcmc_opts *o, int nchains, const int
         CUDA_TRY(cudaMemsetAsync(a.cstate, 0, sizeof(int) * nc, r.st));
         if (use_warp) {
             a.big = 0;
-            // about as many groups as SMs (an 8-GPU partition of config 3: 150 groups on 148 SMs): the fit ends with the
-            // groups that are behind running alone, so the slices are short (measured at 2 392 chains: 0.589 s with 29
-            // slices); many waves of groups balance by themselves
-            if ((nc + WK_WARPS - 1) / WK_WARPS < 4 * sms) sl = ((long long)o->nsimu + 127) / 128;
-            {
-                const char *e = getenv("TC_WARP_SLICES");                       // development switch
-                if (e && atoi(e) > 0) sl = ((long long)o->nsimu + atoi(e) - 1) / atoi(e);
-            }
+            // (more, shorter slices were measured for the one-wave case — 2 392 chains = 150 groups on 148 SMs — and change
+            // nothing: 0.589 s with 29 slices, 0.599 s with 200; what bounds that case is its slowest group, whose slices
+            // are sequential)
             sl = ((sl + unit - 1) / unit) * unit;
             a.seglen = (int)std::max<long long>(sl, unit);
             CUDA_TRY(cudaFuncSetAttribute(dram_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
