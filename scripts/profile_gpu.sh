@@ -1,10 +1,21 @@
 #!/bin/bash
 # Run on the B200 box under gpurun: bench lines + ncu launch list + ncu full captures + HBM traffic -> gpurun_out/
-# usage: bash scripts/profile_gpu.sh <tag> [quick]     (quick: skip the bench lines, captures only)
+# usage: bash scripts/profile_gpu.sh <tag> [quick|traffic]     (quick: skip the bench lines, captures only; traffic: only the
+#        two HBM-traffic captures bench.py's roofline.traffic quotes — rerun after any change of the kernel sources)
 set -x
 R=${1:-r2a}
 mkdir -p gpurun_out
 M=dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum
+LEGS="--no-cpu-baseline --no-config5 --no-config3 --no-writeback"
+if [ "$2" = "traffic" ]; then
+CMD2="python bench.py --steps 1 --warmup 1 $LEGS"
+ncu --metrics $M --clock-control none -k regex:dram_kernel -s 1 -c 1 --csv --log-file gpurun_out/traffic_dram_$R.csv $CMD2 > gpurun_out/ncu_tr_$R.log 2>&1 &&
+python scripts/traffic_json.py gpurun_out/traffic_dram_$R.csv dram_kernel config2 200000 10000 $R
+CMD4="python bench.py --workload config3 --steps 1 --warmup 1 $LEGS"
+ncu --metrics $M --clock-control none -k regex:dram_warp_kernel -s 1 -c 1 --csv --log-file gpurun_out/traffic_warp_$R.csv $CMD4 > gpurun_out/ncu_tr3_$R.log 2>&1 &&
+python scripts/traffic_json.py gpurun_out/traffic_warp_$R.csv dram_warp_kernel config3 20000 10000 $R
+exit 0
+fi
 if [ "$2" != "quick" ]; then
 python bench.py > gpurun_out/bench_$R.json 2> gpurun_out/bench_$R.err || exit 1
 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/bench_ref_$R.json 2>> gpurun_out/bench_$R.err
