@@ -243,3 +243,30 @@ def test_split_rhat_and_ess_from_raw_chains():
     assert np.all(ne / expect < 20) and np.all(ne / expect > 0.05)
     drift = x[:1, :, :1] + np.linspace(0, 3, n)[None, :, None]
     assert diagnostics.split_rhat(drift)[0] > 1.3 and diagnostics.ess(drift)[0] < 0.05 * n
+
+
+def test_headless_curation_writes_approvedfits_back(tmp_path):
+    """curate.ApproveMCMCResults: the reference's ApprovedFits convention (1 / 0 / -1, stored in MCMCresults of the same file,
+    src/ApproveMCMCResults.m:11-15,335) without a display — explicit lists, automatic rules on the fields the current driver
+    writes, 'LoadPrevious' matched on cell_index; every other variable of the file survives."""
+    import scipy.io as sio
+    from transcriptioncycleinference_b200 import curate, mcmc
+    def rec(ci, sigma, app=0.0):
+        r = {f: np.float64(1.0) for f in mcmc.RESULT_FIELDS}
+        r.update(mean_dR=np.zeros((1, 5)), sigma_dR=np.ones((1, 5)), mean_sigma=np.float64(sigma), cell_index=np.float64(ci), ApprovedFits=np.float64(app))
+        return r
+    results = [rec(1, 0.9), rec(2, 5.0), rec(4, 1.1), rec(7, 1.0)]
+    diags = [dict(cell_index=float(c), numChains=4.0, Rhat=np.ones((1, 12)), n_eff=np.ones((1, 12)), Rhat_max=rm,
+                  split_Rhat=np.zeros((0, 0)), ESS=np.zeros((0, 0))) for c, rm in ((1, 1.02), (2, 1.01), (4, 1.8), (7, 1.05))]
+    f = str(tmp_path / "18-Oct-2026-X.mat")
+    sio.savemat(f, dict(MCMCresults=mcmc._struct_array(mcmc.RESULT_FIELDS, results), DatasetName="X",
+                        MCMCplot=np.zeros((1, 4)), MCMCdiagnostics=mcmc._struct_array(mcmc.DIAG_FIELDS, diags)))
+    app = curate.ApproveMCMCResults("file", f, "reject", [4], "maxRhat", 1.1, "maxSigma", 3.0)
+    assert app.tolist() == [1.0, -1.0, -1.0, -1.0]          # ok | noise too large | chains disagree | rejected by hand
+    m = sio.loadmat(f, mat_dtype=True)
+    assert [float(m["MCMCresults"][0, k]["ApprovedFits"].squeeze()) for k in range(4)] == [1.0, -1.0, -1.0, -1.0]
+    assert m["MCMCresults"].dtype.names == mcmc.RESULT_FIELDS and str(m["DatasetName"][0]) == "X" and "MCMCdiagnostics" in m
+    # a later fit of a subset: carry the curation over by cell_index
+    f2 = str(tmp_path / "19-Oct-2026-X.mat")
+    sio.savemat(f2, dict(MCMCresults=mcmc._struct_array(mcmc.RESULT_FIELDS, [rec(7, 1.0), rec(1, 1.0), rec(9, 1.0)]), DatasetName="X"))
+    assert curate.ApproveMCMCResults("file", f2, "LoadPrevious", f, "approve", [3]).tolist() == [-1.0, 1.0, 1.0]
