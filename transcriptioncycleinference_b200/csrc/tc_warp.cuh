@@ -832,9 +832,15 @@ __global__ void __launch_bounds__(WK_THREADS, 1) dram_warp_kernel(const __grid_c
 
         int k = seg == 0 ? 1 : seg * a.seglen;
         int next_adapt = a.adaptint > 0 ? ((k + a.adaptint) / a.adaptint) * a.adaptint : 0x7fffffff;
+#ifdef WK_BAR_EVERY
+        int wk_batch = 0;
+#endif
 #pragma unroll 1
         while (k < k_end) {                                             // the same trip count for every warp of the CTA
             const int g0 = k, gen_upto = min(k + genmax, min(k_end, next_adapt));
+#ifdef WK_BAR_EVERY                                                  // development switch: align the phases only every n-th batch.  Measured
+            if ((wk_batch++ % WK_BAR_EVERY) == 0)                       // (9 568 chains): n = 1 / 2 / 4 -> 55.5 k / 62.9 k / 72.7 k cycles per step
+#endif
             __syncthreads();                                            // phase alignment: generation
             if (active) {
                 WK_PHASE(3);
@@ -842,7 +848,7 @@ __global__ void __launch_bounds__(WK_THREADS, 1) dram_warp_kernel(const __grid_c
                 wk_stage_cell(a.cells, cid, cv);
                 WK_PHASE(0);
             }
-#ifndef WK_NOBAR2
+#if !defined(WK_NOBAR2) && !defined(WK_BAR_EVERY)
             __syncthreads();                                            // phase alignment: the step loop
 #endif
             if (active) WK_PHASE(3);
