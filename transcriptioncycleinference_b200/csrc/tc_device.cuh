@@ -158,25 +158,77 @@ __device__ __forceinline__ double warp_sum(double v)
 // memory (measured: ~2x on the latency of one evaluation).
 extern __shared__ __align__(16) double tc_smem[];
 
+// get4(i, ok, v): elements i .. i+3 (the four consecutive steps a lane owns in the loading scan); ok[e] says whether element
+// e is wanted.  The aligned views fetch them as two 16-byte loads — a lane-stride of 32 bytes costs 2 shared-memory
+// wavefronts per 8 lanes with 16-byte accesses, 4 with 8-byte ones (ncu: the 8-byte pattern was a quarter of all
+// bank conflicts of the samplers) — and may read one element past the last wanted one (always inside the vector).
 struct SmemVec {          // a vector in shared memory
     int off;
     __device__ __forceinline__ double operator[](int i) const { return tc_smem[off + i]; }
+    __device__ __forceinline__ void get4(int i, const bool (&ok)[4], double (&v)[4]) const
+    {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] = ok[e] ? tc_smem[off + i + e] : 0.0;
+    }
 };
-struct SumVec {           // theta = state + proposal increment, both in shared memory; increments are stored
-    int ox, os;           // interleaved (stage 1, stage 2) per parameter, os already includes the stage
-    __device__ __forceinline__ double operator[](int i) const { return tc_smem[ox + i] + tc_smem[os + 2 * i]; }
+struct SmemVecA {         // ... whose element 7 (the first dR) is 16-byte aligned: off is ODD
+    int off;
+    __device__ __forceinline__ double operator[](int i) const { return tc_smem[off + i]; }
+    __device__ __forceinline__ void get4(int i, const bool (&ok)[4], double (&v)[4]) const      // i - 7 a multiple of 4
+    {
+        double2 a = make_double2(0.0, 0.0), b = make_double2(0.0, 0.0);
+        if (ok[0]) a = *reinterpret_cast<const double2 *>(tc_smem + off + i);
+        if (ok[2]) b = *reinterpret_cast<const double2 *>(tc_smem + off + i + 2);
+        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+    }
+};
+struct SumVec {           // theta = state + proposal increment, both in shared memory (the increments of one stage are a plain
+    int ox, os;           // vector); ox and os are ODD, like SmemVecA::off
+    __device__ __forceinline__ double operator[](int i) const { return tc_smem[ox + i] + tc_smem[os + i]; }
+    __device__ __forceinline__ void get4(int i, const bool (&ok)[4], double (&v)[4]) const      // i - 7 a multiple of 4
+    {
+        double2 xa = make_double2(0.0, 0.0), xb = xa, sa = xa, sb = xa;
+        if (ok[0]) { xa = *reinterpret_cast<const double2 *>(tc_smem + ox + i); sa = *reinterpret_cast<const double2 *>(tc_smem + os + i); }
+        if (ok[2]) { xb = *reinterpret_cast<const double2 *>(tc_smem + ox + i + 2); sb = *reinterpret_cast<const double2 *>(tc_smem + os + i + 2); }
+        v[0] = xa.x + sa.x; v[1] = xa.y + sa.y; v[2] = xb.x + sb.x; v[3] = xb.y + sb.y;
+    }
 };
 struct GlobVec {          // a vector in global memory
     const double *p;
     __device__ __forceinline__ double operator[](int i) const { return p[i]; }
+    __device__ __forceinline__ void get4(int i, const bool (&ok)[4], double (&v)[4]) const
+    {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] = ok[e] ? p[i + e] : 0.0;
+    }
 };
 
+// Where the loading scan reads the model grid and its steps: lane l of the warp owns the four consecutive steps
+// 4l .. 4l+3 of a block of 128, so in shared memory tg / dtg are stored PERMUTED inside each block of 128 (a shorter last
+// block: length blen, q = ceil(blen / 4)): step i sits at block + (i & 3) * q + ((i & 127) >> 2).  The four loads of a lane
+// are then lane-contiguous (conflict-free) instead of 32 bytes apart (4 wavefronts per 8-byte load).  The dataset keeps
+// permuted copies (CellsDev::tgp / dtgp, cell c at off[c] + 4 c, (N + 3) & ~3 entries), so staging a cell is a plain copy.
+__host__ __device__ __forceinline__ int cell_perm(int N, int i)
+{
+    const int r0 = i & ~127, rem = N - r0, q = ((rem < 128 ? rem : 128) + 3) >> 2;
+    return r0 + (i & 3) * q + ((i & 127) >> 2);
+}
 struct SmemCell {         // one cell's constants staged in shared memory (offsets into tc_smem)
     int N;
     double d;             // mean(diff(t))                       SumofSquares...m:29
     int o_tg, o_dtg, o_ms2, o_pp7, o_iw, o_ik;
-    __device__ __forceinline__ double tg(int i) const { return tc_smem[o_tg + i]; }     // model grid
-    __device__ __forceinline__ double dtg(int i) const { return tc_smem[o_dtg + i]; }   // tg[i+1]-tg[i]
+    __device__ __forceinline__ double tg(int i) const { return tc_smem[o_tg + cell_perm(N, i)]; }     // model grid (permuted)
+    __device__ __forceinline__ double dtg(int i) const { return tc_smem[o_dtg + cell_perm(N, i)]; }   // tg[i+1]-tg[i] (permuted)
+    // steps r0 + 4 lane + e, e = 0..3, of the block of 128 starting at r0
+    __device__ __forceinline__ void grid4(int r0, int lane, const bool (&ok)[4], double (&t)[4], double (&dt)[4]) const
+    {
+        const int q = (min(128, N - r0) + 3) >> 2, b = r0 + lane;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            t[e] = ok[e] ? tc_smem[o_tg + b + e * q] : 0.0;
+            dt[e] = ok[e] ? tc_smem[o_dtg + b + e * q] : 0.0;
+        }
+    }
     __device__ __forceinline__ double ms2(int i) const { return tc_smem[o_ms2 + i]; }   // data, NaN = missing
     __device__ __forceinline__ double pp7(int i) const { return tc_smem[o_pp7 + i]; }
     __device__ __forceinline__ double iw(int i) const { return tc_smem[o_iw + i]; }     // interp1 weight
@@ -189,24 +241,32 @@ struct GlobCell {         // the same view straight onto the device-resident dat
     const int *p_ik;
     __device__ __forceinline__ double tg(int i) const { return p_tg[i]; }
     __device__ __forceinline__ double dtg(int i) const { return p_dtg[i]; }
+    __device__ __forceinline__ void grid4(int r0, int lane, const bool (&ok)[4], double (&t)[4], double (&dt)[4]) const
+    {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            t[e] = ok[e] ? p_tg[r0 + 4 * lane + e] : 0.0;
+            dt[e] = ok[e] ? p_dtg[r0 + 4 * lane + e] : 0.0;
+        }
+    }
     __device__ __forceinline__ double ms2(int i) const { return p_ms2[i]; }
     __device__ __forceinline__ double pp7(int i) const { return p_pp7[i]; }
     __device__ __forceinline__ double iw(int i) const { return p_iw[i]; }
     __device__ __forceinline__ int ik(int i) const { return p_ik[i]; }
 };
-struct Work {             // one warp's forward-model scratch (offsets into tc_smem), each [N+2]
-    int K, n, S, F1, F2, thr;
+struct Work {             // one warp's forward-model scratch (offsets into tc_smem), each [N+2]; K and S start at ODD offsets:
+    int K, n, S, F1, F2, thr;   // the scan stores K[4l+1 .. 4l+4] / S[...] of lane l as two aligned 16-byte stores
 };
 
-__host__ __device__ inline int work_doubles(int N) { return 5 * (N + 2) + 4 + 1; }
-__host__ __device__ inline int cell_doubles(int N) { return 5 * (N + 1) + (N + 2) / 2 + 1; }
+__host__ __device__ inline int work_doubles(int N) { return 5 * (N + 2) + 4 + 1 + 4; }
+__host__ __device__ inline int cell_doubles(int N) { return 2 * ((N + 3) & ~3) + 3 * (N + 1) + (N + 2) / 2 + 1; }
 
 // carve from offset `o` (doubles); returns the next free offset
 __device__ inline int carve_cell(int o, int N, SmemCell &cv)
 {
     cv.N = N;
-    cv.o_tg = o; o += N + 1;
-    cv.o_dtg = o; o += N + 1;
+    cv.o_tg = o; o += (N + 3) & ~3;
+    cv.o_dtg = o; o += (N + 3) & ~3;
     cv.o_ms2 = o; o += N + 1;
     cv.o_pp7 = o; o += N + 1;
     cv.o_iw = o; o += N + 1;
@@ -217,9 +277,9 @@ __device__ inline int carve_work(int o, int N, Work &w)
 {
     o += o & 1;                                            // 16-byte align (thr is read as int4)
     w.thr = o; o += 4;
-    w.K = o; o += N + 2;
+    w.K = o + 1; o += (N + 4) & ~1;                        // odd start, even length (>= N + 3: a pair store may run one past K[n])
+    w.S = o + 1; o += (N + 4) & ~1;
     w.n = o; o += N + 2;
-    w.S = o; o += N + 2;
     w.F1 = o; o += N + 2;
     w.F2 = o; o += N + 2;
     return o;
@@ -231,25 +291,32 @@ struct CellsDev {        // device-resident packed dataset (one per device)
     const long long *off;
     const double *t, *tg, *dtraw, *dtg, *ms2, *pp7, *iw, *dmean;
     const int *ik;
+    const double *tgp, *dtgp;                      // tg / dtg in the shared-memory order (cell_perm), cell c at off[c] + 4 c
 };
 
-// stage cell `cid` into shared memory (whole CTA); raw_grid selects the raw experimental times
-__device__ inline void load_cell(const CellsDev &cd, int cid, bool raw_grid, SmemCell &cv)
+// copy cell `cid` (model grid) into its shared-memory view, by `nthr` threads of which this is thread `t`
+__device__ __forceinline__ void stage_cell(const CellsDev &cd, int cid, const SmemCell &cv, int t, int nthr)
 {
-    const int N = cv.N;
-    const long long o = cd.off[cid];
-    const double *gr = raw_grid ? cd.t : cd.tg;
-    const double *dg = raw_grid ? cd.dtraw : cd.dtg;
+    const int N = cv.N, N4 = (N + 3) & ~3;
+    const long long o = cd.off[cid], op = o + 4LL * cid;
     int *ikp = reinterpret_cast<int *>(tc_smem + cv.o_ik);
-#pragma unroll 1
-    for (int i = threadIdx.x; i < N; i += blockDim.x) {
-        tc_smem[cv.o_tg + i] = gr[o + i];
-        tc_smem[cv.o_dtg + i] = dg[o + i];
-        tc_smem[cv.o_ms2 + i] = cd.ms2[o + i];
-        tc_smem[cv.o_pp7 + i] = cd.pp7[o + i];
-        tc_smem[cv.o_iw + i] = cd.iw[o + i];
-        ikp[i] = cd.ik[o + i];
+#pragma unroll 2
+    for (int i = t; i < N4; i += nthr) {
+        tc_smem[cv.o_tg + i] = cd.tgp[op + i];
+        tc_smem[cv.o_dtg + i] = cd.dtgp[op + i];
+        if (i < N) {
+            tc_smem[cv.o_ms2 + i] = cd.ms2[o + i];
+            tc_smem[cv.o_pp7 + i] = cd.pp7[o + i];
+            tc_smem[cv.o_iw + i] = cd.iw[o + i];
+            ikp[i] = cd.ik[o + i];
+        }
     }
+}
+
+// stage cell `cid` (model grid) into shared memory (whole CTA)
+__device__ inline void load_cell(const CellsDev &cd, int cid, SmemCell &cv)
+{
+    stage_cell(cd, cid, cv, threadIdx.x, blockDim.x);
     cv.d = cd.dmean[cid];
 }
 __device__ inline GlobCell view_cell(const CellsDev &cd, int cid, bool raw_grid)
@@ -317,7 +384,7 @@ __device__ __noinline__ void scan_counts_sequential(Cell cv, Vec th, double R, d
 #endif
 template <class Cell, class Vec>
 __device__ __forceinline__ void scan_counts(const Cell &cv, const Vec &th, double R, double ton, const Work &w,
-                                            bool force_sequential)
+                                            bool force_sequential, bool want_n)
 {
     const int lane = threadIdx.x & 31;
     const int n = cv.N - 1;                        // increments i = 0..n-1
@@ -329,9 +396,16 @@ __device__ __forceinline__ void scan_counts(const Cell &cv, const Vec &th, doubl
 #pragma unroll 1
         for (int r0 = 0; r0 < n; r0 += 128) {
             const int i0 = r0 + 4 * lane;
-            double p[4];
+            const bool ok[4] = {i0 < n, i0 + 1 < n, i0 + 2 < n, i0 + 3 < n};
+            double p[4], thv[4], tgv[4], dtv[4];
+            th.get4(7 + i0, ok, thv);
+            cv.grid4(r0, lane, ok, tgv, dtv);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) p[e] = i0 + e < n ? load_increment(cv, th, i0 + e, R, ton) : 0.0;
+            for (int e = 0; e < 4; ++e) {                  // load_increment(), on the values fetched above
+                double r = R + thv[e];
+                r = r < 0.0 ? 0.0 : r;
+                p[e] = (ok[e] && !(tgv[e] < ton)) ? __dmul_rn(r, dtv[e]) : 0.0;
+            }
             p[1] = __dadd_rn(p[0], p[1]); p[2] = __dadd_rn(p[1], p[2]); p[3] = __dadd_rn(p[2], p[3]);
             double t = p[3];                       // inclusive scan of the lane totals
 #pragma unroll
@@ -350,15 +424,15 @@ __device__ __forceinline__ void scan_counts(const Cell &cv, const Vec &th, doubl
                 f[e] = floor(c);
                 const double fr = c - f[e];
                 // c == 0: every increment so far is exactly 0 (they are all >= 0): exact in any order
-                risky |= (i0 + e < n) && (c != 0.0) && (fr < 1e-7 || fr > 1.0 - 1e-7);
+                risky |= ok[e] && (c != 0.0) && (fr < 1e-7 || fr > 1.0 - 1e-7);
             }
             double fl = __shfl_up_sync(0xffffffffu, f[3], 1);      // floor at the end of the previous lane
             if (lane == 0) fl = fprev;
             const double nn0 = f[0] - fl, nn1 = f[1] - f[0], nn2 = f[2] - f[1], nn3 = f[3] - f[2];
-            const int q0 = i0 < n ? i0 * (int)nn0 : 0;
-            const int q1 = q0 + (i0 + 1 < n ? (i0 + 1) * (int)nn1 : 0);
-            const int q2 = q1 + (i0 + 2 < n ? (i0 + 2) * (int)nn2 : 0);
-            const int q3 = q2 + (i0 + 3 < n ? (i0 + 3) * (int)nn3 : 0);
+            const int q0 = ok[0] ? i0 * (int)nn0 : 0;
+            const int q1 = q0 + (ok[1] ? (i0 + 1) * (int)nn1 : 0);
+            const int q2 = q1 + (ok[2] ? (i0 + 2) * (int)nn2 : 0);
+            const int q3 = q2 + (ok[3] ? (i0 + 3) * (int)nn3 : 0);
             int ts = q3;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -369,10 +443,22 @@ __device__ __forceinline__ void scan_counts(const Cell &cv, const Vec &th, doubl
             int exS = __shfl_up_sync(0xffffffffu, ts, 1);
             if (lane == 0) exS = 0;
             exS += carryS;
-            if (i0 < n) { tc_smem[w.K + i0 + 1] = f[0]; tc_smem[w.n + i0] = nn0; tc_smem[w.S + i0 + 1] = (double)(exS + q0); }
-            if (i0 + 1 < n) { tc_smem[w.K + i0 + 2] = f[1]; tc_smem[w.n + i0 + 1] = nn1; tc_smem[w.S + i0 + 2] = (double)(exS + q1); }
-            if (i0 + 2 < n) { tc_smem[w.K + i0 + 3] = f[2]; tc_smem[w.n + i0 + 2] = nn2; tc_smem[w.S + i0 + 3] = (double)(exS + q2); }
-            if (i0 + 3 < n) { tc_smem[w.K + i0 + 4] = f[3]; tc_smem[w.n + i0 + 3] = nn3; tc_smem[w.S + i0 + 4] = (double)(exS + q3); }
+            // K[i0+1 .. i0+4], S[...]: w.K / w.S are odd, so the pairs are 16-byte aligned; the second element of a pair may
+            // lie one past the last step (steps beyond n add exactly 0: it repeats the last floor / moment, and nobody reads it)
+            if (ok[0]) {
+                *reinterpret_cast<double2 *>(tc_smem + w.K + i0 + 1) = make_double2(f[0], f[1]);
+                *reinterpret_cast<double2 *>(tc_smem + w.S + i0 + 1) = make_double2((double)(exS + q0), (double)(exS + q1));
+            }
+            if (ok[2]) {
+                *reinterpret_cast<double2 *>(tc_smem + w.K + i0 + 3) = make_double2(f[2], f[3]);
+                *reinterpret_cast<double2 *>(tc_smem + w.S + i0 + 3) = make_double2((double)(exS + q2), (double)(exS + q3));
+            }
+            if (want_n) {                                           // cohort sizes: only the pairs algorithm reads them
+                if (ok[0]) tc_smem[w.n + i0] = nn0;
+                if (ok[1]) tc_smem[w.n + i0 + 1] = nn1;
+                if (ok[2]) tc_smem[w.n + i0 + 2] = nn2;
+                if (ok[3]) tc_smem[w.n + i0 + 3] = nn3;
+            }
             fprev = __shfl_sync(0xffffffffu, f[3], 31);            // steps beyond n add exactly 0: lane 31 holds the block's last floor
             carry = __dadd_rn(carry, tot);
             carryS += totS;
@@ -460,7 +546,7 @@ __device__ __noinline__ double ss_eval(const tc_construct &C, Cell cv, Vec th, W
 #endif
     const double vd = v * cv.d, inv_vd = 1.0 / vd;              // started here: the division overlaps with the scan
     // (a) loaded-polymerase counts K and cohort sizes n
-    scan_counts(cv, th, R, ton, w, seq_scan);
+    scan_counts(cv, th, R, ton, w, seq_scan, algo != TC_ALGO_TOEPLITZ);
     __syncwarp();
     SS_MARK(0);
     // (b) fluorescence per time point, one loop set at a time: the basal clamp sits inside the

@@ -110,7 +110,9 @@ __global__ void __launch_bounds__(SS_THREADS, SS_MIN_CTAS) ss_batch_kernel(const
 __global__ void __launch_bounds__(SS_THREADS, 2) ss_stream_kernel(const __grid_constant__ SsArgs a)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int o_cell = warp * (a.csz + 2 * a.ld2 + a.wsz), o_th = o_cell + a.csz, o_work = o_th + 2 * a.ld2;
+    // theta buffers start at an ODD offset: element 7 (the first dR) is then 16-byte aligned and the loading scan fetches
+    // the four steps of a lane with two 16-byte loads (SmemVecA)
+    const int o_cell = warp * (a.csz + 2 * a.ld2 + 2 + a.wsz), o_th = o_cell + a.csz + 1, o_work = o_cell + a.csz + 2 + 2 * a.ld2;
     const long long nw = (long long)gridDim.x * SS_WARPS, wi = (long long)blockIdx.x * SS_WARPS + warp;
     const long long chunk = (a.nbatch + nw - 1) / nw, b0 = wi * chunk, b1 = min(a.nbatch, b0 + chunk);
     const unsigned sth = (unsigned)__cvta_generic_to_shared(tc_smem + o_th);
@@ -135,24 +137,14 @@ __global__ void __launch_bounds__(SS_THREADS, 2) ss_stream_kernel(const __grid_c
             const int N = a.cells.N[cid];
             carve_cell(o_cell, N, cv);
             carve_work(o_work, N, w);
-            const long long o = a.cells.off[cid];
-            int *ikp = reinterpret_cast<int *>(tc_smem + cv.o_ik);
-#pragma unroll 2
-            for (int i = lane; i < N; i += 32) {
-                tc_smem[cv.o_tg + i] = a.cells.tg[o + i];
-                tc_smem[cv.o_dtg + i] = a.cells.dtg[o + i];
-                tc_smem[cv.o_ms2 + i] = a.cells.ms2[o + i];
-                tc_smem[cv.o_pp7 + i] = a.cells.pp7[o + i];
-                tc_smem[cv.o_iw + i] = a.cells.iw[o + i];
-                ikp[i] = a.cells.ik[o + i];
-            }
+            stage_cell(a.cells, cid, cv, lane, 32);
             cv.d = a.cells.dmean[cid];
             cur = cid;
         }
         if (more) asm volatile("cp.async.wait_group 1;" ::: "memory");
         else asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();
-        const double ss = ss_eval(a.cons, cv, SmemVec{o_th + buf * a.ld2}, w, a.algo, false, nullptr, nullptr);
+        const double ss = ss_eval(a.cons, cv, SmemVecA{o_th + buf * a.ld2}, w, a.algo, false, nullptr, nullptr);
         if (lane == 0) a.ss_out[b] = ss;
         __syncwarp();                                           // the buffer is free for the copy issued two items on
     }
@@ -203,7 +195,11 @@ __host__ __device__ inline int chol_ws_doubles(int n)
     return 16 * T + (T + 3) / 4 + 2;                      // tiles + the u16 tile table
 }
 
-__host__ __device__ inline int dram_slot(int N) { return 2 * (7 + N) + 2 + 8; }
+// one ring slot = [pad | increments of stage 1: s1 doubles | of stage 2: s1 | pad | 8 per-step scalars]; the two increment
+// vectors start at ODD offsets (slot + 1, slot + 1 + s1, s1 even): element 7, the first dR, is then 16-byte aligned for the
+// loading scan's vector loads (SumVec::get4)
+__host__ __device__ inline int dram_s1(int N) { return (7 + N + 1) & ~1; }
+__host__ __device__ inline int dram_slot(int N) { return 2 * dram_s1(N) + 2 + 8; }
 // Two shared-memory layouts:
 //   regular (big = 0): ring of RING = 16 slots, all 10 per-parameter vectors in shared memory, the Cholesky workspace
 //                      of the proposal factor inside ring + per-warp areas (N up to ~210);
@@ -872,7 +868,7 @@ struct ChainState {
 // Immutable per-chain context, built once in shared memory so that the out-of-line phases below
 // (kept out of line to keep the hot loop inside the instruction cache) can share it.
 struct ChainCtx {
-    int N, npar, npad, ld, slot_sz, wsz, ch, first_row, nstore, ring_mask, uni;
+    int N, npar, npad, ld, slot_sz, s1, wsz, ch, first_row, nstore, ring_mask, uni;
     double blk[4];                                      // uni: common lo, hi, mu, 1/sig of the parameters >= 7 (the dR block)
     unsigned long long uid;
     double adascale, inv_dr, chi_d, chi_c;              // chi_d, chi_c: Marsaglia-Tsang constants of chi2(N0 + 2 N)
@@ -883,6 +879,7 @@ struct ChainCtx {
     double *ring, *x, *lo, *hi, *mu, *pinv, *wmean, *wM2, *rdiag, *mb, *dm, *U;
     double *gRb, *gM2, *gRows, *gWts, *cmean;
     __device__ __forceinline__ int slot_o(int step) const { return o_ring + (step & ring_mask) * slot_sz; }
+    __device__ __forceinline__ int slot_i(int step) const { return o_ring + (step & ring_mask) * slot_sz + 1; }   // stage-1 increments (stage 2: + s1)
     __device__ __forceinline__ double *slot_d(int step) const { return tc_smem + o_ring + (step & ring_mask) * slot_sz; }
     __device__ __forceinline__ double *slot_sc(int step) const { return tc_smem + o_ring + (step & ring_mask) * slot_sz + (slot_sz - 8); }
 };
@@ -890,7 +887,7 @@ struct ChainCtx {
 // The chain rows [r0, r1) all equal the current state x (a run: the accept at row r0, then rejections).
 // Fold the run into the summaries (Welford with multiplicity; rows >= n_burn-1 only), the optional chain
 // storage, and the distinct-row buffer of the current covariance block (row + weight); then, when
-// so >= 0, move the state: x += increment at tc_smem[so + 2 i].  Every thread owns the indices i = tid, tid+256, ..
+// so >= 0, move the state: x += increment at tc_smem[so + i].  Every thread owns the indices i = tid, tid+256, ..
 // so the whole thing is one pass.  The caller accounts for wcnt / ndist with the same formulas.
 __device__ __noinline__ void flush_run(const RunArgs &a, const ChainCtx &cx, int r0, int r1, double wcnt, int ndist, int so, int t0)
 {
@@ -919,7 +916,7 @@ __device__ __noinline__ void flush_run(const RunArgs &a, const ChainCtx &cx, int
             grow[i] = xo;
             tc_smem[omb + i] = fma((double)m_c, xo, tc_smem[omb + i]);
         }
-        if (so >= 0) tc_smem[ox + i] = xo + tc_smem[so + 2 * i];
+        if (so >= 0) tc_smem[ox + i] = xo + tc_smem[so + i];
     }
     if (cov && tid == 0) cx.gWts[ndist] = (double)m_c;
 }
@@ -1085,13 +1082,13 @@ __device__ __noinline__ void gen_increments_tma(const ChainCtx &cx, int g0, int 
 #undef GENB_ISSUE
     __syncthreads();                                                // every warp is done reading Z: the increments overwrite it
     if (ar < nnew) {
-        const int oo = cx.slot_o(g0 + ar);
+        const int oo = cx.slot_i(g0 + ar), o2 = oo + cx.s1;
         const double inv_dr = cx.inv_dr;
 #pragma unroll
         for (int j = 0; j < GENB_MAXT; ++j) {
             const int jc = 8 * (warp + SPEC * (mcnt - 1 - j)) + 2 * ak;     // accumulator j = the j-th tile from the top
-            if (j < mcnt && jc < npar) *reinterpret_cast<double2 *>(tc_smem + oo + 2 * jc) = make_double2(acc[j][0], acc[j][2] * inv_dr);
-            if (j < mcnt && jc + 1 < npar) *reinterpret_cast<double2 *>(tc_smem + oo + 2 * jc + 2) = make_double2(acc[j][1], acc[j][3] * inv_dr);
+            if (j < mcnt && jc < npar) { tc_smem[oo + jc] = acc[j][0]; tc_smem[o2 + jc] = acc[j][2] * inv_dr; }
+            if (j < mcnt && jc + 1 < npar) { tc_smem[oo + jc + 1] = acc[j][1]; tc_smem[o2 + jc + 1] = acc[j][3] * inv_dr; }
         }
     }
     __syncthreads();
@@ -1199,12 +1196,19 @@ __device__ __noinline__ void generate(const RunArgs &a, const ChainCtx &cx, int 
 #pragma unroll 1
         for (int sidx = 0; sidx < nnew; ++sidx) {
             const double2 *dz = reinterpret_cast<const double2 *>(ZROW(sidx));
-            double2 *out = reinterpret_cast<double2 *>(cx.slot_d(g0 + sidx));
-#pragma unroll 1
-            for (int j = tid; j < npar; j += DRAM_THREADS) {
-                const double r = cx.rdiag[j];
-                const double2 zz = dz[j];
-                out[j] = make_double2(zz.x * r, zz.y * (r * cx.inv_dr));
+            const int o1 = cx.slot_i(g0 + sidx), o2 = o1 + cx.s1;
+            // (big layout: Z is this very slot, interleaved; every thread reads all its pairs before anyone stores)
+            double2 zz[(7 + 414 + DRAM_THREADS - 1) / DRAM_THREADS];
+#pragma unroll
+            for (int m = 0; m < (int)(sizeof(zz) / sizeof(zz[0])); ++m) { const int j = tid + m * DRAM_THREADS; if (j < npar) zz[m] = dz[j]; }
+            if (big || TC_TMA_ALL) __syncthreads();
+#pragma unroll
+            for (int m = 0; m < (int)(sizeof(zz) / sizeof(zz[0])); ++m) {
+                const int j = tid + m * DRAM_THREADS;
+                if (j < npar) {
+                    const double r = cx.rdiag[j];
+                    tc_smem[o1 + j] = zz[m].x * r; tc_smem[o2 + j] = zz[m].y * (r * cx.inv_dr);
+                }
             }
         }
     } else if (big || TC_TMA_ALL) {
@@ -1219,7 +1223,7 @@ __device__ __noinline__ void generate(const RunArgs &a, const ChainCtx &cx, int 
         // tile of round r = NT-1 - (8 r + (r odd ? 7-w : w)).
         const int oa = cx.o_U + ar * zs;                              // A row of this lane (offset into tc_smem); rows >= nnew hold
                                                                       // stale scratch: their results are dropped
-        const int oo = cx.slot_o(g0 + ar);                            // output slot of this lane's row
+        const int oo = cx.slot_i(g0 + ar), oo2 = oo + cx.s1;          // output vectors (stage 1, stage 2) of this lane's row
         const bool rowok = ar < nnew;
         const int nt4 = (npar + 3) >> 2;
         const int inner = 4 * ak + (ar & 3);                          // position of (row 4kk+ak, column 8nt+ar) inside its 4x4 tile
@@ -1283,8 +1287,8 @@ __device__ __noinline__ void generate(const RunArgs &a, const ChainCtx &cx, int 
             const double acc2 = (acc[0][2] + acc[1][2]) + (acc[2][2] + acc[3][2]), acc3 = (acc[0][3] + acc[1][3]) + (acc[2][3] + acc[3][3]);
             const int jc = 8 * nt + 2 * ak;
             if (rowok) {
-                if (jc < npar) *reinterpret_cast<double2 *>(tc_smem + oo + 2 * jc) = make_double2(acc0, acc2 * inv_dr);
-                if (jc + 1 < npar) *reinterpret_cast<double2 *>(tc_smem + oo + 2 * jc + 2) = make_double2(acc1, acc3 * inv_dr);
+                if (jc < npar) { tc_smem[oo + jc] = acc0; tc_smem[oo2 + jc] = acc2 * inv_dr; }
+                if (jc + 1 < npar) { tc_smem[oo + jc + 1] = acc1; tc_smem[oo2 + jc + 1] = acc3 * inv_dr; }
             }
         }
         SUBP(2);
@@ -1314,13 +1318,12 @@ __device__ __forceinline__ void cand_bounds_t(const ChainCtx &cx, int k, int C, 
     const double blo = cx.blk[0], bhi = cx.blk[1], bmu = cx.blk[2], bpinv = cx.blk[3];
 #pragma unroll 1
     for (int c = warp; c < C; c += SPEC) {
-        const double2 *dd = reinterpret_cast<const double2 *>(tc_smem + cx.slot_o(k + c));
+        const int o1 = cx.slot_i(k + c), o2 = o1 + cx.s1;
         double pr1 = 0.0, pr2 = 0.0;
         unsigned oob = 0;
 #pragma unroll 4
         for (int j = lane; j < npar; j += 32) {
-            const double2 dj = dd[j];
-            const double xj = tc_smem[ox + j], a1 = xj + dj.x, a2 = xj + dj.y;
+            const double xj = tc_smem[ox + j], a1 = xj + tc_smem[o1 + j], a2 = xj + tc_smem[o2 + j];
             double lo, hi, mu, pinv;
             if (UNI && j >= 8) { lo = blo; hi = bhi; mu = bmu; pinv = bpinv; }
             else {
@@ -1669,13 +1672,14 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
             o += o & 1;
             if (tid == 0) {
                 cx.N = N; cx.npar = npar; cx.npad = (npar + 3) & ~3; cx.ld = a.ld;
-                cx.slot_sz = dram_slot(N); cx.wsz = a.wsz; cx.ch = ch; cx.first_row = a.n_burn - 1;
+                cx.slot_sz = dram_slot(N); cx.s1 = dram_s1(N); cx.wsz = a.wsz; cx.ch = ch; cx.first_row = a.n_burn - 1;
                 cx.nstore = a.nsimu - (a.n_burn - 1);
                 cx.uid = a.chain_uid ? a.chain_uid[ch] : (unsigned long long)ch;
                 cx.adascale = a.adascale > 0.0 ? a.adascale : 2.4 / sqrt((double)npar);
                 cx.inv_dr = 1.0 / a.drscale;
                 chi2_consts(a.N0 + 2.0 * N, cx.chi_d, cx.chi_c);
                 cx.cv = cv; cx.cv.d = a.cells.dmean[cid];
+                o |= 1;                                             // x at an ODD offset: x[7] is 16-byte aligned (SumVec::get4)
                 cx.o_x = o;
                 cx.x = tc_smem + o; o += npar;
                 cx.o_lo = a.big ? -1 : o;                           // lo, hi, mu consecutive
@@ -1701,7 +1705,7 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
                 cx.gWts = a.gWts ? a.gWts + (size_t)ch * (size_t)a.adaptint : nullptr;
                 cx.cmean = a.gCmean ? a.gCmean + (size_t)ch * a.ld : nullptr;
             }
-            load_cell(a.cells, cid, false, cv);
+            load_cell(a.cells, cid, cv);
         }
         __syncthreads();
         // this warp's private forward-model scratch
@@ -1785,7 +1789,7 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
 
         if (seg == 0) {
             // ---- row 0: x0 (opens the first run)
-            const double ss0 = ss_eval(a.cons, cx.cv, SumVec{cx.o_x, cx.o_ring}, w, a.algo, false, nullptr, nullptr);   // every warp, same value
+            const double ss0 = ss_eval(a.cons, cx.cv, SumVec{cx.o_x, cx.slot_i(0)}, w, a.algo, false, nullptr, nullptr);   // every warp, same value
             double sp = 0.0;
 #pragma unroll 1
             for (int i = lane; i < npar; i += 32) { const double e = (cx.x[i] - cx.mu[i]) * cx.pinv[i]; sp += e * e; }
@@ -1853,7 +1857,7 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
                 const int mc = __ffs(tmask) - 1;
                 const int e0 = __shfl_sync(0xffffffffu, exc, mc), ob = __shfl_sync(0xffffffffu, c_oob, mc);
                 const int stage = (warp == e0 && !(ob & 1)) ? 0 : 1;
-                const double v = ss_eval(a.cons, cx.cv, SumVec{cx.o_x, cx.slot_o(k + mc) + stage}, w, a.algo, false, nullptr, nullptr);
+                const double v = ss_eval(a.cons, cx.cv, SumVec{cx.o_x, cx.slot_i(k + mc) + stage * cx.s1}, w, a.algo, false, nullptr, nullptr);
                 if (lane == 0) s_ssv[2 * mc + stage] = v;
             }
             SUBP(18);
@@ -1912,7 +1916,7 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
             SUBP(20);
             if (accd) {
                 // close the run of the old state at row r_acc and move x by the accepted increment
-                flush_run(a, cx, run_r0, r_acc, wcnt, ndist, cx.slot_o(r_acc) + (acc_t == 2 ? 1 : 0), 32);
+                flush_run(a, cx, run_r0, r_acc, wcnt, ndist, cx.slot_i(r_acc) + (acc_t == 2 ? cx.s1 : 0), 32);
             }
             SUBP(21);
             if (warp == 0) {
@@ -2121,7 +2125,7 @@ struct tc_cells {
     int ncells = 0, Nmax = 0;
     std::vector<int> N;
     std::vector<long long> off;
-    std::vector<double> t, tg, dtraw, dtg, ms2, pp7, iw, dmean;
+    std::vector<double> t, tg, dtraw, dtg, ms2, pp7, iw, dmean, tgp, dtgp;
     std::vector<int> ik;
     std::vector<DevCells> dev;
 };
@@ -2294,6 +2298,14 @@ int tc_cells_create(const tc_construct *construct, int ncells, const int32_t *N,
             c->iw[c->off[ci] + j] = (z - G[k]) / (G[k + 1] - G[k]);
         }
     }
+    // tg / dtg in the order the kernels keep them in shared memory (cell_perm): cell ci at off[ci] + 4 ci
+    c->tgp.assign(tot + 4LL * ncells, 0.0); c->dtgp.assign(tot + 4LL * ncells, 0.0);
+    for (int ci = 0; ci < ncells; ++ci)
+        for (int i = 0; i < N[ci]; ++i) {
+            const long long dst = c->off[ci] + 4LL * ci + cell_perm(N[ci], i);
+            c->tgp[dst] = c->tg[c->off[ci] + i];
+            c->dtgp[dst] = c->dtg[c->off[ci] + i];
+        }
     c->dev.resize(ndev);
     for (int d = 0; d < ndev; ++d) {
         DevCells &dc = c->dev[d];
@@ -2306,7 +2318,8 @@ int tc_cells_create(const tc_construct *construct, int ncells, const int32_t *N,
             (rc = upload(dc, c->tg, dc.d.tg)) || (rc = upload(dc, c->dtraw, dc.d.dtraw)) ||
             (rc = upload(dc, c->dtg, dc.d.dtg)) || (rc = upload(dc, c->ms2, dc.d.ms2)) ||
             (rc = upload(dc, c->pp7, dc.d.pp7)) || (rc = upload(dc, c->iw, dc.d.iw)) ||
-            (rc = upload(dc, c->dmean, dc.d.dmean)) || (rc = upload(dc, c->ik, dc.d.ik))) {
+            (rc = upload(dc, c->dmean, dc.d.dmean)) || (rc = upload(dc, c->ik, dc.d.ik)) ||
+            (rc = upload(dc, c->tgp, dc.d.tgp)) || (rc = upload(dc, c->dtgp, dc.d.dtgp))) {
             std::string m = g_err;
             tc_cells_destroy(c);
             return fail(rc, m);
@@ -2362,7 +2375,7 @@ static int launch_ss(const tc_cells *c, const DevCells *dc, long long nbatch, co
         // 52.7 M evaluations/s there, 34.2 M with 16 warps/SM here).
         a.csz = (cell_doubles(c->Nmax) + 1) & ~1;
         a.ld2 = (ld + 1) & ~1;
-        const size_t smem2 = sizeof(double) * (size_t)(a.csz + 2 * a.ld2 + a.wsz) * SS_WARPS;
+        const size_t smem2 = sizeof(double) * (size_t)(a.csz + 2 * a.ld2 + 2 + a.wsz) * SS_WARPS;
         int optin = 0;
         CUDA_TRY(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dc->device));
         if (2 * (smem2 + 1024) <= (size_t)optin + 1024) {

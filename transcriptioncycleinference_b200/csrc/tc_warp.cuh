@@ -39,7 +39,8 @@ __host__ __device__ inline int wk_overlay(int N)
     if (need < ad) need = ad;
     return (need + 1) & ~1;
 }
-__host__ __device__ inline int wk_region(int N) { return 2 * wk_ldp(N) + wk_overlay(N); }
+// the two theta slots start at ODD offsets (region + 1, region + 1 + ldp): element 7, the first dR, is 16-byte aligned (SmemVecA)
+__host__ __device__ inline int wk_region(int N) { return 2 * wk_ldp(N) + 2 + wk_overlay(N); }
 
 // per-warp mutable book-keeping in shared memory (lane 0 writes; everything hot lives in registers)
 struct WkState {
@@ -69,16 +70,20 @@ __shared__ WkState wk_st[WK_WARPS];
 __device__ __forceinline__ void wk_stage_cell(const CellsDev &cd, int cid, const SmemCell &cv)
 {
     const int N = cv.N, lane = threadIdx.x & 31;
-    const long long o = cd.off[cid];
+    const long long o = cd.off[cid], op = o + 4LL * cid;           // tgp / dtgp: the grid in its shared-memory order (cell_perm)
     int *ikp = reinterpret_cast<int *>(tc_smem + cv.o_ik);
 #pragma unroll 5
     for (int i = lane; i < N; i += 32) {
-        tc_smem[cv.o_tg + i] = cd.tg[o + i];
-        tc_smem[cv.o_dtg + i] = cd.dtg[o + i];
+        tc_smem[cv.o_tg + i] = cd.tgp[op + i];
+        tc_smem[cv.o_dtg + i] = cd.dtgp[op + i];
         tc_smem[cv.o_ms2 + i] = cd.ms2[o + i];
         tc_smem[cv.o_pp7 + i] = cd.pp7[o + i];
         tc_smem[cv.o_iw + i] = cd.iw[o + i];
         ikp[i] = cd.ik[o + i];
+    }
+    if (lane < 3 && N + lane < ((N + 3) & ~3)) {                    // the permuted order spreads N entries over (N + 3) & ~3 places
+        tc_smem[cv.o_tg + N + lane] = cd.tgp[op + N + lane];
+        tc_smem[cv.o_dtg + N + lane] = cd.dtgp[op + N + lane];
     }
     __syncwarp();
 }
@@ -714,7 +719,7 @@ __global__ void __launch_bounds__(WK_THREADS, 1) dram_warp_kernel(const __grid_c
         double *gst = nullptr;
         SmemCell cv{};
         Work w{};
-        int ox = o_reg, ob = o_reg + ldp;
+        int ox = o_reg + 1, ob = o_reg + 1 + ldp;
         double ss = 0.0, pri = 0.0, sig2 = a.sigma2_0;
         int r_diag = 1, run_r0 = 0, ndist = 0;
         bool bad0 = false, uni = false;
@@ -725,7 +730,7 @@ __global__ void __launch_bounds__(WK_THREADS, 1) dram_warp_kernel(const __grid_c
             if (lane == 0) {
                 c.N = N; c.npar = npar; c.ld = a.ld; c.ldp = ldp; c.ch = ch; c.first_row = a.n_burn - 1;
                 c.nstore = a.nsimu - (a.n_burn - 1);
-                c.o_s0 = o_reg; c.o_ov = o_reg + 2 * ldp; c.o_work = c.o_ov + wk_cell_sz(a.ld - 7);
+                c.o_s0 = o_reg + 1; c.o_ov = o_reg + 2 * ldp + 2; c.o_work = c.o_ov + wk_cell_sz(a.ld - 7);
                 c.uid = a.chain_uid ? a.chain_uid[ch] : (unsigned long long)ch;
                 c.inv_dr = 1.0 / a.drscale;
                 c.adascale = a.adascale > 0.0 ? a.adascale : 2.4 / sqrt((double)npar);
@@ -774,7 +779,7 @@ __global__ void __launch_bounds__(WK_THREADS, 1) dram_warp_kernel(const __grid_c
                 }
                 __syncwarp();
                 // row 0: x0
-                ss = ss_eval(a.cons, cv, SmemVec{ox}, w, a.algo, false, nullptr, nullptr);
+                ss = ss_eval(a.cons, cv, SmemVecA{ox}, w, a.algo, false, nullptr, nullptr);
                 double sp = 0.0;
 #pragma unroll 1
                 for (int i = lane; i < npar; i += 32) { const double e = (tc_smem[ox + i] - __ldg(c.mu + i)) * __ldcg(c.pinv + i); sp += e * e; }
@@ -866,7 +871,7 @@ __global__ void __launch_bounds__(WK_THREADS, 1) dram_warp_kernel(const __grid_c
                 if (o1) { fl |= TC_FL_OOB1; noob = 1; pr1 = 0.0; }
                 else {
                     WK_T0;
-                    ss1 = ss_eval(a.cons, cv, SmemVec{ob}, w, a.algo, false, nullptr, nullptr);
+                    ss1 = ss_eval(a.cons, cv, SmemVecA{ob}, w, a.algo, false, nullptr, nullptr);
                     WK_T1(7);
                     nev = 1;
                     x12 = -0.5 * ((ss1 - ss) / sig2 + pr1 - pri);
@@ -881,7 +886,7 @@ __global__ void __launch_bounds__(WK_THREADS, 1) dram_warp_kernel(const __grid_c
                     if (o2) { fl |= TC_FL_OOB2; ++noob; }
                     else {
                         WK_T0;
-                        const double ss2 = ss_eval(a.cons, cv, SmemVec{ob}, w, a.algo, false, nullptr, nullptr);
+                        const double ss2 = ss_eval(a.cons, cv, SmemVecA{ob}, w, a.algo, false, nullptr, nullptr);
                         WK_T1(7);
                         ++nev;
                         if (resolve_dr_v(-0.5 * (s_n1 - s_n0), s_u2, o1, x12, pr1, pr2, ss1, ss2, ss, pri, sig2)) { acc = 2; fl |= TC_FL_STAGE2; ssn = ss2; prin = pr2; }
