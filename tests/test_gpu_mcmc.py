@@ -117,6 +117,30 @@ def test_results_independent_of_partition(gpu_cells):
     assert np.array_equal(full["sig"][2], sub["sig"][0])
 
 
+def test_solo_sm_scheduling_is_transparent(gpu_cells, monkeypatch):
+    """With about as many chains as CTA slots the CTA-per-chain kernel lets a lagging chain take its SM (the neighbour CTA
+    gives way at its next slice boundary, csrc/tc_mcmc.cu: smctl).  That is scheduling only: 299 chains x 6 000 steps give
+    bit-identical summaries and counters with the rule off (TC_SOLO_LAG=0), at its default, and at its most eager setting
+    with many short slices."""
+    from transcriptioncycleinference_b200 import _lib
+    cc = np.arange(299, dtype=np.int32)
+    inputs = _setup(gpu_cells, cc, 77)
+    opts = _lib.default_opts(nsimu=6000, burnintime=1000, n_burn=1000)
+    outs = []
+    for lag, nseg in (("0", "32"), (None, None), ("1", "512")):
+        for k, v in (("TC_SOLO_LAG", lag), ("TC_NSEG", nseg)):
+            if v is None:
+                monkeypatch.delenv(k, raising=False)
+            else:
+                monkeypatch.setenv(k, v)
+        outs.append(gpu_cells.mcmc_run(opts, cc, *inputs))
+    for o in outs[1:]:
+        assert np.array_equal(o["mean"], outs[0]["mean"])
+        assert np.array_equal(o["std"], outs[0]["std"])
+        assert np.array_equal(o["sig"], outs[0]["sig"])
+        assert np.array_equal(o["counters"][:, :8], outs[0]["counters"][:, :8])      # the rest are cycle counts
+
+
 def test_chain_layout_and_bounds(gpu_cells, cells_npz):
     """Row 1 = x0, s2chain(1) = sigma2_0 = 1, n_steps - n_burn + 1 stored rows, samples inside the
     bounds (SURVEY 0.1 #7, 4.2)."""

@@ -254,11 +254,16 @@ struct GlobCell {         // the same view straight onto the device-resident dat
     __device__ __forceinline__ double iw(int i) const { return p_iw[i]; }
     __device__ __forceinline__ int ik(int i) const { return p_ik[i]; }
 };
-struct Work {             // one warp's forward-model scratch (offsets into tc_smem), each [N+2]; K and S start at ODD offsets:
-    int K, n, S, F1, F2, thr;   // the scan stores K[4l+1 .. 4l+4] / S[...] of lane l as two aligned 16-byte stores
+// One warp's forward-model scratch.  n, F1, F2, thr: offsets in doubles into tc_smem, [N+2] each.  K and S (counts and first
+// moments: integers) are kept as 32-BIT INTEGERS — half the shared-memory wavefronts of the per-time-point prefix differences,
+// which are then exact integer subtractions — and are offsets in INTS into tc_smem_i(), = 3 mod 4: the scan stores
+// K[4l+1 .. 4l+4] / S[...] of lane l as ONE aligned 16-byte store each.
+struct Work {
+    int K, n, S, F1, F2, thr;
 };
-
-__host__ __device__ inline int work_doubles(int N) { return 5 * (N + 2) + 4 + 1 + 4; }
+__device__ __forceinline__ int *tc_smem_i() { return reinterpret_cast<int *>(tc_smem); }
+__host__ __device__ inline int work_ks_doubles(int N) { return (((N + 9) >> 1) + 1) & ~1; }     // 3 + (N + 2) + 3 ints, even number of doubles
+__host__ __device__ inline int work_doubles(int N) { return 3 * (N + 2) + 2 * work_ks_doubles(N) + 4 + 1; }
 __host__ __device__ inline int cell_doubles(int N) { return 2 * ((N + 3) & ~3) + 3 * (N + 1) + (N + 2) / 2 + 1; }
 
 // carve from offset `o` (doubles); returns the next free offset
@@ -277,8 +282,8 @@ __device__ inline int carve_work(int o, int N, Work &w)
 {
     o += o & 1;                                            // 16-byte align (thr is read as int4)
     w.thr = o; o += 4;
-    w.K = o + 1; o += (N + 4) & ~1;                        // odd start, even length (>= N + 3: a pair store may run one past K[n])
-    w.S = o + 1; o += (N + 4) & ~1;
+    w.K = 2 * o + 3; o += work_ks_doubles(N);              // ints; the 16-byte store of a lane may run up to three past K[n]
+    w.S = 2 * o + 3; o += work_ks_doubles(N);
     w.n = o; o += N + 2;
     w.F1 = o; o += N + 2;
     w.F2 = o; o += N + 2;
@@ -360,11 +365,11 @@ template <class Cell, class Vec>
 __device__ __noinline__ void scan_counts_sequential(Cell cv, Vec th, double R, double ton, int oK)
 {
     double c = 0.0;
-    tc_smem[oK] = 0.0;
+    tc_smem_i()[oK] = 0;
 #pragma unroll 1
     for (int i = 0; i < cv.N - 1; ++i) {
         c = __dadd_rn(c, load_increment(cv, th, i, R, ton));
-        tc_smem[oK + i + 1] = floor(c);
+        tc_smem_i()[oK + i + 1] = (int)floor(c);
     }
 }
 
@@ -390,8 +395,8 @@ __device__ __forceinline__ void scan_counts(const Cell &cv, const Vec &th, doubl
     const int n = cv.N - 1;                        // increments i = 0..n-1
     bool redo = force_sequential;
     if (!force_sequential) {
-        double carry = 0.0, fprev = 0.0;           // running counter / its floor at the end of the previous block of 128
-        int carryS = 0;
+        double carry = 0.0;                        // running counter / its floor at the end of the previous block of 128
+        int carryS = 0, fprev = 0;
         bool risky = false;
 #pragma unroll 1
         for (int r0 = 0; r0 < n; r0 += 128) {
@@ -426,13 +431,14 @@ __device__ __forceinline__ void scan_counts(const Cell &cv, const Vec &th, doubl
                 // c == 0: every increment so far is exactly 0 (they are all >= 0): exact in any order
                 risky |= ok[e] && (c != 0.0) && (fr < 1e-7 || fr > 1.0 - 1e-7);
             }
-            double fl = __shfl_up_sync(0xffffffffu, f[3], 1);      // floor at the end of the previous lane
+            const int k0 = (int)f[0], k1 = (int)f[1], k2 = (int)f[2], k3 = (int)f[3];
+            int fl = __shfl_up_sync(0xffffffffu, k3, 1);            // floor at the end of the previous lane
             if (lane == 0) fl = fprev;
-            const double nn0 = f[0] - fl, nn1 = f[1] - f[0], nn2 = f[2] - f[1], nn3 = f[3] - f[2];
-            const int q0 = ok[0] ? i0 * (int)nn0 : 0;
-            const int q1 = q0 + (ok[1] ? (i0 + 1) * (int)nn1 : 0);
-            const int q2 = q1 + (ok[2] ? (i0 + 2) * (int)nn2 : 0);
-            const int q3 = q2 + (ok[3] ? (i0 + 3) * (int)nn3 : 0);
+            const int nn0 = k0 - fl, nn1 = k1 - k0, nn2 = k2 - k1, nn3 = k3 - k2;
+            const int q0 = ok[0] ? i0 * nn0 : 0;
+            const int q1 = q0 + (ok[1] ? (i0 + 1) * nn1 : 0);
+            const int q2 = q1 + (ok[2] ? (i0 + 2) * nn2 : 0);
+            const int q3 = q2 + (ok[3] ? (i0 + 3) * nn3 : 0);
             int ts = q3;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -443,40 +449,36 @@ __device__ __forceinline__ void scan_counts(const Cell &cv, const Vec &th, doubl
             int exS = __shfl_up_sync(0xffffffffu, ts, 1);
             if (lane == 0) exS = 0;
             exS += carryS;
-            // K[i0+1 .. i0+4], S[...]: w.K / w.S are odd, so the pairs are 16-byte aligned; the second element of a pair may
-            // lie one past the last step (steps beyond n add exactly 0: it repeats the last floor / moment, and nobody reads it)
+            // K[i0+1 .. i0+4], S[...]: one aligned 16-byte store each; the elements past the last step repeat the last floor /
+            // moment (steps beyond n add exactly 0) and nobody reads them
             if (ok[0]) {
-                *reinterpret_cast<double2 *>(tc_smem + w.K + i0 + 1) = make_double2(f[0], f[1]);
-                *reinterpret_cast<double2 *>(tc_smem + w.S + i0 + 1) = make_double2((double)(exS + q0), (double)(exS + q1));
-            }
-            if (ok[2]) {
-                *reinterpret_cast<double2 *>(tc_smem + w.K + i0 + 3) = make_double2(f[2], f[3]);
-                *reinterpret_cast<double2 *>(tc_smem + w.S + i0 + 3) = make_double2((double)(exS + q2), (double)(exS + q3));
+                *reinterpret_cast<int4 *>(tc_smem_i() + w.K + i0 + 1) = make_int4(k0, k1, k2, k3);
+                *reinterpret_cast<int4 *>(tc_smem_i() + w.S + i0 + 1) = make_int4(exS + q0, exS + q1, exS + q2, exS + q3);
             }
             if (want_n) {                                           // cohort sizes: only the pairs algorithm reads them
-                if (ok[0]) tc_smem[w.n + i0] = nn0;
-                if (ok[1]) tc_smem[w.n + i0 + 1] = nn1;
-                if (ok[2]) tc_smem[w.n + i0 + 2] = nn2;
-                if (ok[3]) tc_smem[w.n + i0 + 3] = nn3;
+                if (ok[0]) tc_smem[w.n + i0] = (double)nn0;
+                if (ok[1]) tc_smem[w.n + i0 + 1] = (double)nn1;
+                if (ok[2]) tc_smem[w.n + i0 + 2] = (double)nn2;
+                if (ok[3]) tc_smem[w.n + i0 + 3] = (double)nn3;
             }
-            fprev = __shfl_sync(0xffffffffu, f[3], 31);            // steps beyond n add exactly 0: lane 31 holds the block's last floor
+            fprev = __shfl_sync(0xffffffffu, k3, 31);              // steps beyond n add exactly 0: lane 31 holds the block's last floor
             carry = __dadd_rn(carry, tot);
             carryS += totS;
         }
-        if (lane == 0) { tc_smem[w.K] = 0.0; tc_smem[w.S] = 0.0; }
+        if (lane == 0) { tc_smem_i()[w.K] = 0; tc_smem_i()[w.S] = 0; }
         redo = __any_sync(0xffffffffu, risky);
     }
     if (redo) {
         if (lane == 0) scan_counts_sequential(cv, th, R, ton, w.K);
         __syncwarp();
 #pragma unroll 1
-        for (int i = lane; i < n; i += 32) tc_smem[w.n + i] = tc_smem[w.K + i + 1] - tc_smem[w.K + i];
+        for (int i = lane; i < n; i += 32) tc_smem[w.n + i] = (double)(tc_smem_i()[w.K + i + 1] - tc_smem_i()[w.K + i]);
         __syncwarp();
         if (lane == 0) {
-            double sacc = 0.0;
-            tc_smem[w.S] = 0.0;
+            int sacc = 0;
+            tc_smem_i()[w.S] = 0;
 #pragma unroll 1
-            for (int i = 0; i < n; ++i) { sacc += (double)i * tc_smem[w.n + i]; tc_smem[w.S + i + 1] = sacc; }
+            for (int i = 0; i < n; ++i) { sacc += i * (tc_smem_i()[w.K + i + 1] - tc_smem_i()[w.K + i]); tc_smem_i()[w.S + i + 1] = sacc; }
         }
     }
 }
@@ -560,6 +562,8 @@ __device__ __noinline__ double ss_eval(const tc_construct &C, Cell cv, Vec th, W
         if (algo == TC_ALGO_TOEPLITZ) {
             // lag thresholds of the piecewise response, by exact predicate on p = v*(d*lag):
             // ramp = [la, le), plateau = [lb, lL); lanes 0-3: MS2, lanes 4-7: PP7
+            // (A straight-line version — all 32 lanes testing the four candidate lags around the guess of each threshold at once
+            // — was measured: +0.8 % on the batched kernel, -3 % on both samplers, whose instruction footprint it enlarges.)
             int *thr = reinterpret_cast<int *>(tc_smem + w.thr);
             if (lane < 8) {
                 const bool c2 = lane >= 4;
@@ -593,9 +597,10 @@ __device__ __noinline__ double ss_eval(const tc_construct &C, Cell cv, Vec th, W
                     const int a2i = r2ok ? jj - la2 + 1 : 0, b2i = r2ok ? jj - lh2 : 0;
                     const int p1a = p1ok ? jj - lb1 + 1 : 0, p1b = p1ok ? max(jj - lL1 + 1, 0) : 0;
                     const int p2a = p2ok ? jj - lb2 + 1 : 0, p2b = p2ok ? max(jj - lL2 + 1, 0) : 0;
-                    const double dK1 = tc_smem[w.K + a1i] - tc_smem[w.K + b1i], dS1 = tc_smem[w.S + a1i] - tc_smem[w.S + b1i];
-                    const double dK2 = tc_smem[w.K + a2i] - tc_smem[w.K + b2i], dS2 = tc_smem[w.S + a2i] - tc_smem[w.S + b2i];
-                    const double pl1 = tc_smem[w.K + p1a] - tc_smem[w.K + p1b], pl2 = tc_smem[w.K + p2a] - tc_smem[w.K + p2b];
+                    const int *ks = tc_smem_i();
+                    const double dK1 = (double)(ks[w.K + a1i] - ks[w.K + b1i]), dS1 = (double)(ks[w.S + a1i] - ks[w.S + b1i]);
+                    const double dK2 = (double)(ks[w.K + a2i] - ks[w.K + b2i]), dS2 = (double)(ks[w.S + a2i] - ks[w.S + b2i]);
+                    const double pl1 = (double)(ks[w.K + p1a] - ks[w.K + p1b]), pl2 = (double)(ks[w.K + p2a] - ks[w.K + p2b]);
                     double c1 = fma(f1, pl1, sc1 * (vd * (dj * dK1 - dS1) - s1 * dK1));
                     double c2 = fma(f2, pl2, sc2 * (vd * (dj * dK2 - dS2) - s2 * dK2));
                     if (s > 0) { c1 += tc_smem[w.F1 + jj]; c2 += tc_smem[w.F2 + jj]; }

@@ -59,6 +59,10 @@ struct DeviceGuard {
 #ifndef TC_WARP_MIN_CHAINS_PER_SM
 #define TC_WARP_MIN_CHAINS_PER_SM 13  // chain-per-warp kernel from this many chains per SM on (measured crossover on B200: ~1 900 chains)
 #endif
+#ifndef TC_SOLO_LAG
+#define TC_SOLO_LAG 2       // dram_kernel: slices a chain must lag the mean progress by to get its SM to itself (0: never)
+#define TC_SOLO_NSEG 128    // ... and the number of time slices per chain then
+#endif
 #define COV_CR 32          // weighted rows of the covariance block staged per pass of the scatter update
 
 // development aid: cycle counts of sub-phases, chain 0 only (build with -DTC_SUBPROF; see scripts/subprof.py)
@@ -181,6 +185,10 @@ struct RunArgs {
     // time slicing
     int seglen;
     int *cstate;
+    // dram_kernel, two CTAs per SM: a chain that lags the mean progress by solo_lag slices or more gets its SM to itself
+    // (smctl[%smid] = 1 + blockIdx of the owner; 0: shared); solo_lag <= 0: off
+    int solo_lag;
+    int *smctl;
 };
 
 // Shared-memory budget of the sampler (doubles), N = max time points over the dataset.
@@ -1602,7 +1610,7 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
     __shared__ double s_ssv[2 * RING];
     __shared__ ChainCtx cx;
     __shared__ S2Stats s_s2;
-    __shared__ int s_item, s_done;
+    __shared__ int s_item, s_done, s_sum, s_own;
     __shared__ unsigned s_min;
     __shared__ ChainState st;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -1616,29 +1624,47 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
     const int LOCK = 1 << 30;
     const int nseg = (a.nsimu + a.seglen - 1) / a.seglen;
     int start = (int)(((long long)blockIdx.x * a.nchains) / gridDim.x);
+    // Two CTAs share an SM and slow each other down: a chain runs ~24 % faster with the SM to itself (scripts/solo_sm.py), and
+    // the fit lasts as long as its slowest chain.  So a CTA whose chain lags the mean progress of all chains by solo_lag slices
+    // takes the SM (smctl[%smid]); its neighbour finishes the slice it is in, claims nothing and sleeps until the SM is
+    // shared again.  Chains that are ahead wait for a slot instead (the furthest-behind chain is always claimed first), so
+    // the slots given up come out of the time the fast chains would have idled at the end of the fit.
+    unsigned smid = 0;
+    asm("mov.u32 %0, %%smid;" : "=r"(smid));
+    int *const smc = (a.solo_lag > 0 && nseg > 1) ? a.smctl + (smid & 1023) : nullptr;
+    const int me = (int)blockIdx.x + 1;
+    bool own = false;                                       // uniform: this CTA holds its SM
 #pragma unroll 1
     for (;;) {
         // claim a chain: the whole CTA scans the state words in parallel; key = (slices done, distance from `start`)
 #pragma unroll 1
         for (;;) {
             __syncthreads();
-            if (tid == 0) s_min = 0xffffffffu;
+            if (tid == 0) { s_min = 0xffffffffu; s_sum = 0; }
+            if (smc && !own && tid == 0) {
+                // the neighbour holds the SM: stay out of its way
+#pragma unroll 1
+                while (*reinterpret_cast<volatile int *>(smc) != 0) __nanosleep(4000);
+            }
             __syncthreads();
-            int pending = 0;
+            int pending = 0, prog = 0;
 #pragma unroll 1
             for (int base = 0; base < a.nchains; base += DRAM_THREADS) {
                 const int i = base + tid;
                 int hit = 0;
                 if (i < a.nchains) {
                     const int v = *reinterpret_cast<volatile int *>(a.cstate + (start + i) % a.nchains);
+                    prog += min(v & ~LOCK, nseg);
                     if (v & LOCK) pending = 1;
                     else if (v < nseg) { hit = 1; atomicMin(&s_min, ((unsigned)v << 24) | (unsigned)min(i, 0xffffff)); }
                 }
                 if (__syncthreads_or(hit) && nseg == 1) break;           // unsliced: any free chain will do
             }
+            if (smc) { prog = __reduce_add_sync(0xffffffffu, prog); if (lane == 0) atomicAdd(&s_sum, prog); }
             pending = __syncthreads_or(pending);
             const unsigned kmin = s_min;
             if (kmin == 0xffffffffu) {
+                if (own) { if (tid == 0) atomicExch(smc, 0); own = false; }   // nothing to run: the neighbour may
                 if (!pending) { if (tid == 0) s_item = -1; break; }     // every chain is finished
                 __nanosleep(20000);
                 continue;
@@ -1649,13 +1675,27 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
                 const bool ok = !(v & LOCK) && v < nseg && atomicCAS(a.cstate + c, v, v | LOCK) == v;
                 s_item = ok ? c : -2;
                 s_done = v;
+                s_own = own ? 1 : 0;
+                if (ok && smc) {
+                    const bool lagging = (long long)s_sum - (long long)v * a.nchains >= (long long)a.solo_lag * a.nchains;
+                    if (lagging) {
+                        if (!own) {
+                            if (atomicCAS(smc, 0, me) == 0) s_own = 1;
+                            else { atomicExch(a.cstate + c, v); s_item = -2; }      // the neighbour took the SM meanwhile: give the chain back
+                        }
+                    } else {
+                        if (own) { atomicExch(smc, 0); s_own = 0; }
+                        else if (*reinterpret_cast<volatile int *>(smc) != 0) { atomicExch(a.cstate + c, v); s_item = -2; }
+                    }
+                }
             }
             __syncthreads();
+            own = s_own != 0;
             if (s_item != -2) break;
         }
         __syncthreads();
         const int ch = s_item, seg = s_done;
-        if (ch < 0) break;                                  // every chain is finished
+        if (ch < 0) break;                                  // every chain is finished (own is false here)
         start = (ch + 1) % a.nchains;
         __threadfence();
         const int k_end = min(a.nsimu, (seg + 1) * a.seglen);
@@ -2672,6 +2712,9 @@ int tc_mcmc_run(const tc_cells *c, const tc_mcmc_opts *o, int nchains, const int
         // time slices: a multiple of adaptint, ~32 per chain
         const int unit = o->adaptint > 0 ? o->adaptint : 1;
         long long sl = ((long long)o->nsimu + 31) / 32;
+        CUDA_TRY(r.buf.alloc(a.smctl, 1024));
+        CUDA_TRY(cudaMemsetAsync(a.smctl, 0, sizeof(int) * 1024, r.st));
+        a.solo_lag = 0;
         CUDA_TRY(r.buf.alloc(a.gState, (size_t)nc * state_doubles(ld)));
         CUDA_TRY(r.buf.alloc(a.cstate, nc));
         CUDA_TRY(cudaMemsetAsync(a.cstate, 0, sizeof(int) * nc, r.st));
@@ -2712,12 +2755,20 @@ int tc_mcmc_run(const tc_cells *c, const tc_mcmc_opts *o, int nchains, const int
                                    "(one CTA per chain: the cell, the chain state, 8 proposal slots and 8 forward-model scratch areas must fit in one SM)");
         CUDA_TRY(cudaFuncSetAttribute(dram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         // persistent grid = resident CTA slots
-        if (nc >= 4 * 296) sl = o->nsimu;                 // many chains per CTA slot: imbalance averages out, no slicing
-        sl = ((sl + unit - 1) / unit) * unit;
-        a.seglen = (int)std::max<long long>(sl, unit);
         int per_sm = 0;
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dram_kernel, DRAM_THREADS, smem));
         if (per_sm < 1) return fail(TC_EINVAL, "sampler kernel does not fit on this device");
+        if (nc >= 4 * 296) sl = o->nsimu;                 // many chains per CTA slot: imbalance averages out, no slicing
+        else if (per_sm == 2 && nc > sms) {
+            // about as many chains as CTA slots, two CTAs per SM: lagging chains get an SM to themselves (dram_kernel's claim
+            // loop); finer slices, so that the neighbour of such a chain gives way soon
+            const char *e1 = getenv("TC_SOLO_LAG"), *e2 = getenv("TC_NSEG");          // development switches
+            a.solo_lag = e1 ? atoi(e1) : TC_SOLO_LAG;
+            const int ns = e2 ? atoi(e2) : TC_SOLO_NSEG;
+            if (a.solo_lag > 0) sl = std::max<long long>(((long long)o->nsimu + ns - 1) / ns, 4LL * unit);
+        }
+        sl = ((sl + unit - 1) / unit) * unit;
+        a.seglen = (int)std::max<long long>(sl, unit);
         const int grid = std::min(nc, per_sm * sms);           // every CTA resident: slices may wait on each other
         if (a.big && do_cov) CUDA_TRY(r.buf.alloc(a.gW, (size_t)grid * ldR));
         CUDA_TRY(cudaEventRecord(r.e0, r.st));
