@@ -279,6 +279,9 @@ __device__ __forceinline__ bool chol8(double (&A)[8][8], double (&dinv)[8])
     }
     return bad;
 }
+// (Measured and dropped: the root-free elimination U' D^-1 U — the next pivot then waits only for a reciprocal (MUFU.RCP64H seed +
+// two Newton steps) and the reciprocal square roots are side chains: -2 % on the factorisation of dram_kernel, +4 % on the
+// chain-per-warp kernel's, whose FP64 pipe is shared by 16 factorisations and sees the extra instructions.)
 
 // Factor the 8x8 diagonal block that starts at tile row b0 (one 4x4 tile when it is the last row of an odd nt4): every
 // lane of the calling warp factors it redundantly in registers (a chain of 8 dependent rsqrt's, no communication),
@@ -1666,7 +1669,7 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
             if (kmin == 0xffffffffu) {
                 if (own) { if (tid == 0) atomicExch(smc, 0); own = false; }   // nothing to run: the neighbour may
                 if (!pending) { if (tid == 0) s_item = -1; break; }     // every chain is finished
-                __nanosleep(20000);
+                __nanosleep(50000);                                     // (a slice lasts milliseconds; the scan costs the neighbour issue slots)
                 continue;
             }
             if (tid == 0) {
