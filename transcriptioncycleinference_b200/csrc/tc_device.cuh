@@ -385,7 +385,9 @@ __device__ __noinline__ void scan_counts_sequential(Cell cv, Vec th, double R, d
 // sequentially.  Error bound of either order: (N-1) * eps * max(c) < 400 * 1.1e-16 * 3e4 << 1e-7, so the two paths
 // agree otherwise.
 #ifndef TC_SS_UNR
-#define TC_SS_UNR 2         // time points per lane per pass of the forward model (unroll-and-jam factor; 4 doubles the code for no gain)
+#define TC_SS_UNR 1         // time points per lane per pass of the forward model (unroll-and-jam factor).  1: the smallest code — ss_eval
+                            // is 13 KB of SASS instead of 18.6 KB with 2, and the samplers' round (bounds, ss_eval, resolve, flush: ~33 KB with 2)
+                            // runs against a 32 KB instruction cache: config 2 +2 %, config 3 +1 % (measured); 4 doubles the code for no gain
 #endif
 template <class Cell, class Vec>
 __device__ __forceinline__ void scan_counts(const Cell &cv, const Vec &th, double R, double ton, const Work &w,

@@ -63,6 +63,9 @@ struct DeviceGuard {
 #define TC_SOLO_LAG 2       // dram_kernel: slices a chain must lag the mean progress by to get its SM to itself (0: never)
 #define TC_SOLO_NSEG 128    // ... and the number of time slices per chain then
 #endif
+#ifndef TC_CB_UNR
+#define TC_CB_UNR 1         // unroll factor of the bounds / prior loop of a round (phase A): 1 = smallest code (measured: +1 % on config 2 against 4)
+#endif
 #define COV_CR 32          // weighted rows of the covariance block staged per pass of the scatter update
 
 // development aid: cycle counts of sub-phases, chain 0 only (build with -DTC_SUBPROF; see scripts/subprof.py)
@@ -1332,7 +1335,13 @@ __device__ __forceinline__ void cand_bounds_t(const ChainCtx &cx, int k, int C, 
         const int o1 = cx.slot_i(k + c), o2 = o1 + cx.s1;
         double pr1 = 0.0, pr2 = 0.0;
         unsigned oob = 0;
+#if TC_CB_UNR == 4
 #pragma unroll 4
+#elif TC_CB_UNR == 2
+#pragma unroll 2
+#else
+#pragma unroll 1
+#endif
         for (int j = lane; j < npar; j += 32) {
             const double xj = tc_smem[ox + j], a1 = xj + tc_smem[o1 + j], a2 = xj + tc_smem[o2 + j];
             double lo, hi, mu, pinv;

@@ -258,22 +258,50 @@ __device__ __noinline__ void wk_generate(const RunArgs &a, const WkCtx &c, int g
     } else {
         float *Z1 = reinterpret_cast<float *>(tc_smem + c.o_ov), *Z2 = Z1 + WK_GEN * ldz;
         const int npairs = (npar + 1) >> 1;
+        // Two steps per pass: a lane draws the parameter pairs lane, lane + 32 of step s and of step s + 1 — four independent
+        // Philox + Box-Muller chains in flight instead of two — and the norms of the two steps are reduced side by side.
+        // (npairs <= 64 here: npar <= 128 + ...; the general case loops.)
 #pragma unroll 1
-        for (int s = 0; s < nnew; ++s) {
-            double n1 = 0.0, n0 = 0.0;
-#pragma unroll 3                                                    // independent Philox blocks: their dependent chains interleave
-            for (int q = lane; q < npairs; q += 32) {
-                const double4 z = normal_quad_inl(a.seed, c.uid, g0 + s, q);  // (z1[2q], z1[2q+1], z2[2q], z2[2q+1]): FP32 values
-                *reinterpret_cast<float2 *>(Z1 + s * ldz + 2 * q) = make_float2((float)z.x, (float)z.y);
-                *reinterpret_cast<float2 *>(Z2 + s * ldz + 2 * q) = make_float2((float)z.z, (float)z.w);
-                const double d0 = z.x - z.z * inv_dr;
-                n1 = fma(d0, d0, n1); n0 = fma(z.x, z.x, n0);
-                if (2 * q + 1 < npar) { const double d1 = z.y - z.w * inv_dr; n1 = fma(d1, d1, n1); n0 = fma(z.y, z.y, n0); }
+        for (int s = 0; s < nnew; s += 2) {
+            const bool two = s + 1 < nnew;
+            double n1a = 0.0, n0a = 0.0, n1b = 0.0, n0b = 0.0;
+#pragma unroll 1
+            for (int q0 = 0; q0 < npairs; q0 += 64) {
+                double4 z[4];
+                bool on[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int q = q0 + lane + 32 * (u & 1), ss = s + (u >> 1);
+                    on[u] = q < npairs && ss < nnew;
+                    z[u] = normal_quad_inl(a.seed, c.uid, g0 + ss, on[u] ? q : 0);   // (z1[2q], z1[2q+1], z2[2q], z2[2q+1]): FP32 values
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int q = q0 + lane + 32 * (u & 1), ss = s + (u >> 1);
+                    if (on[u]) {
+                        *reinterpret_cast<float2 *>(Z1 + ss * ldz + 2 * q) = make_float2((float)z[u].x, (float)z[u].y);
+                        *reinterpret_cast<float2 *>(Z2 + ss * ldz + 2 * q) = make_float2((float)z[u].z, (float)z[u].w);
+                        double &n1 = (u >> 1) ? n1b : n1a, &n0 = (u >> 1) ? n0b : n0a;      // (compile-time: the loop is unrolled)
+                        const double d0 = z[u].x - z[u].z * inv_dr;
+                        n1 = fma(d0, d0, n1); n0 = fma(z[u].x, z[u].x, n0);
+                        if (2 * q + 1 < npar) { const double d1 = z[u].y - z[u].w * inv_dr; n1 = fma(d1, d1, n1); n0 = fma(z[u].y, z[u].y, n0); }
+                    }
+                }
             }
             __syncwarp();
-            if (lane < ldz - npar) { Z1[s * ldz + npar + lane] = 0.0f; Z2[s * ldz + npar + lane] = 0.0f; }   // padding columns (incl. the odd pair's spare)
-            warp_sum2(n1, n0);
-            if (lane == 0) { __stcg(c.gSc + 8 * s + 3, n1); __stcg(c.gSc + 8 * s + 4, n0); }
+            if (lane < ldz - npar) {                                                                        // padding columns (incl. the odd pair's spare)
+                Z1[s * ldz + npar + lane] = 0.0f; Z2[s * ldz + npar + lane] = 0.0f;
+                if (two) { Z1[(s + 1) * ldz + npar + lane] = 0.0f; Z2[(s + 1) * ldz + npar + lane] = 0.0f; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                n1a += __shfl_xor_sync(0xffffffffu, n1a, o); n0a += __shfl_xor_sync(0xffffffffu, n0a, o);
+                n1b += __shfl_xor_sync(0xffffffffu, n1b, o); n0b += __shfl_xor_sync(0xffffffffu, n0b, o);
+            }
+            if (lane == 0) {
+                __stcg(c.gSc + 8 * s + 3, n1a); __stcg(c.gSc + 8 * s + 4, n0a);
+                if (two) { __stcg(c.gSc + 8 * (s + 1) + 3, n1b); __stcg(c.gSc + 8 * (s + 1) + 4, n0b); }
+            }
         }
     }
     __syncwarp();
