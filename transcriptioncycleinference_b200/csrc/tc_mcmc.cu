@@ -1152,6 +1152,9 @@ __device__ __noinline__ void generate(const RunArgs &a, const ChainCtx &cx, int 
             }
         }
     } else {
+        // (Measured and dropped: warp w owning step g0 + w — its row's normals with the two norms folded in on the way, its
+        // uniforms and chi-square on lane 0.  The norms pass disappears (1.8 k -> 0.7 k cycles per call) but every warp then
+        // pays the serial chi-square + log chain, ~4.5 k cycles: randomness 5.5 k -> 7.6 k per call.)
         // lanes 0..nnew-1 of warp 0: the uniforms and the chi-square of step g0 + lane (a long serial draw, one step
         // per lane); everybody: one work item = the 4 normals of a parameter pair.  The items are dealt from warp 1
         // on, so that the odd extra item round lands on warp 7, not on warp 0.
