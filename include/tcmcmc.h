@@ -173,7 +173,7 @@ int tc_forward(const tc_cells *cells, int64_t nbatch, const int32_t *cell_id, co
  *   sig [nchains x 2]          sqrt(mean(s2chain)), std(sqrt(s2chain),1) over ALL rows (:302-303)
  *   counters [nchains x TC_NCOUNTERS] int64
  *   chain [nchains x (nsimu-n_burn+1) x ld], s2chain [nchains x nsimu]   (store_chain = 1)
- * Series length: max(N) <= 414 (one CTA per chain holds the cell, the chain state, the proposal slots and the
+ * Series length: max(N) <= 441 (one CTA per chain holds the cell, the chain state, the proposal slots and the
  * forward-model scratch in one SM; beyond ~210 points the large-series layout of opts->layout is used); longer series
  * return TC_EINVAL.
  * Replay harness (opts->replay = 1): z1,z2 [nchains x nsimu x ld], u1,u2,chi2 [nchains x nsimu]

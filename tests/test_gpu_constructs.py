@@ -77,12 +77,13 @@ def test_truncated_window_cells(cells_npz, orc):
     cells.close()
 
 
-@pytest.mark.parametrize("N", [12, 200, 250, 400])
+@pytest.mark.parametrize("N", [12, 200, 250, 400, 441])
 def test_series_length_extremes_replay(orc, N):
     """Series much shorter / longer than TestData's 113-129 points: N = 12 (npar = 19: 3 column tiles, 5 Cholesky tile
     rows), N = 200 (npar = 207: one CTA per SM, 26 column tiles, several passes of the scatter update), and N = 250 /
     N = 400 (BASELINE config 5's length; npar = 257 / 407: the big layout — ring of 8 slots, bounds read from HBM/L2, proposal
-    factor factorised through HBM/L2 by chol_global; 257 has an odd number of 4x4 tile rows).  Synthetic irregular time
+    factor factorised through HBM/L2 by chol_global; 257 has an odd number of 4x4 tile rows), and N = 441, the longest series
+    the engine takes (npar = 448: seven column tiles of 8 per warp in gen_increments_tma).  Synthetic irregular time
     grid with missing data; the DRAM replay must match the oracle flag for flag."""
     from transcriptioncycleinference_b200 import _lib, setup_cell
     from transcriptioncycleinference_b200.engine import Cells
@@ -114,6 +115,25 @@ def test_series_length_extremes_replay(orc, N):
                       *[x[i, :npar] for x in inputs], streams=sti)
         assert np.array_equal(out["flags"][i], ref["flags"]), (N, i)
         np.testing.assert_allclose(out["chain"][i][:, :npar], ref["chain"], rtol=0, atol=1e-7)
+    cells.close()
+
+
+def test_series_longer_than_the_limit_are_rejected():
+    """max(N) = 442 does not fit the one-CTA-per-chain layouts (include/tcmcmc.h): tc_mcmc_run returns TC_EINVAL, it does not
+    run a kernel that would silently drop column tiles."""
+    from transcriptioncycleinference_b200 import _lib, setup_cell
+    from transcriptioncycleinference_b200.engine import Cells
+    if _lib.device_count() < 1:
+        pytest.skip("no CUDA device")
+    N = 442
+    rng = np.random.default_rng(5)
+    t = np.concatenate([[0.0], np.cumsum(rng.uniform(0.15, 0.35, N - 1))])
+    cells = Cells([t], [rng.uniform(0, 3, N)], [rng.uniform(0, 10, N)])
+    cc = np.zeros(1, dtype=np.int32)
+    inputs = setup_cell.chain_inputs(cells, cc, np.random.default_rng(7))
+    with pytest.raises(Exception) as ei:
+        cells.mcmc_run(_lib.default_opts(nsimu=200, burnintime=100, n_burn=100), cc, *inputs)
+    assert "too large" in str(ei.value)
     cells.close()
 
 

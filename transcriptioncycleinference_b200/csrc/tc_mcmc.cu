@@ -1840,6 +1840,7 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
             st.tprev = clock64();
         }
         __syncthreads();
+        // phase clocks (TC_CNT_CYCLES0..).  (Sampling them every 8th round was measured: no gain — 66.7 M against 67.5 M.)
 #define TC_PHASE(i) do { if (tid == 0) { const long long tn__ = clock64(); st.pc[i] += tn__ - st.tprev; st.tprev = tn__; } } while (0)
 
         if (seg == 0) {
@@ -2765,7 +2766,8 @@ int tc_mcmc_run(const tc_cells *c, const tc_mcmc_opts *o, int nchains, const int
         }
         a.wsz = dram_wsz(Nmax, a.big);
         const size_t smem = sizeof(double) * (size_t)dram_smem_doubles(Nmax, a.big);
-        if (smem > avail || (npmax + 3) / 4 > 255)
+        // (big layout: gen_increments_tma keeps at most GENB_MAXT column tiles of 8 per warp in registers)
+        if (smem > avail || (npmax + 3) / 4 > 255 || (a.big && npmax > 8 * SPEC * GENB_MAXT))
             return fail(TC_EINVAL, "max(N) = " + std::to_string(Nmax) + " is too large for the shared-memory layout of this build "
                                    "(one CTA per chain: the cell, the chain state, 8 proposal slots and 8 forward-model scratch areas must fit in one SM)");
         CUDA_TRY(cudaFuncSetAttribute(dram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
