@@ -1125,6 +1125,21 @@ __device__ __noinline__ void gen_increments_tma(const ChainCtx &cx, int g0, int 
 #ifndef TC_NOLOAD
 #define TC_NOLOAD 0        // development switch: 1 = skip the loads of R (isolates the MMA loop in scripts/subprof.py)
 #endif
+// 1 / d to within an ulp or two: MUFU.RCP64H seed + two Newton steps (the IEEE quotient is ~25 dependent instructions with a
+// slow-path branch; where this is used a product with the reciprocal replaces a quotient anyway)
+__device__ __forceinline__ double tc_rcp(double d)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    r = fma(fma(-d, r, 1.0), r, r);
+    r = fma(fma(-d, r, 1.0), r, r);
+    return r;
+}
+__device__ __forceinline__ void warp_sum2(double &p, double &q)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { p += __shfl_xor_sync(0xffffffffu, p, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+}
 __device__ __noinline__ void generate(const RunArgs &a, const ChainCtx &cx, int g0, int nnew, bool r_diag)
 {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, npar = cx.npar;
@@ -1202,7 +1217,7 @@ __device__ __noinline__ void generate(const RunArgs &a, const ChainCtx &cx, int 
             n1 = fma(d, d, n1);
             n0 = fma(zz.x, zz.x, n0);
         }
-        n1 = warp_sum(n1); n0 = warp_sum(n0);
+        warp_sum2(n1, n0);                                          // (the two butterflies side by side)
         if (lane == 0) { double *sc = cx.slot_sc(g0 + warp); sc[3] = n1; sc[4] = n0; }
     }
     SUBP(1);
@@ -1315,11 +1330,6 @@ __device__ __noinline__ void generate(const RunArgs &a, const ChainCtx &cx, int 
 #undef ZROW
 }
 
-__device__ __forceinline__ void warp_sum2(double &p, double &q)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { p += __shfl_xor_sync(0xffffffffu, p, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
-}
 
 // Round phase A: bounds and prior of both proposals of the candidate steps k .. k+C-1 (warp w: candidates w, w+8).
 // The proposals are never materialised: theta = x + ring increment, the very expression the forward model
@@ -1385,9 +1395,12 @@ __device__ __noinline__ int resolve_dr(const double *sc, bool o1, double x12, do
     double a32 = e32;
     a32 = a32 > 1.0 ? 1.0 : a32;
     if (!(a32 >= 0.0)) a32 = 0.0;
-    double a13 = e13 * (1.0 - a32) / (1.0 - a12);
-    a13 = a13 > 1.0 ? 1.0 : a13;
-    return ((a13 >= 1.0) || (a13 > sc[1])) ? 1 : 0;
+    // accept iff min(1, e13 (1 - a32) / (1 - a12)) > u2 (or = 1), decided without the quotient: 1 - a12 > 0 because stage 1
+    // rejected (a12 < u1 < 1; an out-of-bounds first stage has a12 = 0), so the test is num > u2 den (or num >= den).  A
+    // denominator that rounds to 0 keeps the quotient's answer: +Inf -> accept when num > 0, 0/0 -> reject.
+    const double num = e13 * (1.0 - a32), den = 1.0 - a12;
+    if (!(den > 0.0)) return num > 0.0 ? 1 : 0;
+    return (num >= den || num > sc[1] * den) ? 1 : 0;
 }
 
 // dst[e] = src[e] * sc, e < n 16-byte units, src in HBM/L2: 8 independent loads in flight per thread (written as one loop
@@ -1874,7 +1887,7 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
             // step k sees sig2, step k + w sees (N0 S20 + ss) / chi2_{k+w-1}, i.e. 1/sigma2 = chi2_{k+w-1} * rden.  (A product
             // with a rounded reciprocal instead of a quotient: the acceptance exponent moves by an ulp, like the log-domain
             // decision of stage 1.)
-            const double rden = 1.0 / (a.N0 * a.S20 + ss), rsig = 1.0 / sig2;
+            const double rden = tc_rcp(a.N0 * a.S20 + ss), rsig = tc_rcp(sig2);
 
             if (gen_upto < bound && gen_upto - k < (a.big ? 1 : SPEC)) {
                 // fewer than SPEC steps ready => at least GEN_M of the RING slots are free (big layout: ring of GEN_M
