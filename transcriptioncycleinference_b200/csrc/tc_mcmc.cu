@@ -874,6 +874,7 @@ struct S2Stats { double sum, sq_sum, cnt, pad; };      // sum s2, sum sqrt(s2), 
 // (between the post-speculation barrier and the end-of-round barrier), read by everyone at the top of a round.
 struct ChainState {
     double ss, pri, sigma2, cov_n, wcnt;
+    double rden, rsig;                                  // 1 / (N0 S20 + ss) and 1 / sigma2 as the next step sees it (= chi2 of the last row * rden)
     int r_diag, bad0, run_r0, ndist;
     long long n_ss, n_acc1, n_acc2, n_oob, n_adapt, n_cholfail, n_dr, n_spec, rej, reju;
     long long pc[8], tprev;
@@ -1841,6 +1842,7 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
             } else {
                 st.ss = __ldcg(gst + 0); st.pri = __ldcg(gst + 1); st.sigma2 = __ldcg(gst + 2); st.cov_n = __ldcg(gst + 3);
                 st.wcnt = __ldcg(gst + 4); st.r_diag = __ldcg(gst + 5) != 0.0; st.bad0 = 0;
+                st.rden = __ldcg(gst + 10); st.rsig = __ldcg(gst + 11);
                 s_s2.sum = __ldcg(gst + 6); s_s2.sq_sum = __ldcg(gst + 7); s_s2.cnt = __ldcg(gst + 9);
                 const long long *gc = reinterpret_cast<const long long *>(gst + 16);
                 st.n_ss = __ldcg(gc + 0); st.n_acc1 = __ldcg(gc + 1); st.n_acc2 = __ldcg(gc + 2); st.n_oob = __ldcg(gc + 3);
@@ -1864,7 +1866,7 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
             for (int i = lane; i < npar; i += 32) { const double e = (cx.x[i] - cx.mu[i]) * cx.pinv[i]; sp += e * e; }
             sp = warp_sum(sp);
             const bool bad = !isfinite(ss0);
-            if (tid == 0) { st.ss = ss0; st.pri = sp; st.bad0 = bad ? 1 : 0; }
+            if (tid == 0) { st.ss = ss0; st.pri = sp; st.bad0 = bad ? 1 : 0; st.rden = tc_rcp(a.N0 * a.S20 + ss0); st.rsig = 1.0 / a.sigma2_0; }
             if (!bad && warp == 0) emit_s2(a, cx, &s_s2, 0, 0, 1, 1, ss0, ss0, a.sigma2_0);
             __syncthreads();
         }
@@ -1887,7 +1889,7 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
             // step k sees sig2, step k + w sees (N0 S20 + ss) / chi2_{k+w-1}, i.e. 1/sigma2 = chi2_{k+w-1} * rden.  (A product
             // with a rounded reciprocal instead of a quotient: the acceptance exponent moves by an ulp, like the log-domain
             // decision of stage 1.)
-            const double rden = tc_rcp(a.N0 * a.S20 + ss), rsig = tc_rcp(sig2);
+            const double rden = st.rden, rsig = st.rsig;
 
             if (gen_upto < bound && gen_upto - k < (a.big ? 1 : SPEC)) {
                 // fewer than SPEC steps ready => at least GEN_M of the RING slots are free (big layout: ring of GEN_M
@@ -1999,7 +2001,11 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
                         if (a.do_cov && r_acc > run_r0) st.ndist = ndist + 1;
                         st.run_r0 = r_acc;
                     }
-                    if (a.updatesigma) st.sigma2 = (a.N0 * a.S20 + ss_new) / cx.slot_sc(k + ncommit - 1)[2];
+                    // sigma2 of the next step = (N0 S20 + ss_new) / chi2 of the last committed row, kept as its reciprocal (the
+                    // same product chi2 * rden the later steps of a round use: the chain does not depend on where rounds are cut)
+                    const double rd = accd ? tc_rcp(a.N0 * a.S20 + ss_new) : rden;
+                    if (accd) st.rden = rd;
+                    if (a.updatesigma) st.rsig = cx.slot_sc(k + ncommit - 1)[2] * rd;
                 }
             } else if (warp == SPEC - 1) {
                 // meanwhile: per-row scalars of the committed rows (lane = row) — sigma2 of the row (rows before the accept
@@ -2009,7 +2015,7 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
                 if (lane < ncommit) {
                     const int r = k + lane;
                     const double ssr = lane < first ? ss : ss_new;
-                    s2 = a.updatesigma ? (a.N0 * a.S20 + ssr) / cx.slot_sc(r)[2] : sig2;
+                    s2 = a.updatesigma ? (a.N0 * a.S20 + ssr) * tc_rcp(cx.slot_sc(r)[2]) : sig2;
                     sq = sqrt(s2);
                     if (a.store_chain && a.s2chain) a.s2chain[(size_t)cx.ch * a.nsimu + r] = s2;
                     if (a.flags) a.flags[(size_t)cx.ch * a.nsimu + r] = so_.fl;
@@ -2084,7 +2090,7 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
             }
             if (tid == 0) {
                 gst[0] = st.ss; gst[1] = st.pri; gst[2] = st.sigma2; gst[3] = st.cov_n; gst[4] = st.wcnt; gst[5] = st.r_diag ? 1.0 : 0.0;
-                gst[6] = s_s2.sum; gst[7] = s_s2.sq_sum; gst[8] = 0.0; gst[9] = s_s2.cnt;
+                gst[6] = s_s2.sum; gst[7] = s_s2.sq_sum; gst[8] = 0.0; gst[9] = s_s2.cnt; gst[10] = st.rden; gst[11] = st.rsig;
                 long long *gc = reinterpret_cast<long long *>(gst + 16);
                 gc[0] = st.n_ss; gc[1] = st.n_acc1; gc[2] = st.n_acc2; gc[3] = st.n_oob; gc[4] = st.n_adapt; gc[5] = st.n_cholfail;
                 gc[6] = st.n_dr; gc[7] = st.n_spec; gc[8] = st.rej;
