@@ -17,6 +17,22 @@
 #include <cuda_runtime.h>
 #include "../../include/tcmcmc.h"
 
+// The construct as the kernels see it: the caller's definition + what depends on it alone — the slope f / (e - s) of the ramp
+// of every loop set, computed once on the host (an IEEE quotient, i.e. the very value the device's own division would give).
+struct ConsX : tc_construct {
+    double sc1[TC_MAX_SETS], sc2[TC_MAX_SETS];
+};
+inline ConsX make_consx(const tc_construct &c)
+{
+    ConsX x{};
+    static_cast<tc_construct &>(x) = c;
+    for (int s = 0; s < TC_MAX_SETS; ++s) {
+        x.sc1[s] = s < c.nsets ? (c.ms2_loopn[s] * (1.0 / 24.0)) / (c.ms2_end[s] - c.ms2_start[s]) : 0.0;
+        x.sc2[s] = s < c.nsets ? (c.pp7_loopn[s] * (1.0 / 24.0)) / (c.pp7_end[s] - c.pp7_start[s]) : 0.0;
+    }
+    return x;
+}
+
 namespace tc {
 #ifdef TC_SS_PROFILE
 __device__ long long tc_ss_prof[8];
@@ -141,6 +157,17 @@ __device__ __noinline__ double tc_log(double x) { return log(x); }
 __device__ __noinline__ void tc_exp3(double x0, double x1, double x2, double &e0, double &e1, double &e2)
 {
     e0 = exp(x0); e1 = exp(x1); e2 = exp(x2);
+}
+
+// 1 / d to within an ulp or two: MUFU.RCP64H seed + two Newton steps (the IEEE quotient is ~25 dependent instructions with a
+// slow-path branch; where this is used a product with the reciprocal replaces a quotient anyway)
+__device__ __forceinline__ double tc_rcp(double d)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    r = fma(fma(-d, r, 1.0), r, r);
+    r = fma(fma(-d, r, 1.0), r, r);
+    return r;
 }
 
 // ------------------------------------------------------------------------------- reductions
@@ -540,7 +567,7 @@ __device__ __noinline__ void rows_pairs(Cell cv, Work w, int s, double v, double
 // When out1/out2 != nullptr the model curves [A*MS2, PP7] on the model grid are also written there
 // (tc_forward).  All 32 lanes must call this.
 template <class Cell, class Vec>
-__device__ __noinline__ double ss_eval(const tc_construct &C, Cell cv, Vec th, Work w, int algo, bool seq_scan,
+__device__ __noinline__ double ss_eval(const ConsX &C, Cell cv, Vec th, Work w, int algo, bool seq_scan,
                                        double *out1, double *out2)
 {
     const int N = cv.N, lane = threadIdx.x & 31;
@@ -548,7 +575,12 @@ __device__ __noinline__ double ss_eval(const tc_construct &C, Cell cv, Vec th, W
 #ifdef TC_SS_PROFILE
     long long tp__ = clock64();
 #endif
-    const double vd = v * cv.d, inv_vd = 1.0 / vd;              // started here: the division overlaps with the scan
+    // 1 / (v d) only seeds the guesses of the lag thresholds (membership is decided by the exact predicate): the hardware's
+    // approximate reciprocal (MUFU.RCP64H, ~20 bits) + one Newton step is plenty, and not the ~25 dependent instructions of a quotient
+    const double vd = v * cv.d;
+    double inv_vd;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(inv_vd) : "d"(vd));
+    inv_vd = fma(fma(-vd, inv_vd, 1.0), inv_vd, inv_vd);
     // (a) loaded-polymerase counts K and cohort sizes n
     scan_counts(cv, th, R, ton, w, seq_scan, algo != TC_ALGO_TOEPLITZ);
     __syncwarp();
@@ -573,7 +605,7 @@ __device__ __noinline__ double ss_eval(const tc_construct &C, Cell cv, Vec th, W
                 const double x = q == 0 ? (c2 ? s2 : s1) : (q == 3 ? (c2 ? L2 : L1) : (c2 ? e2 : e1));
                 thr[lane] = first_lag(v, cv.d, inv_vd, x, N, (q & 1) == 0);        // >s, >=e, >e, >=L
             }
-            const double sc1 = f1 / (e1 - s1), sc2 = f2 / (e2 - s2);      // overlaps with the lanes above
+            const double sc1 = C.sc1[s], sc2 = C.sc2[s];                 // f / (e - s), from the host
             __syncwarp();
             const int4 t1 = *reinterpret_cast<const int4 *>(thr), t2 = *reinterpret_cast<const int4 *>(thr + 4);
             const int la1 = t1.x, le1 = t1.y, lb1 = t1.z, lL1 = t1.w;

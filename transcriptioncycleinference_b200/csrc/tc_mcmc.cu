@@ -81,7 +81,7 @@ __device__ long long tc_subprof[32];
 // --------------------------------------------------------------------------------- SS / forward
 struct SsArgs {
     CellsDev cells;
-    tc_construct cons;
+    ConsX cons;
     long long nbatch;
     const int *cell_id;
     const double *theta;
@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(SS_THREADS, 2) ss_stream_kernel(const __grid_c
 // ------------------------------------------------------------------------------------- sampler
 struct RunArgs {
     CellsDev cells;
-    tc_construct cons;
+    ConsX cons;
     // options
     int nsimu, burnintime, adaptint, ntry, updatesigma, burnin_cumulative, n_burn, store_chain, replay,
         algo, qcovadj_always;
@@ -911,7 +911,9 @@ __device__ __noinline__ void flush_run(const RunArgs &a, const ChainCtx &cx, int
     if (tid < 0) return;
     const int m_c = r1 - r0, rs = max(r0, cx.first_row), m_w = r1 - rs;
     const bool cov = a.do_cov && m_c > 0;
-    const double nn = wcnt + m_w, f1 = m_w > 0 ? m_w / nn : 0.0, f2 = m_w > 0 ? wcnt * m_w / nn : 0.0;
+    // Welford weights m_w / nn and wcnt m_w / nn through ONE reciprocal (every thread computes them: two quotients were ~300
+    // cycles at the head of every accept)
+    const double nn = wcnt + m_w, rnn = m_w > 0 ? tc_rcp(nn) : 0.0, f1 = m_w * rnn, f2 = wcnt * m_w * rnn;
     double *grow = cov ? cx.gRows + (size_t)ndist * cx.ld : nullptr;
     const int ox = cx.o_x, owm = cx.o_wmean, ow2 = cx.o_wM2, omb = cx.o_mb;
 #pragma unroll 1
@@ -1126,16 +1128,6 @@ __device__ __noinline__ void gen_increments_tma(const ChainCtx &cx, int g0, int 
 #ifndef TC_NOLOAD
 #define TC_NOLOAD 0        // development switch: 1 = skip the loads of R (isolates the MMA loop in scripts/subprof.py)
 #endif
-// 1 / d to within an ulp or two: MUFU.RCP64H seed + two Newton steps (the IEEE quotient is ~25 dependent instructions with a
-// slow-path branch; where this is used a product with the reciprocal replaces a quotient anyway)
-__device__ __forceinline__ double tc_rcp(double d)
-{
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
-    r = fma(fma(-d, r, 1.0), r, r);
-    r = fma(fma(-d, r, 1.0), r, r);
-    return r;
-}
 __device__ __forceinline__ void warp_sum2(double &p, double &q)
 {
 #pragma unroll
@@ -2439,7 +2431,7 @@ static int launch_ss(const tc_cells *c, const DevCells *dc, long long nbatch, co
     if (ld < 7 + c->Nmax) return fail(TC_EINVAL, "ld < 7 + max(N)");
     if (nbatch <= 0) return TC_OK;
     SsArgs a{};
-    a.cells = dc->d; a.cons = c->cons; a.nbatch = nbatch; a.cell_id = d_cell; a.theta = d_theta; a.ld = ld;
+    a.cells = dc->d; a.cons = make_consx(c->cons); a.nbatch = nbatch; a.cell_id = d_cell; a.theta = d_theta; a.ld = ld;
     a.algo = algo; a.raw_grid = raw; a.ldo = ldo; a.ss_out = d_ss; a.out1 = d_o1; a.out2 = d_o2;
     a.wsz = (work_doubles(c->Nmax) + 3) & ~1;
     int sms = 0;
@@ -2679,7 +2671,7 @@ int tc_mcmc_run(const tc_cells *c, const tc_mcmc_opts *o, int nchains, const int
         CUDA_TRY(cudaEventCreate(&r.e0));
         CUDA_TRY(cudaEventCreate(&r.e1));
         RunArgs &a = r.a;
-        a.cells = find_dev(c, r.device)->d; a.cons = c->cons;
+        a.cells = find_dev(c, r.device)->d; a.cons = make_consx(c->cons);
         a.nsimu = o->nsimu; a.burnintime = o->burnintime; a.adaptint = o->adaptint; a.ntry = o->ntry;
         a.updatesigma = o->updatesigma; a.burnin_cumulative = o->burnin_cumulative; a.n_burn = o->n_burn;
         a.store_chain = o->store_chain; a.replay = o->replay; a.algo = o->algo; a.qcovadj_always = o->qcovadj_always;
