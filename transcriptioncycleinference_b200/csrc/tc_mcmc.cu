@@ -2126,17 +2126,18 @@ __global__ void __launch_bounds__(DRAM_THREADS, 2) dram_kernel(const __grid_cons
 
 // delayed-rejection decision from values (the chain-per-warp kernel keeps the step's scalars in L2)
 __device__ __noinline__ int resolve_dr_v(double q1, double u2, bool o1, double x12, double pr1, double pr2, double ss1, double ss2,
-                                         double ss, double pri, double s2p)
+                                         double ss, double pri, double is2p)            // is2p = 1 / sigma2 of the step
 {
+    // the arithmetic of resolve_dr(), from values
     double e12, e32, e13;
-    tc_exp3(x12, -0.5 * ((ss1 - ss2) / s2p + pr1 - pr2), -0.5 * ((ss2 - ss) / s2p + pr2 - pri) + q1, e12, e32, e13);
+    tc_exp3(x12, -0.5 * ((ss1 - ss2) * is2p + pr1 - pr2), -0.5 * ((ss2 - ss) * is2p + pr2 - pri) + q1, e12, e32, e13);
     const double a12 = o1 ? 0.0 : e12;
     double a32 = e32;
     a32 = a32 > 1.0 ? 1.0 : a32;
     if (!(a32 >= 0.0)) a32 = 0.0;
-    double a13 = e13 * (1.0 - a32) / (1.0 - a12);
-    a13 = a13 > 1.0 ? 1.0 : a13;
-    return ((a13 >= 1.0) || (a13 > u2)) ? 1 : 0;
+    const double num = e13 * (1.0 - a32), den = 1.0 - a12;
+    if (!(den > 0.0)) return num > 0.0 ? 1 : 0;
+    return (num >= den || num > u2 * den) ? 1 : 0;
 }
 
 #include "tc_warp.cuh"

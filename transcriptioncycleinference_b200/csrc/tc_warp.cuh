@@ -412,7 +412,7 @@ __device__ __noinline__ void wk_flush(const RunArgs &a, const WkCtx &c, int ox, 
     const int lane = threadIdx.x & 31, npar = c.npar;
     const int m_c = r1 - r0, rs = max(r0, c.first_row), m_w = r1 - rs;
     const bool cov = a.do_cov && m_c > 0;
-    const double nn = wcnt + m_w, f1 = m_w > 0 ? m_w / nn : 0.0, f2 = m_w > 0 ? wcnt * m_w / nn : 0.0;
+    const double nn = wcnt + m_w, rnn = m_w > 0 ? tc_rcp(nn) : 0.0, f1 = m_w * rnn, f2 = wcnt * m_w * rnn;     // as flush_run()
     double *grow = cov ? c.gRows + (size_t)ndist * c.ld : nullptr;
 #pragma unroll 1
     for (int i = lane; i < npar; i += 32) {
@@ -748,7 +748,9 @@ __global__ void __launch_bounds__(WK_THREADS, 1) dram_warp_kernel(const __grid_c
         SmemCell cv{};
         Work w{};
         int ox = o_reg + 1, ob = o_reg + 1 + ldp;
-        double ss = 0.0, pri = 0.0, sig2 = a.sigma2_0;
+        // is2 = 1 / sigma2 as the next step sees it, kept as the product chi2 * rden, rden = 1 / (N0 S20 + ss): the expression
+        // dram_kernel uses at every position of a round, so the two kernels decide every step on the same bits
+        double ss = 0.0, pri = 0.0, sig2 = a.sigma2_0, is2 = 1.0 / a.sigma2_0, rden = 0.0;
         int r_diag = 1, run_r0 = 0, ndist = 0;
         bool bad0 = false, uni = false;
         if (valid) {
@@ -822,7 +824,7 @@ __global__ void __launch_bounds__(WK_THREADS, 1) dram_warp_kernel(const __grid_c
             } else {
 #pragma unroll 1
                 for (int i = lane; i < npar; i += 32) tc_smem[ox + i] = __ldcg(gst + ST_VEC0 + i);
-                ss = __ldcg(gst + 0); pri = __ldcg(gst + 1); sig2 = __ldcg(gst + 2);
+                ss = __ldcg(gst + 0); pri = __ldcg(gst + 1); sig2 = __ldcg(gst + 2); is2 = __ldcg(gst + 11);
                 r_diag = __ldcg(gst + 5) != 0.0;
                 bad0 = __ldcg(gst + 8) != 0.0;                          // ss(x0) was not finite: reported at slice 0, nothing left to do
                 run_r0 = seg * a.seglen;
@@ -864,6 +866,7 @@ __global__ void __launch_bounds__(WK_THREADS, 1) dram_warp_kernel(const __grid_c
 #define WK_PHASE(i) do { if (lane == 0) { const long long tn__ = clock64(); st.pc[i] += tn__ - st.tprev; st.tprev = tn__; } } while (0)
 
         int k = seg == 0 ? 1 : seg * a.seglen;
+        rden = tc_rcp(n0s20 + ss);                                  // (a function of ss alone: recomputed, not parked)
         int next_adapt = a.adaptint > 0 ? ((k + a.adaptint) / a.adaptint) * a.adaptint : 0x7fffffff;
 #ifdef WK_BAR_EVERY
         int wk_batch = 0;
@@ -902,7 +905,7 @@ __global__ void __launch_bounds__(WK_THREADS, 1) dram_warp_kernel(const __grid_c
                     ss1 = ss_eval(a.cons, cv, SmemVecA{ob}, w, a.algo, false, nullptr, nullptr);
                     WK_T1(7);
                     nev = 1;
-                    x12 = -0.5 * ((ss1 - ss) / sig2 + pr1 - pri);
+                    x12 = -0.5 * ((ss1 - ss) * is2 + pr1 - pri);
                     if (x12 >= 0.0 || x12 > s_logu) acc = 1;
                 }
                 double ssn = ss1, prin = pr1;
@@ -917,7 +920,7 @@ __global__ void __launch_bounds__(WK_THREADS, 1) dram_warp_kernel(const __grid_c
                         const double ss2 = ss_eval(a.cons, cv, SmemVecA{ob}, w, a.algo, false, nullptr, nullptr);
                         WK_T1(7);
                         ++nev;
-                        if (resolve_dr_v(-0.5 * (s_n1 - s_n0), s_u2, o1, x12, pr1, pr2, ss1, ss2, ss, pri, sig2)) { acc = 2; fl |= TC_FL_STAGE2; ssn = ss2; prin = pr2; }
+                        if (resolve_dr_v(-0.5 * (s_n1 - s_n0), s_u2, o1, x12, pr1, pr2, ss1, ss2, ss, pri, is2)) { acc = 2; fl |= TC_FL_STAGE2; ssn = ss2; prin = pr2; }
                     }
                 }
                 // ---- commit
@@ -930,8 +933,9 @@ __global__ void __launch_bounds__(WK_THREADS, 1) dram_warp_kernel(const __grid_c
                     run_r0 = k;
                     const int t_ = ox; ox = ob; ob = t_;                 // the proposal becomes the state
                     ss = ssn; pri = prin;
+                    rden = tc_rcp(n0s20 + ss);
                 }
-                const double s2 = a.updatesigma ? (n0s20 + ss) / s_chi : sig2;
+                const double s2 = a.updatesigma ? (n0s20 + ss) * tc_rcp(s_chi) : sig2;
                 if (lane == 0) {
                     st.s2sum += s2; st.s2sq += sqrt(s2); st.s2cnt += 1.0;
                     st.n_ss += nev; st.n_oob += noob; if (fl & TC_FL_DR) ++st.n_dr;
@@ -940,7 +944,7 @@ __global__ void __launch_bounds__(WK_THREADS, 1) dram_warp_kernel(const __grid_c
                     if (a.flags) a.flags[(size_t)ch * a.nsimu + k] = fl;
                     if (a.sschain) a.sschain[(size_t)ch * a.nsimu + k] = ss;
                 }
-                if (a.updatesigma) sig2 = s2;
+                if (a.updatesigma) { sig2 = s2; is2 = s_chi * rden; }
                 __syncwarp();
             }
             k = gen_upto;
@@ -987,7 +991,7 @@ __global__ void __launch_bounds__(WK_THREADS, 1) dram_warp_kernel(const __grid_c
             for (int i = lane; i < npar; i += 32) __stcg(gst + ST_VEC0 + i, tc_smem[ox + i]);
             if (lane == 0) {
                 gst[0] = ss; gst[1] = pri; gst[2] = sig2; gst[3] = st.cov_n; gst[4] = st.wcnt; gst[5] = r_diag ? 1.0 : 0.0;
-                gst[6] = st.s2sum; gst[7] = st.s2sq; gst[8] = 0.0; gst[9] = st.s2cnt;
+                gst[6] = st.s2sum; gst[7] = st.s2sq; gst[8] = 0.0; gst[9] = st.s2cnt; gst[11] = is2;
                 long long *gc = reinterpret_cast<long long *>(gst + 16);
                 gc[0] = st.n_ss; gc[1] = st.n_acc1; gc[2] = st.n_acc2; gc[3] = st.n_oob; gc[4] = st.n_adapt; gc[5] = st.n_cholfail;
                 gc[6] = st.n_dr; gc[7] = st.reju; gc[8] = st.rej;
